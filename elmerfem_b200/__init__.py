@@ -1,0 +1,297 @@
+"""elmerfem_b200 -- B200-native (sm_100a) sparse iterative linear-solve path for Elmer.
+
+The product is the C-ABI shared library ``libelmer_b200.so`` (sources in ``csrc/``, interface in
+``include/elmer_b200.h``).  This package is only the ctypes binding the tests and bench.py use to call
+that ABI the way Elmer's Fortran would (all scalars by reference, raw 1-based CRS arrays).
+
+There is no CPU path: importing works without a GPU (so that symbol/ABI checks can run), but every
+compute entry point fails loudly when no CUDA device is present or the library is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libelmer_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "elmer_b200.h")
+
+METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5}
+PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2}
+DECLINED = 100
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into libelmer_b200.so (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error("libelmer_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                        "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vpp = C.POINTER(C.c_void_p)
+    ip = C.POINTER(C.c_int)
+    dp = C.POINTER(C.c_double)
+    L.b200_last_error.restype = C.c_char_p
+    sigs = {
+        "b200_create": [vpp], "b200_destroy": [vpp], "b200_device_count": [ip], "b200_set_device": [vpp, ip],
+        "b200_set_structure": [vpp, ip, ip, ip, ip, ip, ip, ip],
+        "b200_set_values": [vpp, dp, dp], "b200_set_values_device": [vpp, C.c_void_p, C.c_void_p],
+        "b200_factorize": [vpp],
+        "b200_solve": [vpp, dp, dp, ip, dp, ip, ip, dp],
+        "b200_solve_device": [vpp, C.c_void_p, C.c_void_p, ip, dp, ip, ip, C.c_void_p],
+        "b200_itersolver": [vpp, dp, dp, C.c_char_p, ip, ip],
+        "b200_matvec": [vpp, dp, dp], "b200_diag_precondition": [vpp, dp, dp], "b200_lu_precondition": [vpp, dp, dp],
+        "b200_dot": [vpp, ip, dp, dp, dp], "b200_nrm2": [vpp, ip, dp, dp],
+        "b200_get_ilu_values": [vpp, dp], "b200_get_structure": [vpp, ip, ip, ip], "b200_get_levels": [vpp, ip, ip],
+        "b200_comm_unique_id": [C.c_char_p], "b200_comm_init": [vpp, ip, ip, C.c_char_p],
+        "b200_set_partition": [vpp, ip, ip, ip, ip, ip, ip, ip, ip],
+        "b200_get_halo_plan": [vpp, ip, ip, ip, ip, ip, ip],
+        "b200_get_stats": [vpp, dp], "b200_time_matvec": [vpp, ip, dp], "b200_time_lu_precondition": [vpp, ip, dp],
+        "b200_version": [ip, ip],
+    }
+    for name, args in sigs.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = C.c_int
+    L.b200_spmv.argtypes = [vpp, ip, ip, ip, dp, dp, dp, ip]
+    L.b200_spmv.restype = None
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH]).decode()
+    return sorted(line.split()[-1] for line in out.splitlines() if " T " in line)
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(v):
+    return C.byref(C.c_int(int(v)))
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise B200Error("%s failed: %s" % (what, lib().b200_last_error().decode()))
+
+
+def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residual_output=0,
+                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1):
+    """HUTI ipar(50)/dpar(10) exactly as IterSolver fills them (fem/src/IterSolve.F90:245-503;
+    slots fhutiter/src/huti_fdefs.h:101-155)."""
+    ipar = np.zeros(50, dtype=np.int32)
+    dpar = np.zeros(10, dtype=np.float64)
+    ipar[2] = n
+    ipar[3] = {"cg": 4, "bicgstab": 8}.get(method, 1)
+    ipar[4] = residual_output
+    ipar[9] = maxit
+    ipar[10] = minit
+    ipar[11] = stopc
+    ipar[13] = 1
+    if method == "bicgstabl":
+        ipar[15] = max(2, bicgstabl_l)
+    if method == "gcr":
+        ipar[16] = gcr_restart if gcr_restart is not None else min(maxit, 200)
+    if method == "idrs":
+        ipar[17] = idrs_s
+    ipar[27] = 1 if smoothing else 0
+    dpar[0] = tol
+    dpar[1] = maxtol
+    return ipar, dpar
+
+
+class Matrix:
+    """One Elmer Matrix_t on the device: owns the opaque handle slot (Matrix_t%SpMV-style)."""
+
+    def __init__(self):
+        self._h = C.c_void_p(None)
+        _check(lib().b200_create(C.byref(self._h)), "b200_create")
+        self.n = 0
+        self.nnz = 0
+
+    def close(self):
+        if self._h:
+            lib().b200_destroy(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return C.byref(self._h)
+
+    def set_structure(self, rows, cols, diag, index_base=1, ndeg=1):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        diag = np.ascontiguousarray(diag, dtype=np.int32)
+        self.n, self.nnz = rows.size - 1, cols.size
+        _check(lib().b200_set_structure(self.handle, _i(self.n), _i(self.nnz), _ip(rows), _ip(cols), _ip(diag),
+                                        _i(index_base), _i(ndeg)), "b200_set_structure")
+
+    def set_values(self, vals, prec_vals=None):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        pv = None if prec_vals is None else np.ascontiguousarray(prec_vals, dtype=np.float64)
+        _check(lib().b200_set_values(self.handle, _dp(vals), _dp(pv)), "b200_set_values")
+
+    def set_values_device(self, d_vals_ptr, d_prec_ptr=None):
+        _check(lib().b200_set_values_device(self.handle, C.c_void_p(d_vals_ptr), C.c_void_p(d_prec_ptr)), "b200_set_values_device")
+
+    def factorize(self):
+        _check(lib().b200_factorize(self.handle), "b200_factorize")
+
+    def solve(self, b, x0=None, method="bicgstab", precond="none", P=None, **kw):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(self.n) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        ipar, dpar = fill_ipar_dpar(self.n, method, **kw)
+        Pp = None if P is None else np.asfortranarray(P, dtype=np.float64)
+        rc = lib().b200_solve(self.handle, _dp(b), _dp(x), _ip(ipar), _dp(dpar), _i(METHODS[method]), _i(PRECONDS[precond]), _dp(Pp))
+        _check(rc, "b200_solve")
+        return dict(x=x, info=int(ipar[29]), iters=int(ipar[30]), residual=float(dpar[9]), ipar=ipar, dpar=dpar, stats=self.stats())
+
+    def solve_device(self, d_b_ptr, d_x_ptr, method="bicgstab", precond="none", d_P_ptr=None, **kw):
+        ipar, dpar = fill_ipar_dpar(self.n, method, **kw)
+        rc = lib().b200_solve_device(self.handle, C.c_void_p(d_b_ptr), C.c_void_p(d_x_ptr), _ip(ipar), _dp(dpar),
+                                     _i(METHODS[method]), _i(PRECONDS[precond]), C.c_void_p(d_P_ptr))
+        _check(rc, "b200_solve_device")
+        return dict(info=int(ipar[29]), iters=int(ipar[30]), residual=float(dpar[9]), stats=self.stats())
+
+    def itersolver(self, b, x0, sif, solve_count=0):
+        """IterSolver(A,x,b,Solver) through the keyword front-end; returns None when DECLINED."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(self.n) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        sc = C.c_int(solve_count)
+        info = (C.c_int * 2)(0, 0)
+        rc = lib().b200_itersolver(self.handle, _dp(b), _dp(x), sif.encode(), C.byref(sc), info)
+        if rc == DECLINED:
+            return None
+        _check(rc, "b200_itersolver")
+        return dict(x=x, info=int(info[0]), iters=int(info[1]), solve_count=sc.value, stats=self.stats())
+
+    def matvec(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.empty(self.n)
+        _check(lib().b200_matvec(self.handle, _dp(u), _dp(v)), "b200_matvec")
+        return v
+
+    def diag_precondition(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        u = np.empty(self.n)
+        _check(lib().b200_diag_precondition(self.handle, _dp(u), _dp(v)), "b200_diag_precondition")
+        return u
+
+    def lu_precondition(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        u = np.empty(self.n)
+        _check(lib().b200_lu_precondition(self.handle, _dp(u), _dp(v)), "b200_lu_precondition")
+        return u
+
+    def dot(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        r = C.c_double(0)
+        _check(lib().b200_dot(self.handle, _i(x.size), _dp(x), _dp(y), C.byref(r)), "b200_dot")
+        return r.value
+
+    def nrm2(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = C.c_double(0)
+        _check(lib().b200_nrm2(self.handle, _i(x.size), _dp(x), C.byref(r)), "b200_nrm2")
+        return r.value
+
+    def ilu_values(self):
+        out = np.empty(self.nnz)
+        _check(lib().b200_get_ilu_values(self.handle, _dp(out)), "b200_get_ilu_values")
+        return out
+
+    def structure(self):
+        rows = np.empty(self.n + 1, dtype=np.int32)
+        cols = np.empty(self.nnz, dtype=np.int32)
+        diag = np.empty(self.n, dtype=np.int32)
+        _check(lib().b200_get_structure(self.handle, _ip(rows), _ip(cols), _ip(diag)), "b200_get_structure")
+        return rows, cols, diag
+
+    def levels(self, per_row=False):
+        counts = np.zeros(4, dtype=np.int32)
+        lev = np.empty(self.n, dtype=np.int32) if per_row else None
+        _check(lib().b200_get_levels(self.handle, _ip(counts), None if lev is None else _ip(lev)), "b200_get_levels")
+        return dict(forward=int(counts[0]), backward=int(counts[1]), slices_f=int(counts[2]), slices_b=int(counts[3]), level=lev)
+
+    def stats(self):
+        s = np.zeros(16)
+        _check(lib().b200_get_stats(self.handle, _dp(s)), "b200_get_stats")
+        return dict(solve_ms=s[0], matvec=int(s[1]), pcond=int(s[2]), factor_ms=s[3], launches=int(s[4]), h2d=int(s[5]),
+                    d2h=int(s[6]), iters=int(s[7]), spmv_ms=s[8], lu_ms=s[9], residual=s[10], sell_entries=int(s[11]),
+                    levels_f=int(s[12]), levels_b=int(s[13]))
+
+    def time_matvec(self, reps=20):
+        ms = C.c_double(0)
+        _check(lib().b200_time_matvec(self.handle, _i(reps), C.byref(ms)), "b200_time_matvec")
+        return ms.value
+
+    def time_lu(self, reps=10):
+        ms = C.c_double(0)
+        _check(lib().b200_time_lu_precondition(self.handle, _i(reps), C.byref(ms)), "b200_time_lu_precondition")
+        return ms.value
+
+    # ---- multi-GPU -------------------------------------------------------------------------
+    def comm_init(self, nranks, rank, unique_id):
+        _check(lib().b200_comm_init(self.handle, _i(nranks), _i(rank), unique_id), "b200_comm_init")
+
+    def set_partition(self, gn, rows, cols_global, goffset, index_base=1, ndeg=1):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols_global, dtype=np.int32)
+        goffset = np.ascontiguousarray(goffset, dtype=np.int32)
+        self.n = rows.size - 1
+        self.nnz = cols.size
+        _check(lib().b200_set_partition(self.handle, _i(gn), _i(self.n), _i(cols.size), _ip(rows), _ip(cols), _ip(goffset),
+                                        _i(index_base), _i(ndeg)), "b200_set_partition")
+
+    def halo_plan(self):
+        sizes = np.zeros(3, dtype=np.int32)
+        _check(lib().b200_get_halo_plan(self.handle, _ip(sizes), None, None, None, None, None), "b200_get_halo_plan")
+        nn, ns, ng = [int(v) for v in sizes]
+        neigh = np.zeros(max(nn, 1), dtype=np.int32)
+        sp = np.zeros(nn + 1, dtype=np.int32)
+        si = np.zeros(max(ns, 1), dtype=np.int32)
+        rp = np.zeros(nn + 1, dtype=np.int32)
+        gg = np.zeros(max(ng, 1), dtype=np.int32)
+        _check(lib().b200_get_halo_plan(self.handle, _ip(sizes), _ip(neigh), _ip(sp), _ip(si), _ip(rp), _ip(gg)), "b200_get_halo_plan")
+        return dict(neigh=neigh[:nn], send_ptr=sp, send_idx=si[:ns], recv_ptr=rp, ghost_gid=gg[:ng])
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().b200_comm_unique_id(buf), "b200_comm_unique_id")
+    return buf.raw
+
+
+def spmv_hook(slot, rows, cols, vals, u, reinit=0):
+    """Calls b200_spmv exactly as Elmer's matvecsubrext_c does (fem/src/Load.c:806-824)."""
+    n = rows.size - 1
+    v = np.empty(n)
+    lib().b200_spmv(C.byref(slot), _i(n), _ip(rows), _ip(cols), _dp(vals), _dp(u), _dp(v), _i(reinit))
+    return v

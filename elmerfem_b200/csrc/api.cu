@@ -1,0 +1,467 @@
+// C ABI of the library (include/elmer_b200.h).  Thin: argument checks, host<->device staging and
+// exception -> return-code translation.  All numerical work is in the kernel translation units.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "krylov.h"
+#include "../../include/elmer_b200.h"
+#include <algorithm>
+#include <mutex>
+
+namespace b200 {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &s) { g_last_error = s; }
+
+static Handle &H(void **handle) {
+  B200_REQUIRE(handle && *handle, "null handle (call b200_create first)");
+  Handle &h = *static_cast<Handle *>(*handle);
+  B200_CUDA(cudaSetDevice(h.device));
+  return h;
+}
+
+template <class F> static int guarded(F f) {
+  try { f(); return 0; }
+  catch (const std::exception &e) {
+    g_last_error = e.what();
+    fprintf(stderr, "[elmer_b200] %s\n", e.what());
+    return 1;
+  }
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static void ensure_runtime(Handle &h) {
+  if (h.stream) return;
+  B200_CUDA(cudaSetDevice(h.device));
+  B200_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&h.stream2, cudaStreamNonBlocking));
+  cudaEvent_t *evs[] = {&h.ev0, &h.ev1, &h.ev2, &h.ev_end, &h.evf0, &h.evf1};
+  for (auto e : evs) B200_CUDA(cudaEventCreate(e));
+  h.red_partials.ensure((size_t)NRED * MAX_RED_BLOCKS);
+  h.red_counters.ensure(8);
+  B200_CUDA(cudaMemset(h.red_counters.p, 0, 8 * sizeof(unsigned int)));
+  h.scal.ensure(NSCAL);
+  B200_CUDA(cudaMemset(h.scal.p, 0, NSCAL * sizeof(double)));
+  h.ctrl.ensure(1);
+  B200_CUDA(cudaMemset(h.ctrl.p, 0, sizeof(Ctrl)));
+  B200_CUDA(cudaMallocHost((void **)&h.h_pinned, NSCAL * sizeof(double)));
+  B200_CUDA(cudaMallocHost((void **)&h.h_ctrl, 2 * sizeof(Ctrl)));
+  memset(h.h_ctrl, 0, 2 * sizeof(Ctrl));
+  h.spmv_blocks = env_int("B200_SPMV_BLOCKS", 0);
+  h.tri_blocks_per_sm = env_int("B200_TRI_BLOCKS_PER_SM", 0);
+  h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 4));
+  h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", 100);
+  h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
+  h.blas_blocks = env_int("B200_BLAS_BLOCKS", NUM_SMS * 8);
+  if (h.blas_blocks > MAX_RED_BLOCKS) h.blas_blocks = MAX_RED_BLOCKS;
+}
+
+static void reset_ctrl(Handle &h) {
+  B200_CUDA(cudaMemsetAsync(h.ctrl.p, 0, sizeof(Ctrl), h.stream));
+}
+
+__global__ void k_sub_base(long long n, const int *__restrict__ in, int *__restrict__ out, int base) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = in[i] - base;
+}
+__global__ void k_extract_diag(int n, const int *__restrict__ diag, const double *__restrict__ vals, double *__restrict__ dvals) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dvals[i] = vals[diag[i]];
+}
+
+// Installs a 0-based CRS structure given on the host.  Validates what the kernels rely on.
+void install_structure(Handle &h, int n, long long nnz, std::vector<int> &&rows0, std::vector<int> &&cols0, std::vector<int> &&diag0, int ndeg) {
+  ensure_runtime(h);
+  B200_REQUIRE(n >= 0 && nnz >= 0, "negative sizes");
+  B200_REQUIRE((long long)rows0.size() == (long long)n + 1 && (long long)cols0.size() == nnz && (long long)diag0.size() == n, "array sizes");
+  B200_REQUIRE(n == 0 || (rows0[0] == 0 && rows0[n] == nnz), "Rows(1) / Rows(n+1) inconsistent with nnz");
+  bool ok = true; const char *why = "";
+#pragma omp parallel for
+  for (int i = 0; i < n; ++i) {
+    int s = rows0[i], e = rows0[i + 1];
+    if (e < s || s < 0 || e > nnz) { ok = false; why = "Rows not monotone"; continue; }
+    for (int p = s; p < e; ++p) {
+      if (cols0[p] < 0 || cols0[p] >= n) { ok = false; why = "column index out of range"; }
+      if (p > s && cols0[p] <= cols0[p - 1]) { ok = false; why = "columns not sorted ascending within a row (CRS_SortMatrix expected)"; }
+    }
+    int d = diag0[i];
+    if (d < s || d >= e || cols0[d] != i) { ok = false; why = "Diag(i) does not point at the diagonal entry"; }
+  }
+  B200_REQUIRE(ok, why);
+  int nacc = 1;
+  if (ndeg == 2) nacc = 2; else if (ndeg == 3 || ndeg == 6) nacc = 3; else if (ndeg == 4 || ndeg == 8) nacc = 4; else if (ndeg == 5 || ndeg == 10) nacc = 5;
+  if (nacc > 1) for (int i = 0; i < n; ++i) if ((rows0[i + 1] - rows0[i]) % nacc) { nacc = 1; break; }
+  h.n = n; h.nnz = nnz; h.ndeg = ndeg; h.nacc = nacc;
+  h.h_rows = std::move(rows0); h.h_cols = std::move(cols0); h.h_diag = std::move(diag0);
+  h.d_rows.ensure((size_t)n + 1); h.d_cols.ensure(nnz); h.d_diag.ensure(n);
+  B200_CUDA(cudaMemcpyAsync(h.d_rows.p, h.h_rows.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (nnz) B200_CUDA(cudaMemcpyAsync(h.d_cols.p, h.h_cols.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (n) B200_CUDA(cudaMemcpyAsync(h.d_diag.p, h.h_diag.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  B200_CUDA(cudaStreamSynchronize(h.stream));
+  h.have_vals = h.have_prec = h.ilu_valid = h.ilu_exists = false; h.tri_ready = false;
+  h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0;
+  structure_build(h);
+  B200_CUDA(cudaStreamSynchronize(h.stream));
+}
+
+// values already on the device in h.d_vals (and h.d_prec): refresh derived data
+void values_changed(Handle &h) {
+  sell_refresh_values(h, h.A, h.d_vals.p);
+  h.d_dvals.ensure(h.n);
+  if (h.n) k_extract_diag<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.n, h.d_diag.p, h.d_vals.p, h.d_dvals.p);
+  B200_CUDA(cudaGetLastError());
+  h.have_vals = true; h.ilu_valid = false;
+}
+
+static void upload(Handle &h, double *dst, const double *src, size_t n) {
+  if (!n) return;
+  B200_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h.stream));
+  h.st_h2d += n * sizeof(double);
+}
+static void download(Handle &h, double *dst, const double *src, size_t n) {
+  if (!n) return;
+  B200_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+  h.st_d2h += n * sizeof(double);
+}
+
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char *b200_last_error(void) { return g_last_error.c_str(); }
+int b200_version(int *major, int *minor) { if (major) *major = 0; if (minor) *minor = 1; return 0; }
+
+int b200_device_count(int *count) {
+  return guarded([&] { B200_CUDA(cudaGetDeviceCount(count)); B200_REQUIRE(*count > 0, "no CUDA device visible"); });
+}
+
+int b200_create(void **handle) {
+  return guarded([&] {
+    B200_REQUIRE(handle, "null handle slot");
+    int count = 0;
+    B200_CUDA(cudaGetDeviceCount(&count));
+    B200_REQUIRE(count > 0, "no CUDA device visible: this library has no CPU path");
+    Handle *h = new Handle();
+    h->device = env_int("LOCAL_RANK", 0) % count;          // one GPU per rank, cf. amgx.c:161-163
+    *handle = h;
+    ensure_runtime(*h);
+  });
+}
+
+int b200_set_device(void **handle, const int *device) {
+  return guarded([&] {
+    B200_REQUIRE(handle && *handle, "null handle");
+    Handle &h = *static_cast<Handle *>(*handle);
+    B200_REQUIRE(h.n == 0 && !h.have_vals, "b200_set_device must precede b200_set_structure");
+    int count = 0; B200_CUDA(cudaGetDeviceCount(&count));
+    B200_REQUIRE(*device >= 0 && *device < count, "device out of range");
+    if (h.device != *device) B200_REQUIRE(false, "handle already bound to another device; destroy and recreate with LOCAL_RANK set");
+  });
+}
+
+int b200_destroy(void **handle) {
+  return guarded([&] {
+    if (!handle || !*handle) return;
+    Handle *h = static_cast<Handle *>(*handle);
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    halo_release(*h);
+    h->d_rows_in.release(); h->d_cols_in.release(); h->d_diag_in.release();
+    h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
+    h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
+    h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
+    for (auto &w : h->work) w.release();
+    h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
+    h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    cudaEvent_t evs[] = {h->ev0, h->ev1, h->ev2, h->ev_end, h->evf0, h->evf1};
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    delete h;
+    *handle = nullptr;
+  });
+}
+
+int b200_set_structure(void **handle, const int *n, const int *nnz, const int *rows, const int *cols,
+                       const int *diag, const int *index_base, const int *ndeg) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(n && nnz && rows && index_base, "null argument");
+    const int N = *n, base = *index_base; const long long NNZ = *nnz;
+    B200_REQUIRE(base == 0 || base == 1, "index_base must be 0 or 1");
+    B200_REQUIRE(N == 0 || (cols && diag), "null cols/diag");
+    B200_REQUIRE(h.nranks == 1 || h.halo == nullptr, "use b200_set_partition on a partitioned handle");
+    std::vector<int> r0((size_t)N + 1), c0(NNZ), d0(N);
+    for (int i = 0; i <= N; ++i) r0[i] = rows[i] - base;
+#pragma omp parallel for
+    for (long long p = 0; p < NNZ; ++p) c0[p] = cols[p] - base;
+    for (int i = 0; i < N; ++i) d0[i] = diag[i] - base;
+    h.index_base = base;
+    install_structure(h, N, NNZ, std::move(r0), std::move(c0), std::move(d0), ndeg ? *ndeg : 1);
+  });
+}
+
+int b200_set_values(void **handle, const double *vals, const double *prec_vals) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.A.nslots > 0 || h.n == 0, "b200_set_values before b200_set_structure");
+    B200_REQUIRE(vals || h.nnz == 0, "null vals");
+    if (h.halo) {                                   // complete owned rows with global columns
+      B200_REQUIRE(!prec_vals, "PrecValues are not supported on a partitioned handle");
+      partition_set_values(h, vals, false);
+      B200_CUDA(cudaStreamSynchronize(h.stream));
+      return;
+    }
+    h.d_vals.ensure(h.nnz);
+    upload(h, h.d_vals.p, vals, h.nnz);
+    h.have_prec = prec_vals != nullptr;
+    if (prec_vals) { h.d_prec.ensure(h.nnz); upload(h, h.d_prec.p, prec_vals, h.nnz); }
+    values_changed(h);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+}
+
+int b200_set_values_device(void **handle, const double *d_vals, const double *d_prec_vals) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.A.nslots > 0 || h.n == 0, "b200_set_values_device before b200_set_structure");
+    if (h.halo) {
+      B200_REQUIRE(!d_prec_vals, "PrecValues are not supported on a partitioned handle");
+      partition_set_values(h, d_vals, true);
+      B200_CUDA(cudaStreamSynchronize(h.stream));
+      return;
+    }
+    h.d_vals.ensure(h.nnz);
+    if (h.nnz) B200_CUDA(cudaMemcpyAsync(h.d_vals.p, d_vals, (size_t)h.nnz * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+    h.have_prec = d_prec_vals != nullptr;
+    if (d_prec_vals) { h.d_prec.ensure(h.nnz); B200_CUDA(cudaMemcpyAsync(h.d_prec.p, d_prec_vals, (size_t)h.nnz * sizeof(double), cudaMemcpyDeviceToDevice, h.stream)); }
+    values_changed(h);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+}
+
+int b200_factorize(void **handle) {
+  return guarded([&] { Handle &h = H(handle); ilu0_factor(h); });
+}
+
+int b200_solve_device(void **handle, const double *d_b, double *d_x, int *ipar, double *dpar,
+                      const int *method, const int *precond, const double *d_P) {
+  int rc = guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(ipar && dpar && method && precond, "null argument");
+    h.st_h2d = 0;
+    solve_device(h, d_b, d_x, ipar, dpar, *method, *precond, d_P);
+  });
+  if (rc && ipar) ipar[29] = B200_INFO_HALTED;
+  return rc;
+}
+
+int b200_solve(void **handle, const double *b, double *x, int *ipar, double *dpar,
+               const int *method, const int *precond, const double *P) {
+  int rc = guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(ipar && dpar && method && precond, "null argument");
+    B200_REQUIRE((b && x) || h.n == 0, "null b/x");
+    const size_t nv = vec_len(h);
+    h.d_b.ensure(nv); h.d_x.ensure(nv);
+    h.st_h2d = 0;
+    upload(h, h.d_b.p, b, h.n);
+    upload(h, h.d_x.p, x, h.n);
+    const double *dP = nullptr;
+    if (*method == B200_METHOD_IDRS && P) {
+      size_t np = (size_t)h.n * (size_t)ipar[17];
+      h.d_P.ensure(np); upload(h, h.d_P.p, P, np); dP = h.d_P.p;
+    }
+    solve_device(h, h.d_b.p, h.d_x.p, ipar, dpar, *method, *precond, dP);
+    download(h, x, h.d_x.p, h.n);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+  if (rc && ipar) ipar[29] = B200_INFO_HALTED;
+  return rc;
+}
+
+// ---- callbacks on host vectors --------------------------------------------------------------
+int b200_matvec(void **handle, const double *u, double *v) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.have_vals, "b200_matvec before b200_set_values");
+    const size_t nv = vec_len(h);
+    h.d_x.ensure(nv); h.d_b.ensure(nv);
+    upload(h, h.d_x.p, u, h.n);
+    matvec_full(h, h.d_x.p, h.d_b.p);
+    download(h, v, h.d_b.p, h.n);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+}
+int b200_diag_precondition(void **handle, double *u, const double *v) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.have_vals, "b200_diag_precondition before b200_set_values");
+    h.d_x.ensure(h.n); h.d_b.ensure(h.n);
+    upload(h, h.d_x.p, v, h.n);
+    diag_apply(h, h.d_b.p, h.d_x.p);
+    download(h, u, h.d_b.p, h.n);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+}
+int b200_lu_precondition(void **handle, double *u, const double *v) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    if (!h.ilu_valid) ilu0_factor(h);
+    h.d_x.ensure(h.n); h.d_b.ensure(h.n);
+    reset_ctrl(h);
+    upload(h, h.d_x.p, v, h.n);
+    lu_apply(h, h.d_b.p, h.d_x.p);
+    download(h, u, h.d_b.p, h.n);
+    B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, h.stream));
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+    B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "triangular solve: dependency wait timed out");
+  });
+}
+int b200_dot(void **handle, const int *n, const double *x, const double *y, double *result) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    const int N = *n;
+    h.d_x.ensure(N); h.d_b.ensure(N);
+    upload(h, h.d_x.p, x, N); upload(h, h.d_b.p, y, N);
+    dot1(h, N, h.d_x.p, h.d_b.p, h.scal.p + 32);
+    reduce_scalars(h, h.scal.p + 32, 1);
+    B200_CUDA(cudaMemcpyAsync(h.h_pinned, h.scal.p + 32, sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+    *result = h.h_pinned[0];
+  });
+}
+int b200_nrm2(void **handle, const int *n, const double *x, double *result) {
+  double r = 0;
+  int rc = b200_dot(handle, n, x, x, &r);
+  *result = sqrt(r);
+  return rc;
+}
+int b200_get_ilu_values(void **handle, double *ilu_vals) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.ilu_valid, "no valid ILU0 factor");
+    download(h, ilu_vals, h.d_ilu.p, h.nnz);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+}
+int b200_get_structure(void **handle, int *rows, int *cols, int *diag) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    std::vector<int> r((size_t)h.n + 1), c(h.nnz), d(h.n);
+    B200_CUDA(cudaMemcpy(r.data(), h.d_rows.p, r.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h.nnz) B200_CUDA(cudaMemcpy(c.data(), h.d_cols.p, c.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h.n) B200_CUDA(cudaMemcpy(d.data(), h.d_diag.p, d.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int base = h.index_base;
+    for (size_t i = 0; i < r.size(); ++i) rows[i] = r[i] + base;
+    for (size_t i = 0; i < c.size(); ++i) cols[i] = c[i] + base;
+    for (size_t i = 0; i < d.size(); ++i) diag[i] = d[i] + base;
+  });
+}
+int b200_get_levels(void **handle, int *counts, int *level_of_row) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    tri_analyse(h);
+    counts[0] = h.nlev_f; counts[1] = h.nlev_b; counts[2] = h.L.nslices; counts[3] = h.U.nslices;
+    if (level_of_row) for (int i = 0; i < h.n; ++i) level_of_row[i] = h.h_level_f[i];
+  });
+}
+
+// ---- Matrix Vector Proc hook (Load.c:806-824) ------------------------------------------------
+void b200_spmv(void **spmv, int *n, int *rows, int *cols, double *vals, double *u, double *v, int *reinit) {
+  int rc = guarded([&] {
+    B200_REQUIRE(spmv && n && rows && cols && vals && u && v, "null argument");
+    const int N = *n;
+    bool fresh = (*spmv == nullptr) || (reinit && *reinit != 0);
+    if (*spmv == nullptr) { B200_REQUIRE(b200_create(spmv) == 0, g_last_error); }
+    Handle &h = H(spmv);
+    const long long nnz = (long long)rows[N] - rows[0];
+    if (fresh || h.n != N || h.nnz != nnz) {
+      // the hook passes no Diag: structure without the ILU-related checks
+      std::vector<int> r0((size_t)N + 1), c0(nnz), d0(N, 0);
+      for (int i = 0; i <= N; ++i) r0[i] = rows[i] - 1;
+      for (long long p = 0; p < nnz; ++p) c0[p] = cols[p] - 1;
+      for (int i = 0; i < N; ++i) {
+        const int *b = c0.data() + r0[i], *e = c0.data() + r0[i + 1];
+        const int *it = std::lower_bound(b, e, i);
+        B200_REQUIRE(it != e && *it == i, "b200_spmv: row without a diagonal entry");
+        d0[i] = (int)(it - c0.data());
+      }
+      h.index_base = 1;
+      install_structure(h, N, nnz, std::move(r0), std::move(c0), std::move(d0), 1);
+      fresh = true;
+    }
+    // the reference never signals that Values changed (reinit is always 0): detect it
+    double cs = 0.0;
+    for (long long p = 0; p < nnz; ++p) cs += vals[p] * (double)((p & 1023) + 1);
+    if (fresh || h.hook_vals_ptr != vals || cs != h.hook_checksum) {
+      h.d_vals.ensure(nnz);
+      upload(h, h.d_vals.p, vals, nnz);
+      h.have_prec = false;
+      values_changed(h);
+      h.hook_vals_ptr = vals; h.hook_checksum = cs;
+    }
+    h.d_x.ensure(N); h.d_b.ensure(N);
+    upload(h, h.d_x.p, u, N);
+    SpmvArgs a; a.x = h.d_x.p; a.y = h.d_b.p;
+    spmv_launch(h, a, EPI_NONE);
+    download(h, v, h.d_b.p, N);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+  if (rc) { fprintf(stderr, "[elmer_b200] b200_spmv failed: %s\n", g_last_error.c_str()); abort(); }   // no CPU fallback, cf. amgx.c:59-66
+}
+
+// ---- instrumentation -------------------------------------------------------------------------
+int b200_get_stats(void **handle, double *s) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    for (int i = 0; i < 16; ++i) s[i] = 0;
+    s[0] = h.st_solve_ms; s[1] = (double)h.st_matvec; s[2] = (double)h.st_pcond; s[3] = h.st_factor_ms;
+    s[4] = (double)h.st_launch_last; s[5] = (double)h.st_h2d; s[6] = (double)h.st_d2h; s[7] = (double)h.st_iters;
+    s[8] = h.st_spmv_ms; s[9] = h.st_lu_ms; s[10] = h.st_resid; s[11] = (double)h.A.nstore; s[12] = (double)h.nlev_f; s[13] = (double)h.nlev_b;
+  });
+}
+
+int b200_time_matvec(void **handle, const int *reps, double *ms_out) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.have_vals, "b200_time_matvec before b200_set_values");
+    const size_t nv = vec_len(h);
+    h.d_x.ensure(nv); h.d_b.ensure(nv);
+    fill_vec(h, nv, h.d_x.p, 1.0);
+    for (int w = 0; w < 3; ++w) matvec_full(h, h.d_x.p, h.d_b.p);
+    B200_CUDA(cudaEventRecord(h.ev0, h.stream));
+    for (int r = 0; r < *reps; ++r) matvec_full(h, h.d_x.p, h.d_b.p);
+    B200_CUDA(cudaEventRecord(h.ev_end, h.stream));
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+    float ms = 0; B200_CUDA(cudaEventElapsedTime(&ms, h.ev0, h.ev_end));
+    h.st_spmv_ms = ms / *reps; *ms_out = h.st_spmv_ms;
+  });
+}
+
+int b200_time_lu_precondition(void **handle, const int *reps, double *ms_out) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    if (!h.ilu_valid) ilu0_factor(h);
+    h.d_x.ensure(h.n); h.d_b.ensure(h.n);
+    reset_ctrl(h);
+    fill_vec(h, h.n, h.d_x.p, 1.0);
+    for (int w = 0; w < 2; ++w) lu_apply(h, h.d_b.p, h.d_x.p);
+    B200_CUDA(cudaEventRecord(h.ev0, h.stream));
+    for (int r = 0; r < *reps; ++r) lu_apply(h, h.d_b.p, h.d_x.p);
+    B200_CUDA(cudaEventRecord(h.ev_end, h.stream));
+    B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, h.stream));
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+    B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "triangular solve: dependency wait timed out");
+    float ms = 0; B200_CUDA(cudaEventElapsedTime(&ms, h.ev0, h.ev_end));
+    h.st_lu_ms = ms / *reps; *ms_out = h.st_lu_ms;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// Host-side mirror of IterSolver(A,x,b,Solver), fem/src/IterSolve.F90:159-1047: keyword parsing,
+// ipar/dpar filling, preconditioner recompute policy and dispatch -- everything IterSolver does
+// around the HUTI call, for the keyword combinations this library implements.  Anything else is
+// DECLINED (the caller then runs Elmer's own path); declining is not a fallback inside the library.
+#include "common.cuh"
+#include "krylov.h"
+#include "../../include/elmer_b200.h"
+#include <map>
+#include <string>
+#include <sstream>
+#include <algorithm>
+#include <cctype>
+#include <climits>
+
+namespace b200 {
+
+// SIF keyword names are case-insensitive and whitespace-insensitive between words (Lists.F90 lowercases
+// and single-spaces them on read).
+static std::string norm_key(const std::string &s) {
+  std::string o; bool sp = false;
+  for (char ch : s) {
+    if (isspace((unsigned char)ch)) { sp = !o.empty(); continue; }
+    if (sp) { o += ' '; sp = false; }
+    o += (char)tolower((unsigned char)ch);
+  }
+  return o;
+}
+static std::string strip_type(std::string v) {
+  // "Real 1e-8", "Integer 500", "Logical True", "String ilu0", quoted strings
+  std::string n = norm_key(v);
+  for (const char *t : {"real ", "integer ", "logical ", "string "}) if (n.rfind(t, 0) == 0) { n = n.substr(strlen(t)); break; }
+  if (n.size() >= 2 && n.front() == '"' && n.back() == '"') n = n.substr(1, n.size() - 2);
+  return n;
+}
+
+struct Sif {
+  std::map<std::string, std::string> kv;
+  explicit Sif(const char *text) {
+    std::istringstream in(text ? text : "");
+    std::string line;
+    while (std::getline(in, line)) {
+      size_t c = line.find('!'); if (c != std::string::npos) line = line.substr(0, c);
+      size_t e = line.find('=');
+      if (e == std::string::npos) continue;
+      std::string k = norm_key(line.substr(0, e));
+      size_t dc = k.find("::"); if (dc != std::string::npos) k = norm_key(k.substr(dc + 2));   // "Solver 1 :: key"
+      size_t pr = k.find('('); if (pr != std::string::npos) k = norm_key(k.substr(0, pr));
+      kv[k] = strip_type(line.substr(e + 1));
+    }
+  }
+  bool has(const char *k) const { return kv.count(norm_key(k)) > 0; }
+  std::string str(const char *k, const char *d, bool *found = nullptr) const {
+    auto it = kv.find(norm_key(k)); if (found) *found = it != kv.end();
+    return it == kv.end() ? std::string(d) : it->second;
+  }
+  bool logical(const char *k, bool d = false, bool *found = nullptr) const {
+    auto it = kv.find(norm_key(k)); if (found) *found = it != kv.end();
+    if (it == kv.end()) return d;
+    return it->second == "true" || it->second == "1" || it->second == ".true.";
+  }
+  int integer(const char *k, int d, bool *found = nullptr) const {
+    auto it = kv.find(norm_key(k)); if (found) *found = it != kv.end();
+    return it == kv.end() ? d : (int)strtol(it->second.c_str(), nullptr, 10);
+  }
+  double real(const char *k, double d, bool *found = nullptr) const {
+    auto it = kv.find(norm_key(k)); if (found) *found = it != kv.end();
+    if (it == kv.end()) return d;
+    std::string v = it->second; std::replace(v.begin(), v.end(), 'd', 'e');   // Fortran 1.0d-8
+    return strtod(v.c_str(), nullptr);
+  }
+};
+
+struct Declined { std::string why; };
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_itersolver(void **handle, const double *b, double *x, const char *sif, int *solve_count, int *info_out) {
+  try {
+    B200_REQUIRE(handle && *handle, "null handle");
+    Handle &h = *static_cast<Handle *>(*handle);
+    Sif P(sif);
+    int ipar[50] = {0}; double dpar[10] = {0};
+    bool found;
+    // ---- method (IterSolve.F90:250-315)
+    std::string m = P.str("Linear System Iterative Method", "bicgstab", &found);
+    int method;
+    if (m == "cg") method = B200_METHOD_CG;
+    else if (m == "bicgstab") method = B200_METHOD_BICGSTAB;
+    else if (m == "bicgstabl") method = B200_METHOD_BICGSTABL;
+    else if (m == "gcr") method = B200_METHOD_GCR;
+    else if (m == "idrs") method = B200_METHOD_IDRS;
+    else if (m == "bicgstab2" || m == "tfqmr" || m == "cgs" || m == "gmres" || m == "sgs" || m == "jacobi" || m == "richardson")
+      throw Declined{"iterative method '" + m + "' is not on the accelerated path"};
+    else method = B200_METHOD_BICGSTAB;                                  // CASE DEFAULT (313-314)
+    if (P.logical("Linear System Complex") || P.logical("Linear System Pseudo Complex"))
+      throw Declined{"complex / pseudo-complex systems"};
+    const bool internal = method >= B200_METHOD_BICGSTABL;
+    // ---- work sizes and method parameters (327-392)
+    ipar[3] = internal ? 1 : (method == B200_METHOD_CG ? 4 : 8);
+    const int maxit = P.integer("Linear System Max Iterations", 0, &found);
+    B200_REQUIRE(found && maxit >= 1, "'Linear System Max Iterations' missing or < 1");
+    if (method == B200_METHOD_GCR) {
+      int r = P.integer("Linear System GCR Restart", 0, &found);
+      if (!found) r = std::min(maxit, 200);                             // 369-376
+      ipar[16] = r;
+    }
+    if (method == B200_METHOD_BICGSTABL) {
+      int l = P.integer("BiCGstabl polynomial degree", 2, &found);
+      B200_REQUIRE(!found || l >= 2, "'BiCGstabl polynomial degree' < 2");
+      ipar[15] = l;
+    }
+    if (method == B200_METHOD_IDRS) {
+      int s = P.integer("IDRS parameter", 4, &found);
+      B200_REQUIRE(!found || s >= 1, "'IDRS parameter' < 1");
+      ipar[17] = s;
+    }
+    // ---- stopping criterion (397-433)
+    if (P.logical("Linear System Componentwise Backward Error") || P.logical("Linear System Normwise Backward Error"))
+      throw Declined{"backward-error stopping criteria"};
+    ipar[11] = 1;                                                        // HUTI_TRESID_SCALED_BYB
+    ipar[2] = h.n;                                                       // HUTI_NDIM
+    ipar[4] = P.integer("Linear System Residual Output", 1, &found);    // HUTI_DBUGLVL (436-438)
+    ipar[9] = maxit;
+    ipar[10] = P.integer("Linear System Min Iterations", 0);
+    ipar[13] = 1;                                                        // HUTI_USERSUPPLIEDX (473)
+    dpar[0] = P.real("Linear System Convergence Tolerance", 0.0);
+    dpar[1] = P.real("Linear System Divergence Limit", 1.0e20, &found);
+    if (P.logical("Linear System Robust")) throw Declined{"'Linear System Robust'"};
+    ipar[27] = P.logical("IDRS Smoothing") ? 1 : 0;
+    // ---- preconditioner (506-577)
+    if (!internal && P.logical("Linear System Left Preconditioning")) throw Declined{"left-oriented preconditioning"};
+    std::string pcs = P.str("Linear System Preconditioning", "none");
+    int pc;
+    if (P.logical("Linear System Symmetric ILU")) throw Declined{"'Linear System Symmetric ILU' (incomplete Cholesky)"};
+    if (pcs == "none") pc = B200_PRECOND_NONE;
+    else if (pcs == "diagonal") pc = B200_PRECOND_DIAGONAL;
+    else if (pcs == "ilut") throw Declined{"ILUT"};
+    else if (pcs.rfind("ilu", 0) == 0) {
+      int ilun; bool got; double o = P.real("Linear System ILU Order", 0.0, &got);
+      if (got) ilun = (int)lround(o);
+      else ilun = pcs.size() >= 4 ? pcs[3] - '0' : -1;                  // 541-546
+      if (ilun < 0 || ilun > 9) ilun = 0;
+      if (ilun != 0) throw Declined{"ILU order > 0"};
+      pc = B200_PRECOND_ILU0;
+    } else if (pcs.rfind("bilu", 0) == 0 || pcs == "multigrid" || pcs.rfind("vanka", 0) == 0 || pcs == "slave" || pcs == "circuit")
+      throw Declined{"preconditioner '" + pcs + "'"};
+    else { fprintf(stderr, "[elmer_b200] IterSolve: Unknown preconditioner type, feature disabled.\n"); pc = B200_PRECOND_NONE; }
+    if (P.real("Linear System ILU Factor", 0.0) > 2.220446049250313e-16) throw Declined{"'Linear System ILU Factor'"};
+    if (P.logical("Edge Basis")) throw Declined{"'Edge Basis' preconditioner matrix"};
+    // ---- recompute policy (579-587): factorise when no factor exists or Refactorize and SolveCount mod n == 0
+    int sc = solve_count ? *solve_count : 0;
+    if (pc == B200_PRECOND_ILU0) {
+      B200_CUDA(cudaSetDevice(h.device));
+      bool refactor = false;
+      if (!P.logical("No Precondition Recompute")) {
+        int n = P.integer("Linear System Precondition Recompute", 1); if (n <= 0) n = 1;
+        bool Refactorize = P.logical("Linear System Refactorize", true);
+        refactor = !h.ilu_exists || (Refactorize && sc % n == 0);
+      }
+      if (refactor || !h.ilu_exists) ilu0_factor(h);
+      h.ilu_valid = true;                                               // a stale factor is reused on purpose
+    }
+    if (solve_count) *solve_count = sc + 1;                             // A % SolveCount (787)
+    int rc = b200_solve(handle, b, x, ipar, dpar, &method, &pc, nullptr);
+    if (info_out) { info_out[0] = ipar[29]; info_out[1] = ipar[30]; }
+    return rc;
+  } catch (const Declined &d) {
+    set_last_error("declined: " + d.why);
+    return B200_DECLINED;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    fprintf(stderr, "[elmer_b200] %s\n", e.what());
+    if (info_out) { info_out[0] = B200_INFO_HALTED; info_out[1] = 0; }
+    return 1;
+  }
+}

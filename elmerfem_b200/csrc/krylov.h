@@ -1,0 +1,16 @@
+// Internal interfaces between the C ABI layer, the Krylov drivers and the communication layer.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum { B200_M_CG = 1, B200_M_BICGSTAB = 2, B200_M_BICGSTABL = 3, B200_M_GCR = 4, B200_M_IDRS = 5 };
+
+// b, x, P: device pointers; ipar/dpar: host HUTI arrays (fhutiter/src/huti_fdefs.h:101-155)
+void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *dpar, int method, int pc, const double *d_P);
+
+// in-place sum over ranks of `count` device doubles, on the solve stream (no-op for one rank)
+void reduce_scalars(Handle &h, double *d, int count);
+void comm_allreduce_sum(Handle &h, double *d, int count);
+
+}  // namespace b200

@@ -1,0 +1,279 @@
+// Jacobi and ILU(0) preconditioning on the device.
+//
+//   diag_apply   <- CRS_DiagPrecondition          fem/src/CRSMatrix.F90:2279-2326
+//   ilu0_factor  <- CRS_IncompleteLU(A,0)         fem/src/CRSMatrix.F90:3445-3531, 3604-3661
+//   lu_apply     <- CRS_LUPrecondition/CRS_LUSolve fem/src/CRSMatrix.F90:4550-4564, 4590-4663
+//
+// The reference runs the factorisation and both triangular sweeps serially.  Here rows are processed
+// in dependency-level order by a persistent grid; a row starts as soon as the rows it reads are done
+// (point-to-point flags / value sentinels in L2, no grid-wide barrier and no kernel launch per level).
+// No reordering, no approximation: every row performs the reference's operations in the reference's
+// order with separate multiply/add roundings, so ILUValues and the solve results are bit-identical
+// to the CPU loops.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200 {
+
+constexpr int ILU_MAXROW = 128;            // rows up to this length are staged in shared memory
+constexpr long long SPIN_LIMIT = 1LL << 27;
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_diag_apply(int n, const double *__restrict__ dvals, double *__restrict__ u, const double *__restrict__ v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double d = dvals[i];
+    u[i] = (fabs(d) > AEPS) ? __ddiv_rn(v[i], d) : v[i];
+  }
+}
+void diag_apply(Handle &h, double *u, const double *v) {
+  if (h.n == 0) return;
+  int blocks = std::min((h.n + 255) / 256, NUM_SMS * 8);
+  k_diag_apply<<<blocks, 256, 0, h.stream>>>(h.n, h.d_dvals.p, u, v);
+  B200_CUDA(cudaGetLastError());
+  h.st_launch++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp per row, rows taken in forward-level order (the L plan's slot order).
+__global__ void __launch_bounds__(256) k_ilu0_factor(int nslots, const int *__restrict__ perm, const int *__restrict__ rows,
+                                                      const int *__restrict__ cols, const int *__restrict__ diag,
+                                                      const double *__restrict__ Avals, double *LU, int *rowdone, Ctrl *ctrl) {
+  __shared__ double s_val[8][ILU_MAXROW];
+  __shared__ int s_col[8][ILU_MAXROW];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slot = gwarp; slot < nslots; slot += nwarps) {
+    const int r = perm[slot];
+    if (r < 0) continue;
+    const int rs = rows[r], re = rows[r + 1], d = diag[r], len = re - rs, nlow = d - rs;
+    const bool staged = len <= ILU_MAXROW;
+    double *vrow = staged ? s_val[wib] : (LU + rs);
+    const int *crow = staged ? s_col[wib] : (cols + rs);
+    // CRSMatrix.F90:3614-3620: the row in "full form" (here: its own pattern, which is all that is ever touched)
+    for (int t = lane; t < len; t += 32) {
+      double a = Avals[rs + t];
+      if (staged) { s_val[wib][t] = a; s_col[wib][t] = cols[rs + t]; }
+      else LU[rs + t] = a;
+    }
+    __syncwarp();
+    // wait until every row of the strict lower pattern is finished
+    long long spins = 0;
+    for (int t = lane; t < nlow; t += 32) {
+      const int k = crow[t];
+      while (ld_acquire(rowdone + k) == 0) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        __nanosleep(40);
+      }
+    }
+    __syncwarp();
+    // 3624-3637: IKJ elimination, lower entries in column order
+    for (int m = 0; m < nlow; ++m) {
+      double skm = vrow[m];
+      if (skm == 0.0) continue;                                   // 3626
+      const int k = crow[m];
+      const int kd = diag[k];
+      const double ukk = __ldcg(LU + kd);
+      if (fabs(ukk) > AEPS) skm = __ddiv_rn(skm, ukk);           // 3628-3629
+      __syncwarp();
+      if (lane == 0) vrow[m] = skm;
+      const int ke = rows[k + 1];
+      for (int l = kd + 1 + lane; l < ke; l += 32) {              // 3631-3636
+        const int j = cols[l];
+        int lo = m + 1, hi = len;                                 // columns > k live right of position m
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (crow[mid] < j) lo = mid + 1; else hi = mid; }
+        if (lo < len && crow[lo] == j) vrow[lo] = nfms(vrow[lo], skm, __ldcg(LU + l));
+      }
+      __syncwarp();
+    }
+    if (staged) for (int t = lane; t < len; t += 32) __stcg(LU + rs + t, s_val[wib][t]);   // 3643-3649
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(rowdone + r, 1);
+  }
+}
+
+// 3654-3660: store the inverse diagonal (1.0 when tiny)
+__global__ void k_ilu0_invert_diag(int n, const int *__restrict__ diag, double *LU) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double d = LU[diag[i]];
+    LU[diag[i]] = (fabs(d) < AEPS) ? 1.0 : __ddiv_rn(1.0, d);
+  }
+}
+__global__ void k_gather_diag_slots(int nslots, const int *__restrict__ perm, const int *__restrict__ diag,
+                                    const double *__restrict__ LU, double *__restrict__ dinv) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  int r = perm[s];
+  dinv[s] = r >= 0 ? LU[diag[r]] : 0.0;
+}
+
+static int persistent_blocks(const void *kernel, int threads, int want_per_sm) {
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  B200_REQUIRE(per_sm > 0, "kernel does not fit on an SM");
+  if (want_per_sm > 0 && want_per_sm < per_sm) per_sm = want_per_sm;
+  int dev = 0, sms = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return per_sm * sms;
+}
+// The spin waits need every block of the grid resident at once: cooperative launch guarantees it
+// (or fails loudly) even when another stream holds SM resources.
+template <class... Args>
+static void launch_coresident(const void *kernel, int blocks, int threads, cudaStream_t st, Args... args) {
+  void *argv[] = {(void *)&args...};
+  B200_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(threads), argv, 0, st));
+}
+
+void ilu0_factor(Handle &h) {
+  B200_REQUIRE(h.have_vals, "ILU0 requested before b200_set_values");
+  tri_analyse(h);
+  cudaStream_t st = h.stream;
+  h.d_ilu.ensure(h.nnz);
+  B200_CUDA(cudaEventRecord(h.evf0, st));
+  if (h.n > 0) {
+    B200_CUDA(cudaMemsetAsync(h.d_rowdone.p, 0, (size_t)h.n * sizeof(int), st));
+    B200_CUDA(cudaMemsetAsync(&h.ctrl.p->spin_timeout, 0, sizeof(int), st));
+    const double *src = h.have_prec ? h.d_prec.p : h.d_vals.p;        // CRSMatrix.F90:3480-3484
+    if (!h.grid_ilu) h.grid_ilu = persistent_blocks((const void *)k_ilu0_factor, 256, 0);
+    int blocks = std::max(1, std::min(h.grid_ilu, (h.L.nslots + 7) / 8));
+    launch_coresident((const void *)k_ilu0_factor, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, (const int *)h.d_rows.p,
+                      (const int *)h.d_cols.p, (const int *)h.d_diag.p, src, h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
+    int eb = std::min((h.n + 255) / 256, NUM_SMS * 8);
+    k_ilu0_invert_diag<<<eb, 256, 0, st>>>(h.n, h.d_diag.p, h.d_ilu.p);
+    sell_refresh_values(h, h.L, h.d_ilu.p);
+    sell_refresh_values(h, h.U, h.d_ilu.p);
+    if (h.U.nslots) k_gather_diag_slots<<<(h.U.nslots + 255) / 256, 256, 0, st>>>(h.U.nslots, h.U.perm.p, h.d_diag.p, h.d_ilu.p, h.d_dinv_slot.p);
+    B200_CUDA(cudaGetLastError());
+  }
+  B200_CUDA(cudaEventRecord(h.evf1, st));
+  B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  float ms = 0; B200_CUDA(cudaEventElapsedTime(&ms, h.evf0, h.evf1));
+  h.st_factor_ms = ms;
+  B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "ILU0 factorisation: dependency wait timed out");
+  h.ilu_valid = true; h.ilu_exists = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sync-free level-scheduled triangular solve.  Thread = row, warp = 32 rows of ONE level.  `out` is
+// pre-filled with SENTINEL; a consumer spins on the producer's 8-byte result itself, so readiness
+// and value arrive in the same L2 round trip.  All gathers of a row are issued together (one L2
+// latency per row, not one per entry) and only entries still holding the sentinel are re-polled.
+// A single counter of finished slices throttles the grid: a warp starts polling only when every
+// slice up to LOOKAHEAD levels behind its own is finished, so the thousands of resident warps that
+// run ahead of the wavefront prefetch their matrix entries and then sleep on one address instead of
+// flooding L2 with polls.  The counter is only a throttle; correctness rests on the sentinels.
+//   forward  (UPPER = false): out_i = rhs_i - sum_{j<i} L_ij out_j                   (4642-4649)
+//   backward (UPPER = true) : out_i = Dinv_i * (rhs_i - sum_{j>i} U_ij out_j)       (4653-4660)
+__device__ __forceinline__ int ld_relaxed_i(const int *p) {
+  int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// Vectors of the solves live in slot (level) order: `out` has one entry per slot, the column ids of
+// T are slot ids.  rhs_idx == nullptr: rhs is in natural order (forward sweep input); otherwise
+// rhs[rhs_idx[slot]] (backward sweep reading the forward result).  nat_out != nullptr: the result is
+// also scattered to natural order (the preconditioned vector handed back to the Krylov method).
+template <bool UPPER, int CH>
+__global__ void __launch_bounds__(256, 2) k_sptrsv(SellView T, const int *__restrict__ slice_level, const int *__restrict__ lvl_slices,
+                                                    int *lvl_done, int lookahead, unsigned gate_sleep, unsigned spin_sleep,
+                                                    const double *__restrict__ dinv_slot, const double *__restrict__ rhs,
+                                                    const int *__restrict__ rhs_idx, double *out, double *__restrict__ nat_out,
+                                                    Ctrl *ctrl) {
+  if (ctrl->done) return;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slice = gwarp; slice < T.nslices; slice += nwarps) {
+    const long long p0 = T.ptr[slice];
+    const int W = (int)((T.ptr[slice + 1] - p0) >> 5);
+    const int slot = slice * 32 + lane;
+    const int row = T.perm[slot];
+    const int len = T.len[slot];
+    const int *__restrict__ cp = T.cols + p0 + lane;
+    const double *__restrict__ vp = T.vals + p0 + lane;
+    double s = row >= 0 ? rhs[rhs_idx ? rhs_idx[slot] : row] : 0.0;
+    const double dinv = (UPPER && row >= 0) ? dinv_slot[slot] : 1.0;
+    long long spins = 0;
+    bool gated = false;
+    for (int j0 = 0; j0 < W || !gated; j0 += CH) {
+      int c[CH]; double v[CH], xv[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {                      // matrix entries: streamed from HBM ahead of the wavefront
+        const bool in = j0 + k < W;
+        c[k] = in ? ld_stream(cp + (j0 + k) * 32) : 0;
+        v[k] = in ? ld_stream(vp + (j0 + k) * 32) : 0.0;
+      }
+      if (!gated) {                                       // throttle: wait for the wavefront to come near
+        const int wl = slice_level[slice] - lookahead;
+        if (lane == 0 && wl >= 0) {
+          const int need = lvl_slices[wl];
+          while (ld_relaxed_i(lvl_done + wl * 32) < need) {
+            if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+            if (gate_sleep) __nanosleep(gate_sleep);
+          }
+        }
+        __syncwarp();
+        gated = true;
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) xv[k] = (j0 + k < len) ? ld_relaxed(out + c[k]) : 0.0;   // all gathers in flight
+      for (;;) {                                          // re-poll every entry still holding the sentinel, together
+        bool pending = false;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) pending |= is_sentinel(xv[k]);
+        if (!pending) break;
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        if (spin_sleep) __nanosleep(spin_sleep);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) if (is_sentinel(xv[k])) xv[k] = ld_relaxed(out + c[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) if (j0 + k < len) s = nfms(s, v[k], xv[k]);
+    }
+    if (row >= 0) {
+      double res = UPPER ? __dmul_rn(dinv, s) : s;
+      if (res != res) res = __longlong_as_double((long long)CANON_NAN);
+      st_relaxed(out + slot, res);
+      if (nat_out) nat_out[row] = res;
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(lvl_done + slice_level[slice] * 32, 1);
+  }
+}
+
+__global__ void k_tri_prepare(int na, double *a, int nb, double *b, int *counters, int ncounters) {
+  const double sent = __longlong_as_double((long long)SENTINEL);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
+  for (int i = i0; i < na; i += st) a[i] = sent;
+  for (int i = i0; i < nb; i += st) b[i] = sent;
+  for (int i = i0; i < ncounters; i += st) counters[i * 32] = 0;
+}
+
+template <int CH>
+static void lu_launch(Handle &h, double *u, const double *v) {
+  cudaStream_t st = h.stream;
+  if (!h.grid_tri_l) {
+    h.grid_tri_l = persistent_blocks((const void *)k_sptrsv<false, CH>, 256, h.tri_blocks_per_sm);
+    h.grid_tri_u = persistent_blocks((const void *)k_sptrsv<true, CH>, 256, h.tri_blocks_per_sm);
+  }
+  int bl = std::max(1, std::min(h.grid_tri_l, (h.L.nslices + 7) / 8));
+  int bu = std::max(1, std::min(h.grid_tri_u, (h.U.nslices + 7) / 8));
+  const int la = h.tri_lookahead; const unsigned gs = h.tri_gate_sleep, ss = h.tri_spin_sleep;
+  launch_coresident((const void *)k_sptrsv<false, CH>, bl, 256, st, h.L.view(), (const int *)h.L.gate.p, (const int *)h.d_lvlcnt_f.p, h.tri_counters.p, la, gs, ss,
+                    (const double *)nullptr, v, (const int *)nullptr, h.d_yl.p, (double *)nullptr, h.ctrl.p);
+  launch_coresident((const void *)k_sptrsv<true, CH>, bu, 256, st, h.U.view(), (const int *)h.U.gate.p, (const int *)h.d_lvlcnt_b.p,
+                    h.tri_counters.p + (size_t)(h.nlev_f + 1) * 32, la, gs, ss,
+                    (const double *)h.d_dinv_slot.p, (const double *)h.d_yl.p, (const int *)h.d_urhs.p, h.d_xu.p, u, h.ctrl.p);
+}
+
+void lu_apply(Handle &h, double *u, const double *v) {
+  B200_REQUIRE(h.ilu_valid, "LU preconditioner applied without a valid ILU0 factor");
+  if (h.n == 0) return;
+  k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
+  if (h.tri_maxw <= 8) lu_launch<8>(h, u, v); else lu_launch<16>(h, u, v);
+  B200_CUDA(cudaGetLastError());
+  h.st_launch += 3; h.st_pcond++;
+}
+
+}  // namespace b200

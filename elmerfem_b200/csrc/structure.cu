@@ -1,0 +1,200 @@
+// Device-resident matrix structure: CRS mirror -> SELL-32 operand for SpMV, dependency levels and
+// level-sorted SELL-32 plans for the ILU0 triangular solves.
+//
+// Reference data layout being replaced: Matrix_t (fem/src/Types.F90:193-283): Rows/Cols/Diag/Values,
+// with ILURows/ILUCols/ILUDiag aliasing them for ILU(0) (fem/src/CRSMatrix.F90:3488-3491).
+#include "common.cuh"
+#include <thrust/scan.h>
+#include <thrust/execution_policy.h>
+#include <thrust/device_ptr.h>
+#include <algorithm>
+
+namespace b200 {
+
+// kind 0: whole row (SpMV operand)   start = rows[r],    len = rows[r+1]-rows[r]
+// kind 1: strict lower part (L)      start = rows[r],    len = diag[r]-rows[r]
+// kind 2: strict upper part (U)      start = diag[r]+1,  len = rows[r+1]-diag[r]-1
+__global__ void k_slot_extent(int nslots, int n, const int *__restrict__ perm, const int *__restrict__ rows,
+                              const int *__restrict__ diag, int kind, int *__restrict__ start, int *__restrict__ len) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nslots) return;
+  int r = perm ? perm[slot] : (slot < n ? slot : -1);
+  int s = 0, l = 0;
+  if (r >= 0) {
+    if (kind == 0) { s = rows[r]; l = rows[r + 1] - rows[r]; }
+    else if (kind == 1) { s = rows[r]; l = diag[r] - rows[r]; }
+    else { s = diag[r] + 1; l = rows[r + 1] - diag[r] - 1; }
+  }
+  start[slot] = s; len[slot] = l;
+}
+
+// one warp per slice: width = max len, stored as entries (width*32) for the scan
+__global__ void k_slice_entries(int nslices, const int *__restrict__ len, long long *__restrict__ entries) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nslices) return;
+  int l = len[w * 32 + lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l = max(l, __shfl_xor_sync(0xffffffffu, l, o));
+  if (lane == 0) entries[w] = (long long)l * 32;
+}
+
+// Transposes one slice of CRS data into SELL order.  A warp walks its 32 rows entry by entry:
+// lane owns one row; reads are served from L1 (a row is 1-3 cache lines), writes are coalesced.
+template <class T, bool kSubBase>
+__global__ void k_sell_fill(int nslots, const long long *__restrict__ ptr, const int *__restrict__ start,
+                            const int *__restrict__ len, const T *__restrict__ src, T *__restrict__ dst) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nslots) return;
+  int lane = threadIdx.x & 31;
+  long long base = ptr[slot >> 5] + lane;
+  int s = start[slot], l = len[slot];
+  for (int j = 0; j < l; ++j) dst[base + (long long)j * 32] = src[s + j];
+}
+
+// pads: column = a valid index (own row / 0), value = 0; never read because loops stop at len.
+template <class T>
+__global__ void k_fill(long long n, T *p, T v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void k_remap_cols(long long n, int *cols, const int *__restrict__ map) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) cols[i] = map[cols[i]];
+}
+
+// S.start / S.len / S.perm already hold the per-slot extents; lays out the slices and copies the columns.
+void sell_finish(Handle &h, Sell &S, int nslots, bool has_perm, const int *src_cols) {
+  cudaStream_t st = h.stream;
+  S.nslots = nslots; S.nslices = nslots / 32; S.has_perm = has_perm;
+  S.ptr.ensure(S.nslices + 1);
+  if (nslots == 0) { S.nstore = 0; B200_CUDA(cudaMemsetAsync(S.ptr.p, 0, sizeof(long long), st)); return; }
+  k_slice_entries<<<(S.nslices * 32 + 255) / 256, 256, 0, st>>>(S.nslices, S.len.p, S.ptr.p);
+  B200_CUDA(cudaMemsetAsync(S.ptr.p + S.nslices, 0, sizeof(long long), st));
+  thrust::exclusive_scan(thrust::cuda::par.on(st), S.ptr.p, S.ptr.p + S.nslices + 1, S.ptr.p);
+  B200_CUDA(cudaMemcpyAsync(&S.nstore, S.ptr.p + S.nslices, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  S.cols.ensure(S.nstore); S.vals.ensure(S.nstore);
+  if (S.nstore) {
+    B200_CUDA(cudaMemsetAsync(S.cols.p, 0, S.nstore * sizeof(int), st));
+    B200_CUDA(cudaMemsetAsync(S.vals.p, 0, S.nstore * sizeof(double), st));
+    k_sell_fill<int, false><<<(nslots + 255) / 256, 256, 0, st>>>(nslots, S.ptr.p, S.start.p, S.len.p, src_cols, S.cols.p);
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+static void build_sell(Handle &h, Sell &S, int kind, const int *d_perm, int nslots) {
+  S.len.ensure(nslots); S.start.ensure(nslots);
+  if (nslots) k_slot_extent<<<(nslots + 255) / 256, 256, 0, h.stream>>>(nslots, h.n, d_perm, h.d_rows.p, h.d_diag.p, kind, S.start.p, S.len.p);
+  sell_finish(h, S, nslots, d_perm != nullptr, h.d_cols.p);
+}
+
+void sell_refresh_values(Handle &h, Sell &S, const double *crs_vals) {
+  if (S.nslots == 0 || S.nstore == 0) return;
+  k_sell_fill<double, false><<<(S.nslots + 255) / 256, 256, 0, h.stream>>>(S.nslots, S.ptr.p, S.start.p, S.len.p, crs_vals, S.vals.p);
+  B200_CUDA(cudaGetLastError());
+}
+
+void structure_build(Handle &h) {
+  int nslots = ((h.n + 31) / 32) * 32;
+  build_sell(h, h.A, 0, nullptr, nslots);
+}
+
+// Dependency levels of the two triangular solves, computed on the host copy of the pattern (O(nnz),
+// once per structure).  Forward level of row i = 1 + max level of the rows in its strict lower part
+// (exactly the rows CRS_LUSolve's forward sweep, CRSMatrix.F90:4642-4649, and the IKJ elimination of
+// CRS_IncompleteLU, 3624-3637, read before producing row i); backward likewise on the upper part
+// (4653-4660).  Rows are then laid out level by level, each level padded to whole 32-row slices so
+// that no warp ever holds two rows that depend on each other.
+static void level_layout(int n, const std::vector<int> &level, int nlev, std::vector<int> &perm, int &nslots, bool descending,
+                         std::vector<int> &gate, std::vector<int> &lvl_slices) {
+  std::vector<long long> cnt(nlev + 1, 0);
+  for (int i = 0; i < n; ++i) cnt[level[i] + 1]++;
+  std::vector<long long> slice0(nlev + 1, 0);
+  for (int l = 0; l < nlev; ++l) slice0[l + 1] = slice0[l] + (cnt[l + 1] + 31) / 32;
+  long long ns = slice0[nlev] * 32;
+  B200_REQUIRE(ns < 2147483647LL, "level layout exceeds int32 slots");
+  nslots = (int)ns;
+  perm.assign(nslots, -1);
+  // per slice: its level; per level: number of slices (a slice of level l opens once level l - lookahead is finished)
+  gate.assign(nslots / 32, 0);
+  lvl_slices.assign(nlev, 0);
+  for (int l = 0; l < nlev; ++l) {
+    lvl_slices[l] = (int)(slice0[l + 1] - slice0[l]);
+    for (long long sl = slice0[l]; sl < slice0[l + 1]; ++sl) gate[sl] = l;
+  }
+  std::vector<long long> fill(nlev, 0);
+  if (!descending) {
+    for (int i = 0; i < n; ++i) { int l = level[i]; perm[slice0[l] * 32 + fill[l]++] = i; }
+  } else {
+    for (int i = n - 1; i >= 0; --i) { int l = level[i]; perm[slice0[l] * 32 + fill[l]++] = i; }
+  }
+}
+
+void tri_analyse(Handle &h) {
+  if (h.tri_ready) return;
+  const int n = h.n;
+  const std::vector<int> &rows = h.h_rows, &cols = h.h_cols, &diag = h.h_diag;
+  std::vector<int> lf(n, 0), lb(n, 0);
+  int nlf = 0, nlb = 0;
+  for (int i = 0; i < n; ++i) {
+    int l = 0;
+    for (int p = rows[i]; p < diag[i]; ++p) l = std::max(l, lf[cols[p]] + 1);
+    lf[i] = l; nlf = std::max(nlf, l + 1);
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    int l = 0;
+    for (int p = diag[i] + 1; p < rows[i + 1]; ++p) l = std::max(l, lb[cols[p]] + 1);
+    lb[i] = l; nlb = std::max(nlb, l + 1);
+  }
+  if (n == 0) { nlf = nlb = 0; }
+  h.nlev_f = nlf; h.nlev_b = nlb;
+  std::vector<int> pf, pb; int nsf = 0, nsb = 0;
+  std::vector<int> gf, gb, cf, cb;
+  level_layout(n, lf, nlf, pf, nsf, false, gf, cf);
+  level_layout(n, lb, nlb, pb, nsb, true, gb, cb);
+  h.L.perm.ensure(nsf); h.U.perm.ensure(nsb);
+  h.L.gate.ensure(gf.size()); h.U.gate.ensure(gb.size());
+  h.d_lvlcnt_f.ensure(cf.size()); h.d_lvlcnt_b.ensure(cb.size());
+  h.tri_counters.ensure(((size_t)nlf + nlb + 2) * 32);
+  if (!cf.empty()) B200_CUDA(cudaMemcpyAsync(h.d_lvlcnt_f.p, cf.data(), cf.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (!cb.empty()) B200_CUDA(cudaMemcpyAsync(h.d_lvlcnt_b.p, cb.data(), cb.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (!gf.empty()) B200_CUDA(cudaMemcpyAsync(h.L.gate.p, gf.data(), gf.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (!gb.empty()) B200_CUDA(cudaMemcpyAsync(h.U.gate.p, gb.data(), gb.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (nsf) B200_CUDA(cudaMemcpyAsync(h.L.perm.p, pf.data(), (size_t)nsf * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (nsb) B200_CUDA(cudaMemcpyAsync(h.U.perm.p, pb.data(), (size_t)nsb * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  B200_CUDA(cudaStreamSynchronize(h.stream));
+  build_sell(h, h.L, 1, h.L.perm.p, nsf);
+  build_sell(h, h.U, 2, h.U.perm.p, nsb);
+  // The solves keep their vectors in level (slot) order: a warp's 32 rows store one coalesced line, and
+  // the entries it gathers from the previous levels sit in neighbouring slots instead of being strewn
+  // over the natural numbering.  Columns of L/U are renumbered to slots; the backward sweep reads its
+  // right-hand side (the forward result, L-slot order) through urhs.
+  {
+    std::vector<int> slotL(std::max(n, 1), 0), slotU(std::max(n, 1), 0), urhs(std::max(nsb, 1), 0);
+    for (int s = 0; s < nsf; ++s) if (pf[s] >= 0) slotL[pf[s]] = s;
+    for (int s = 0; s < nsb; ++s) if (pb[s] >= 0) { slotU[pb[s]] = s; urhs[s] = slotL[pb[s]]; }
+    DBuf<int> dL, dU; dL.ensure(n); dU.ensure(n); h.d_urhs.ensure(nsb);
+    if (n) {
+      B200_CUDA(cudaMemcpyAsync(dL.p, slotL.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+      B200_CUDA(cudaMemcpyAsync(dU.p, slotU.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+      B200_CUDA(cudaMemcpyAsync(h.d_urhs.p, urhs.data(), (size_t)nsb * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+      if (h.L.nstore) k_remap_cols<<<NUM_SMS * 8, 256, 0, h.stream>>>(h.L.nstore, h.L.cols.p, dL.p);
+      if (h.U.nstore) k_remap_cols<<<NUM_SMS * 8, 256, 0, h.stream>>>(h.U.nstore, h.U.cols.p, dU.p);
+      B200_CUDA(cudaGetLastError());
+      B200_CUDA(cudaStreamSynchronize(h.stream));
+    }
+    dL.release(); dU.release();
+  }
+  h.d_yl.ensure(nsf); h.d_xu.ensure(nsb);
+  h.d_dinv_slot.ensure(nsb);
+  {
+    int mw = 0;
+    for (int i = 0; i < n; ++i) mw = std::max(mw, std::max(diag[i] - rows[i], rows[i + 1] - diag[i] - 1));
+    h.tri_maxw = mw;
+  }
+  h.d_rowdone.ensure(n);
+  h.h_level_f.swap(lf);
+  h.tri_ready = true;
+}
+
+}  // namespace b200

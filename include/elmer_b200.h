@@ -1,0 +1,159 @@
+/*
+ * elmer_b200.h -- C ABI of the B200-native sparse iterative linear-solve path for Elmer.
+ *
+ * Drop-in boundary.  Everything is `extern "C"`, every scalar is passed by
+ * reference so the entry points are directly callable from Fortran through ISO_C_BINDING
+ * (elmerfem_b200/fortran/B200Solve.F90 holds the INTERFACE blocks), and no CUDA, NCCL or torch
+ * type appears in a signature.  The matrix handle is an opaque pointer slot owned by the caller
+ * (Elmer stores such slots in Matrix_t%SpMV / %AMGX, fem/src/Types.F90:264-267); the library owns
+ * all device memory behind it.  Host arrays stay owned by the caller.
+ *
+ * Reference interfaces each entry point replaces (paths relative to ElmerCSC/elmerfem):
+ *
+ *   b200_solve            <- IterSolver's method call: IterCall(iterProc, x, b, ipar, dpar, work, mv, pcl, pcr,
+ *                            dot, norm, stopc), fem/src/IterSolve.F90:1004-1005, i.e. the HUTI solver entry
+ *                            fhutiter/src/huti_interfaces.F90:203-218 with the five callbacks
+ *                            CRS_MatrixVectorProd / CRS_DiagPrecondition / CRS_LUPrecondition / ddot / dnrm2 bound
+ *                            inside; ipar(50)/dpar(10) are the HUTI arrays verbatim (fhutiter/src/huti_fdefs.h:101-155).
+ *                            Same shape as the in-tree GPU bridges ROCSerialSolve / AMGXSolve
+ *                            (fem/src/SolverUtils.F90:15314-15333, 15075-15087).
+ *   b200_set_structure    <- the CRS container Matrix_t (fem/src/Types.F90:193-283): Rows, Cols, Diag, ndeg.
+ *   b200_set_values       <- A%Values / A%PrecValues as read by CRS_IncompleteLU (fem/src/CRSMatrix.F90:3480-3484)
+ *                            and CRS_MatrixVectorProd (4772-4776); once per nonlinear iteration.
+ *   b200_factorize        <- CRS_IncompleteLU(A,0), fem/src/CRSMatrix.F90:3445-3661, called from IterSolve.F90:741
+ *                            under the recompute policy of IterSolve.F90:579-587 (the caller applies the policy).
+ *   b200_matvec           <- CRS_MatrixVectorProd(u,v,ipar), fem/src/CRSMatrix.F90:4744-4905.
+ *   b200_diag_precondition<- CRS_DiagPrecondition(u,v,ipar), fem/src/CRSMatrix.F90:2279-2326.
+ *   b200_lu_precondition  <- CRS_LUPrecondition(u,v,ipar) -> CRS_LUSolve, fem/src/CRSMatrix.F90:4550-4564, 4590-4663.
+ *   b200_dot / b200_nrm2  <- ddot / dnrm2 (mathlibs/src/blas) as bound at IterSolve.F90:910-912, and their MPI
+ *                            forms SParDotProd / SParNorm (fem/src/SParIterComm.F90:5081-5136) when a partition is set.
+ *   b200_spmv             <- the `Matrix Vector Proc` hook: matvecsubrext_c, fem/src/Load.c:806-824, called from
+ *                            fem/src/CRSMatrix.F90:1527-1529 and 4778-4781.  Exact signature of that hook.
+ *   b200_set_partition /
+ *   b200_comm_*           <- SParIterSolver's parallel structure (fem/src/SParIterSolver.F90:123-836, 1409-1594) in the
+ *                            "complete owned rows + continuous global numbering" form the ROCSolver/AMGXSolver
+ *                            bridges already build (fem/src/SolverUtils.F90:15461-15579, rocalution.cpp:64-372);
+ *                            SParMatrixVector's interface exchange (SParIterSolver.F90:2630-2745) becomes a halo
+ *                            exchange of x over NCCL.
+ *   b200_itersolver       <- IterSolver(A,x,b,Solver) itself (fem/src/IterSolve.F90:159-1047): keyword parsing,
+ *                            ipar/dpar filling, x = 1e-8 rule, preconditioner recompute policy, error mapping.
+ *
+ * Return value of every function: 0 = ok, non-zero = failure (message on stderr and via b200_last_error()).
+ * b200_solve additionally reports through ipar(30) = HUTI_INFO exactly as the HUTI routines do; a CUDA/NCCL
+ * failure maps to HUTI_HALTED (4).  There is no CPU fallback anywhere in this library.
+ */
+#ifndef ELMER_B200_H
+#define ELMER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Linear System Iterative Method (IterSolve.F90:278-315) */
+#define B200_METHOD_CG        1   /* huti_dcgsolv        */
+#define B200_METHOD_BICGSTAB  2   /* huti_dbicgstabsolv  */
+#define B200_METHOD_BICGSTABL 3   /* itermethod_bicgstabl*/
+#define B200_METHOD_GCR       4   /* itermethod_gcr      */
+#define B200_METHOD_IDRS      5   /* itermethod_idrs     */
+
+/* Linear System Preconditioning (IterSolve.F90:529-547) */
+#define B200_PRECOND_NONE     0
+#define B200_PRECOND_DIAGONAL 1
+#define B200_PRECOND_ILU0     2
+
+/* HUTI_INFO codes (fhutiter/src/huti_fdefs.h:18-50) */
+#define B200_INFO_CONVERGENCE 1
+#define B200_INFO_MAXITER     2
+#define B200_INFO_DIVERGENCE  3
+#define B200_INFO_HALTED      4
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int b200_create(void **handle);                    /* *handle must be NULL or garbage; set on return   */
+int b200_destroy(void **handle);                   /* frees device memory, sets *handle = NULL         */
+const char *b200_last_error(void);
+int b200_device_count(int *count);                 /* cudaGetDeviceCount; fails loudly without a GPU   */
+int b200_set_device(void **handle, const int *device);  /* default: LOCAL_RANK or 0 (amgx.c:161-163)   */
+
+/* ---- matrix ---------------------------------------------------------------------------- */
+/* rows[n+1], cols[nnz], diag[n] are Elmer's arrays as they are (index_base = 1) or 0-based copies
+ * (index_base = 0, as the ROC/AMGX bridges pass).  Columns must be sorted ascending within each row
+ * (CRS_SortMatrix) and every row must hold its diagonal.  The integer arrays are mirrored on the
+ * device bit-exactly (b200_get_structure reads them back for the parity tests).  ndeg = Matrix_t%ndeg. */
+int b200_set_structure(void **handle, const int *n, const int *nnz, const int *rows, const int *cols,
+                       const int *diag, const int *index_base, const int *ndeg);
+/* vals[nnz] host; prec_vals may be NULL (A%PrecValues absent). Marks the ILU factor stale. */
+int b200_set_values(void **handle, const double *vals, const double *prec_vals);
+/* Same, but vals/prec_vals are DEVICE pointers (values assembled or kept on the GPU). */
+int b200_set_values_device(void **handle, const double *d_vals, const double *d_prec_vals);
+int b200_factorize(void **handle);                 /* ILU0 of PrecValues (if given) else Values        */
+
+/* ---- solve ----------------------------------------------------------------------------- */
+/* b[n] in, x[n] in/out (initial guess in, solution out), ipar[50] in/out, dpar[10] in.
+ * P: n x ipar(18) column-major shadow space for IDR(s) (the shim fills it with RANDOM_NUMBER as
+ * IterativeMethods.F90:1640 does) or NULL for a built-in counter-based generator.
+ * The ILU0 factor is (re)computed here only if none exists for the current values and
+ * precond = ILU0 -- call b200_factorize / b200_set_values to apply IterSolver's recompute policy. */
+int b200_solve(void **handle, const double *b, double *x, int *ipar, double *dpar,
+               const int *method, const int *precond, const double *P);
+/* Same with b, x, P resident in device memory (used to time the solve without PCIe traffic). */
+int b200_solve_device(void **handle, const double *d_b, double *d_x, int *ipar, double *dpar,
+                      const int *method, const int *precond, const double *d_P);
+
+/* IterSolver(A,x,b,Solver): `sif` is the text of the Solver section's linear-system keywords, one
+ * "Keyword = value" per line (case-insensitive, as in a .sif).  solve_count in/out = A%SolveCount.
+ * info_out[0] = HUTI_INFO, info_out[1] = iterations.  Unsupported keywords that would change the
+ * algorithm (complex, ILU order > 0, BILU, ILUT, left preconditioning, user stopping criteria ...)
+ * make it return B200_DECLINED without touching x so that the caller runs Elmer's own path. */
+#define B200_DECLINED 100
+int b200_itersolver(void **handle, const double *b, double *x, const char *sif, int *solve_count,
+                    int *info_out);
+
+/* ---- the callbacks, exposed for parity tests and for user code ----------------------------- */
+int b200_matvec(void **handle, const double *u, double *v);                /* v = A u            */
+int b200_diag_precondition(void **handle, double *u, const double *v);     /* u = D^-1 v         */
+int b200_lu_precondition(void **handle, double *u, const double *v);       /* u = (LU)^-1 v      */
+int b200_dot(void **handle, const int *n, const double *x, const double *y, double *result);
+int b200_nrm2(void **handle, const int *n, const double *x, double *result);
+int b200_get_ilu_values(void **handle, double *ilu_vals);                  /* ILUValues(nnz)     */
+int b200_get_structure(void **handle, int *rows, int *cols, int *diag);    /* device mirror back */
+/* level schedule of the triangular solves: counts[0]=forward levels, [1]=backward levels,
+ * [2]=forward slices, [3]=backward slices.  level_of_row may be NULL, else int[n] forward levels. */
+int b200_get_levels(void **handle, int *counts, int *level_of_row);
+
+/* `Matrix Vector Proc = "libelmer_b200 b200_spmv"` (Load.c:806-824): *spmv is Matrix_t%SpMV,
+ * rows/cols are the raw 1-based arrays, u and v host arrays, reinit is always 0 in the reference.
+ * The structure is uploaded on the first call; values are re-uploaded whenever their host
+ * pointer or a checksum of vals changes (the hook cannot be told), or when *reinit != 0. */
+void b200_spmv(void **spmv, int *n, int *rows, int *cols, double *vals, double *u, double *v, int *reinit);
+
+/* ---- multi-GPU (one process per GPU) ----------------------------------------------------- */
+/* id: 128 bytes. rank 0 calls b200_comm_unique_id and ships the bytes to the other ranks with
+ * whatever the host has (MPI_Bcast in Elmer, torch.distributed in the tests). */
+int b200_comm_unique_id(char *id128);
+int b200_comm_init(void **handle, const int *nranks, const int *rank, const char *id128);
+/* Complete owned rows in continuous global numbering (SParIterSolver.F90:1453-1488): this rank owns
+ * global rows goffset[rank] .. goffset[rank+1]-1 (0-based offsets, goffset[nranks] = gn).  rows[n_own+1],
+ * cols[nnz] hold GLOBAL column ids in index_base numbering, sorted ascending per row.  Builds the
+ * owned x owned block, the ghost block and the halo send/receive lists in the canonical form of
+ * rocalution.cpp:121-156, 222-297 (b200_get_halo_plan reads them back, they must be bit-exact). */
+int b200_set_partition(void **handle, const int *gn, const int *n_own, const int *nnz, const int *rows,
+                       const int *cols, const int *goffset, const int *index_base, const int *ndeg);
+/* sizes[0]=nneigh, [1]=nsend, [2]=nghost; then arrays sized by a first call with NULL pointers. */
+int b200_get_halo_plan(void **handle, int *sizes, int *neigh, int *send_ptr, int *send_idx,
+                       int *recv_ptr, int *ghost_gid);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+/* stats[0] last solve device ms (CUDA events on the solve stream), [1] matvec calls, [2] precond
+ * applications, [3] last factorisation device ms, [4] kernels launched by the last solve,
+ * [5] last solve H2D bytes, [6] D2H bytes, [7] iterations, [8] last SpMV-only device ms (b200_time_matvec),
+ * [9] last LU-solve-only device ms, [10] final residual. */
+int b200_get_stats(void **handle, double *stats16);
+/* Time `reps` back-to-back v = A u launches on resident vectors with CUDA events; ms_out = mean ms. */
+int b200_time_matvec(void **handle, const int *reps, double *ms_out);
+int b200_time_lu_precondition(void **handle, const int *reps, double *ms_out);
+int b200_version(int *major, int *minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELMER_B200_H */

@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer work bit-exact; iteration counts within 2 %; converged
+solution's relative L2 difference <= 10 x Linear System Convergence Tolerance.  The row-wise kernels
+(SpMV, ILU0 factor, triangular solves, Jacobi) reproduce the reference's operation order, so for
+them the bar used here is bit-exact.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-8
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def iters_close(a, b):
+    return abs(a - b) <= max(1, int(np.ceil(0.02 * max(a, b))))
+
+
+@pytest.fixture(scope="module")
+def heat(oracle):
+    A, b = oracle.heat_cube(24, faces=["x0"], source=1.0)
+    A = A.copy()
+    x = np.zeros(A.n)
+    oracle.scale_system(A, b, x)          # Elmer's default Linear System Scaling
+    return A, b
+
+
+@pytest.fixture(scope="module")
+def heat_gpu(b200, heat):
+    A, b = heat
+    M = b200.Matrix()
+    M.set_structure(A.rows, A.cols, A.diag, 1, A.ndeg)
+    M.set_values(A.vals)
+    yield M
+    M.close()
+
+
+def test_structure_mirror_bit_exact(heat, heat_gpu):
+    A, _ = heat
+    r, c, d = heat_gpu.structure()
+    assert np.array_equal(r, A.rows) and np.array_equal(c, A.cols) and np.array_equal(d, A.diag)
+
+
+def test_spmv_bit_exact(oracle, heat, heat_gpu):
+    A, _ = heat
+    rng = np.random.RandomState(1)
+    for _ in range(3):
+        u = rng.standard_normal(A.n)
+        assert np.array_equal(heat_gpu.matvec(u), oracle.matvec(A, u))
+
+
+def test_diag_precondition_bit_exact(oracle, b200):
+    A, b = oracle.heat_cube(10, faces=["x0"])      # unscaled: diagonal != 1
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag); M.set_values(A.vals)
+    v = np.random.RandomState(2).standard_normal(A.n)
+    assert np.array_equal(M.diag_precondition(v), oracle.diag_precond(A, v))
+    M.close()
+
+
+def test_ilu0_factor_bit_exact(oracle, heat, heat_gpu):
+    A, _ = heat
+    heat_gpu.factorize()
+    assert np.array_equal(heat_gpu.ilu_values(), oracle.ilu0(A))
+
+
+def test_lu_solve_bit_exact(oracle, heat, heat_gpu):
+    A, _ = heat
+    ilu = oracle.ilu0(A)
+    v = np.random.RandomState(3).standard_normal(A.n)
+    assert np.array_equal(heat_gpu.lu_precondition(v), oracle.lu_precond(A, ilu, v))
+
+
+def test_levels_of_structured_grid(heat_gpu):
+    # forward level of node (a,b,c) on an x-fastest hex8 grid is a + 2b + 4c
+    n1 = 25
+    lv = heat_gpu.levels(per_row=True)
+    a, b, c = np.meshgrid(np.arange(n1), np.arange(n1), np.arange(n1), indexing="ij")
+    expect = (a + 2 * b + 4 * c).transpose(2, 1, 0).reshape(-1)
+    assert np.array_equal(lv["level"], expect)
+    assert lv["forward"] == 7 * (n1 - 1) + 1
+
+
+def test_dot_and_norm(oracle, heat_gpu):
+    rng = np.random.RandomState(4)
+    x = rng.standard_normal(heat_gpu.n); y = rng.standard_normal(heat_gpu.n)
+    assert abs(heat_gpu.dot(x, y) - oracle.ddot(x, y)) <= 1e-12 * np.linalg.norm(x) * np.linalg.norm(y)
+    assert abs(heat_gpu.nrm2(x) - oracle.dnrm2(x)) <= 1e-13 * oracle.dnrm2(x)
+
+
+@pytest.mark.parametrize("method", ["cg", "bicgstab", "bicgstabl", "gcr", "idrs"])
+@pytest.mark.parametrize("precond", ["none", "diagonal", "ilu0"])
+def test_krylov_parity_heat(oracle, heat, heat_gpu, method, precond):
+    A, b = heat
+    kw = dict(tol=TOL, maxit=2000, bicgstabl_l=4)
+    P = oracle.shadow_space(A.n, 4) if method == "idrs" else None
+    ref = oracle.itersolve(A, b, method=method, precond=precond, P=P, **kw)
+    got = heat_gpu.solve(b, method=method, precond=precond, P=P, **kw)
+    assert ref["info"] == 1 and got["info"] == 1, (ref["info"], got["info"])
+    assert iters_close(got["iters"], ref["iters"]), (got["iters"], ref["iters"])
+    assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    # true residual of the GPU answer
+    r = oracle.matvec(A, got["x"]) - b
+    assert np.linalg.norm(r) / np.linalg.norm(b) <= 20 * TOL
+
+
+def test_call_counts_match_reference(oracle, heat, heat_gpu):
+    A, b = heat
+    ref = oracle.itersolve(A, b, method="bicgstab", precond="ilu0", tol=TOL, maxit=500)
+    got = heat_gpu.solve(b, method="bicgstab", precond="ilu0", tol=TOL, maxit=500)
+    if got["iters"] == ref["iters"]:
+        assert got["stats"]["matvec"] == ref["counts"]["matvec"]
+        assert got["stats"]["pcond"] == ref["counts"]["pcond"]
+
+
+def test_maxiter_and_info_codes(oracle, heat, heat_gpu):
+    A, b = heat
+    for method in ["cg", "bicgstab", "bicgstabl", "gcr", "idrs"]:
+        ref = oracle.itersolve(A, b, method=method, precond="none", tol=1e-14, maxit=3, bicgstabl_l=2)
+        got = heat_gpu.solve(b, method=method, precond="none", tol=1e-14, maxit=3, bicgstabl_l=2)
+        assert got["info"] == ref["info"] == 2, (method, got["info"], ref["info"])
+        assert got["iters"] == ref["iters"], (method, got["iters"], ref["iters"])
+        assert rel_l2(got["x"], ref["x"]) < 1e-10
+
+
+def test_elasticity_ndeg3(oracle, b200):
+    A, b = oracle.elasticity_beam(12, 4, 4, lx=3.0)
+    A = A.copy(); x = np.zeros(A.n); oracle.scale_system(A, b, x)
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 3); M.set_values(A.vals)
+    u = np.random.RandomState(5).standard_normal(A.n)
+    assert np.array_equal(M.matvec(u), oracle.matvec(A, u))          # the 3-accumulator variant, bit for bit
+    M.factorize()
+    assert np.array_equal(M.ilu_values(), oracle.ilu0(A))
+    ref = oracle.itersolve(A, b, method="bicgstabl", precond="ilu0", tol=TOL, maxit=500, bicgstabl_l=4)
+    got = M.solve(b, method="bicgstabl", precond="ilu0", tol=TOL, maxit=500, bicgstabl_l=4)
+    assert got["info"] == ref["info"] == 1
+    assert iters_close(got["iters"], ref["iters"])
+    assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    M.close()
+
+
+def test_nonsymmetric_cavity(oracle, b200):
+    A, b = oracle.cavity_flow(6)
+    A = A.copy(); x = np.zeros(A.n); oracle.scale_system(A, b, x)
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 4); M.set_values(A.vals)
+    u = np.random.RandomState(6).standard_normal(A.n)
+    assert np.array_equal(M.matvec(u), oracle.matvec(A, u))
+    for method in ["gcr", "idrs", "bicgstabl"]:
+        P = oracle.shadow_space(A.n, 4) if method == "idrs" else None
+        ref = oracle.itersolve(A, b, method=method, precond="ilu0", tol=TOL, maxit=1000, bicgstabl_l=4, P=P)
+        got = M.solve(b, method=method, precond="ilu0", tol=TOL, maxit=1000, bicgstabl_l=4, P=P)
+        assert got["info"] == ref["info"], (method, got["info"], ref["info"])
+        if ref["info"] == 1:
+            assert iters_close(got["iters"], ref["iters"]), (method, got["iters"], ref["iters"])
+            assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    M.close()
+
+
+def test_testmat_known_answer(oracle, b200):
+    """fhutiter/examples/ex1/testmat(.out): committed copy under tests/golden/."""
+    import os
+    import scipy.sparse as sp
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    d = np.loadtxt(os.path.join(g, "huti_ex1_testmat.txt"))
+    xref = np.loadtxt(os.path.join(g, "huti_ex1_testmat_out.txt"))[:, 1]
+    Ms = sp.coo_matrix((d[:, 2], (d[:, 0].astype(int) - 1, d[:, 1].astype(int) - 1)), shape=(100, 100)).tocsr()
+    A = oracle.CRS.from_scipy(Ms)
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag); M.set_values(A.vals)
+    for method in ["bicgstabl", "gcr", "idrs"]:
+        got = M.solve(np.ones(100), method=method, precond="none", tol=1e-10, maxit=500, bicgstabl_l=4)
+        assert got["info"] == 1
+        assert np.abs(got["x"] - xref).max() < 1e-6
+    M.close()
+
+
+def test_spmv_hook_matches_load_c_signature(oracle, b200, heat):
+    A, _ = heat
+    slot = C.c_void_p(None)
+    u = np.random.RandomState(7).standard_normal(A.n)
+    v = b200.spmv_hook(slot, A.rows, A.cols, A.vals, u)
+    assert np.array_equal(v, oracle.matvec(A, u))
+    vals2 = A.vals * 2.0                       # the hook is never told that Values changed
+    v2 = b200.spmv_hook(slot, A.rows, A.cols, vals2, u)
+    assert np.array_equal(v2, 2.0 * v)
+    b200.lib().b200_destroy(C.byref(slot))
+
+
+def test_itersolver_keywords(oracle, heat, heat_gpu):
+    A, b = heat
+    sif = """
+      Linear System Solver = Iterative
+      Linear System Iterative Method = BiCGStab
+      Linear System Preconditioning = ILU0
+      Linear System Max Iterations = 500
+      Linear System Convergence Tolerance = 1.0e-8
+      Linear System Residual Output = 0
+    """
+    got = heat_gpu.itersolver(b, None, sif, solve_count=0)
+    ref = oracle.itersolve(A, b, method="bicgstab", precond="ilu0", tol=1e-8, maxit=500)
+    assert got is not None and got["info"] == 1 and got["solve_count"] == 1
+    assert iters_close(got["iters"], ref["iters"])
+    assert rel_l2(got["x"], ref["x"]) <= 1e-7
+    declined = heat_gpu.itersolver(b, None, sif.replace("ILU0", "ILU1"), 0)
+    assert declined is None
+    assert heat_gpu.itersolver(b, None, sif.replace("BiCGStab", "GMRES"), 0) is None
+
+
+def test_empty_and_tiny_systems(oracle, b200):
+    import scipy.sparse as sp
+    for n in [1, 2, 33]:
+        Ms = sp.diags([np.full(n, 4.0)] + ([np.full(n - 1, -1.0)] * 2 if n > 1 else []), [0] + ([-1, 1] if n > 1 else [])).tocsr()
+        A = oracle.CRS.from_scipy(Ms)
+        M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag); M.set_values(A.vals)
+        b = np.arange(1, n + 1, dtype=float)
+        for method in ["cg", "bicgstab"]:
+            ref = oracle.itersolve(A, b, method=method, precond="ilu0", tol=1e-10, maxit=50)
+            got = M.solve(b, method=method, precond="ilu0", tol=1e-10, maxit=50)
+            assert got["info"] == ref["info"]
+            assert rel_l2(got["x"], ref["x"]) < 1e-9
+        M.close()
