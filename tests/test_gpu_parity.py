@@ -121,9 +121,10 @@ def test_call_counts_match_reference(oracle, heat, heat_gpu):
 
 def test_maxiter_and_info_codes(oracle, heat, heat_gpu):
     A, b = heat
+    P = oracle.shadow_space(A.n, 4)
     for method in ["cg", "bicgstab", "bicgstabl", "gcr", "idrs"]:
-        ref = oracle.itersolve(A, b, method=method, precond="none", tol=1e-14, maxit=3, bicgstabl_l=2)
-        got = heat_gpu.solve(b, method=method, precond="none", tol=1e-14, maxit=3, bicgstabl_l=2)
+        ref = oracle.itersolve(A, b, method=method, precond="none", tol=1e-14, maxit=3, bicgstabl_l=2, P=P)
+        got = heat_gpu.solve(b, method=method, precond="none", tol=1e-14, maxit=3, bicgstabl_l=2, P=P)
         assert got["info"] == ref["info"] == 2, (method, got["info"], ref["info"])
         assert got["iters"] == ref["iters"], (method, got["iters"], ref["iters"])
         assert rel_l2(got["x"], ref["x"]) < 1e-10
