@@ -79,6 +79,14 @@ def exported_symbols():
     return sorted(line.split()[-1] for line in out.splitlines() if " T " in line)
 
 
+def header_symbols():
+    """Entry points declared in include/elmer_b200.h."""
+    import re
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
