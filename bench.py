@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- Krylov throughput of the B200 linear-solve path on BASELINE.json's workloads.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                    (the CPU restatement of Elmer's path, host cores)
+
+Workload (config.workload):
+  N = 1 : BASELINE.json configs[1]: steady heat equation, unit cube, 200^3 hex8 (8,120,601 dofs, 217,081,801 nnz),
+          Elmer's default diagonal scaling, BiCGStab + ILU0, tol 1e-8, fp64.
+  N > 1 : the same problem weak-scaled: 200 x 200 x 200*N elements, slab-partitioned along z (ElmerGrid
+          `-partition 1 1 N`), one slab of ~8.1M dofs per GPU, block-Jacobi ILU0 as in Elmer's MPI path.
+
+A step is one IterSolver call on resident data: x = 0, BiCGStab+ILU0 to convergence.  `value` is
+Krylov iterations x global dofs / second (so that it aggregates over GPUs under weak scaling);
+`iters_per_s` is the plain BASELINE.json figure.  The ILU0 factorisation is done (and timed, `factor_ms`)
+once per step outside the solve timer, for both arms.  `e2e` goes through b200_solve with pinned HOST
+b/x (H2D + D2H inside the timed region).  The matrix (2.6 GB) is far larger than L2 (126 MB), so no
+flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOL = 1e-8
+MAXIT = 2000
+
+
+# ------------------------------------------------------------------------------------------------
+def spmv_bytes(n, nnz):
+    """CRS-equivalent algorithmic bytes of one fp64 SpMV."""
+    return 12 * nnz + 20 * n + 4
+
+
+def lu_bytes(n, nnz):
+    """one ILU0 application (forward + backward sweep)."""
+    return 12 * nnz + 4 * (n + 1) + 4 * n + 24 * n
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def make_problem(args, rank, nranks, allreduce_sum=None):
+    """Scaled system of this rank.  Returns dict(A=CRS local, b, gn, goffset, cols_global or None)."""
+    from elmerfem_b200 import synth
+    ne = args.ne
+    if nranks == 1:
+        A, b = synth.workload("heat", ne)
+        return dict(A=A, b=b, gn=A.n, part=None, name="heat_cube_%d^3_hex8" % ne)
+    part = synth.heat_slab(ne, ne, ne * nranks, rank, nranks, allreduce_sum=allreduce_sum)
+    return dict(A=None, b=part["b"], gn=part["gn"], part=part, name="heat_slab_%dx%dx%d_hex8_z-slabs" % (ne, ne, ne * nranks))
+
+
+def run_b200(args):
+    import torch
+    import elmerfem_b200 as B
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def allsum(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    prob = make_problem(args, rank, world, allsum if world > 1 else None)
+    M = B.Matrix()
+    t0 = time.time()
+    if world == 1:
+        A = prob["A"]
+        M.set_structure(A.rows, A.cols, A.diag, 1, A.ndeg)
+        n, nnz = A.n, A.nnz
+        vals = A.vals
+    else:
+        ids = [B.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        M.comm_init(world, rank, ids[0])
+        p = prob["part"]
+        M.set_partition(p["gn"], p["rows"], p["cols"], p["goffset"], 1, 1)
+        n, nnz = p["rows"].size - 1, p["cols"].size
+        vals = p["vals"]
+    t_struct = time.time() - t0
+    t0 = time.time()
+    M.set_values(vals)
+    t_upload = time.time() - t0
+    gn = prob["gn"]
+    b_host = torch.from_numpy(np.ascontiguousarray(prob["b"])).pin_memory()
+    x_host = torch.zeros(n, dtype=torch.float64).pin_memory()
+    nvec = M.vec_len()
+    d_b = torch.zeros(nvec, dtype=torch.float64, device="cuda")
+    d_b[:n].copy_(b_host)
+    d_x = torch.zeros(nvec, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    kw = dict(method="bicgstab", precond="ilu0", tol=TOL, maxit=MAXIT)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        M.factorize()
+        d_x.zero_()
+        torch.cuda.synchronize()
+        r = M.solve_device(d_b.data_ptr(), d_x.data_ptr(), **kw)
+        return r
+
+    def step_e2e():
+        x_host.zero_()
+        t = time.perf_counter()
+        r = M.solve_host(b_host.data_ptr(), x_host.data_ptr(), **kw)      # b200_solve: H2D b, x; solve; D2H x
+        return r, time.perf_counter() - t
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        r = step_resident()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    # ---- timed: K steps, device time of the solve (CUDA events on the solve stream, inside the library)
+    barrier()
+    wall0 = time.perf_counter()
+    solve_ms, factor_ms, iters, launches = 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        r = step_resident()
+        st = r["stats"]
+        solve_ms += st["solve_ms"]; factor_ms += st["factor_ms"]; iters += r["iters"]; launches += st["launches"] + st["factor_launches"]
+        assert r["info"] == 1, "solve did not converge: HUTI_INFO=%d" % r["info"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    # ---- e2e through the host-buffer entry point
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    e2e_s, e2e_iters, h2d, d2h = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        r2, dt = step_e2e()
+        e2e_s += dt; e2e_iters += r2["iters"]; h2d = r2["stats"]["h2d"]; d2h = r2["stats"]["d2h"] + 0
+        assert r2["info"] == 1
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    # ---- kernel rooflines, measured live with CUDA events on the solve stream
+    spmv_ms = M.time_matvec(20)
+    lu_ms = M.time_lu(10)
+
+    def maxr(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumr(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    solve_ms = maxr(solve_ms); factor_ms = maxr(factor_ms); e2e_s = maxr(e2e_s); spmv_ms_max = maxr(spmv_ms); lu_ms_max = maxr(lu_ms)
+    launches = int(sumr(launches)); nnz_tot = sumr(float(nnz)); h2d = int(sumr(h2d)); d2h = int(sumr(d2h))
+    res_true = None
+    if world == 1:
+        # true residual of the answer on the device data: one more SpMV, checked on the host
+        xs = d_x[:n].cpu().numpy()
+        ax = M.matvec(xs)
+        res_true = float(np.linalg.norm(ax - prob["b"]) / np.linalg.norm(prob["b"]))
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        its = iters / (solve_ms / 1e3)
+        e2e_its = e2e_iters / e2e_s
+        bs, bl = spmv_bytes(n, nnz), lu_bytes(n, nnz)
+        spmv_gbs = bs / (spmv_ms_max * 1e-3) / 1e9
+        lu_gbs = bl / (lu_ms_max * 1e-3) / 1e9
+        ipi = iters / args.steps
+        # share of the solve spent in each kernel family (per iteration: 3 SpMV + 2 LU applications)
+        share_spmv = 3 * spmv_ms_max * ipi / (solve_ms / args.steps)
+        share_lu = 2 * lu_ms_max * ipi / (solve_ms / args.steps)
+        dominant = "lu" if share_lu > share_spmv else "spmv"
+        roof = {"spmv": {"kernel": "k_spmv_sell", "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
+                         "traffic": None, "bytes_per_launch": bs, "ms_per_launch": spmv_ms_max, "share_of_step": share_spmv, "peak_source": peak_src},
+                "lu": {"kernel": "k_sptrsv (L then U sweep)", "bound": "hbm", "achieved": lu_gbs, "peak": peak, "unit": "GB/s", "frac": lu_gbs / peak,
+                       "traffic": None, "bytes_per_launch": bl, "ms_per_launch": lu_ms_max, "share_of_step": share_lu, "peak_source": peak_src}}
+        out = {
+            "metric": "fp64 Krylov iterations/s x global Mdof (BiCGStab+ILU0, heat 200^3 per GPU); iters_per_s and spmv_gbs beside it",
+            "value": its * gn / 1e6, "unit": "Mdof*iterations/s",
+            "iters_per_s": its, "spmv_gbs": spmv_gbs * world, "spmv_frac_of_hbm_peak": spmv_gbs / peak,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": solve_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": prob["name"] + ", BiCGStab+ILU0, tol 1e-8, Linear System Scaling on", "global_dofs": int(gn),
+                       "global_nnz": int(nnz_tot), "dofs_per_gpu": int(n), "iterations_per_solve": ipi,
+                       "l2": "inputs (2.6 GB matrix per GPU) larger than L2; no flush", "parallelism": "row partition, z-slabs x%d" % world},
+            "roofline": roof[dominant], "roofline_spmv": roof["spmv"], "roofline_lu": roof["lu"],
+            "e2e": {"value": e2e_its * gn / 1e6, "unit": "Mdof*iterations/s", "iters_per_s": e2e_its, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches, "factor_ms": factor_ms / args.steps, "upload_values_s": t_upload, "structure_s": t_struct,
+            "iters_per_s_incl_factor": iters / ((solve_ms + factor_ms) / 1e3), "wall_s_timed_region": wall,
+            "true_residual": res_true, "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(prob, budget_s=args.cpu_budget)
+    M.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(O, A, b, ilu, maxit):
+    t = time.perf_counter()
+    r = O.itersolve(A, b, method="bicgstab", precond="ilu0", ilu=ilu, tol=TOL, maxit=maxit)
+    return r, time.perf_counter() - t
+
+
+def cpu_baseline(prob, budget_s=20.0):
+    """The oracle (literal C++ restatement of Elmer's CPU path: OpenMP SpMV/vector loops, serial ILU0
+    solves exactly as the reference) on this box's host cores, on a bounded sample of the same system:
+    the first m BiCGStab+ILU0 iterations."""
+    from oracle import oracle as O
+    A, b = prob["A"], prob["b"]
+    cores = O.max_threads()
+    O.set_threads(cores)
+    t = time.perf_counter(); ilu = O.ilu0(A); t_f = time.perf_counter() - t
+    r, dt = cpu_sample(O, A, b, ilu, 2)
+    m = int(max(2, min(MAXIT, budget_s / (dt / 2))))
+    r, dt = cpu_sample(O, A, b, ilu, m)
+    its = r["iters"] if r["info"] == 1 else min(r["iters"], m)
+    return {"value": its / dt * A.n / 1e6, "unit": "Mdof*iterations/s", "iters_per_s": its / dt, "cores": cores, "kind": "port",
+            "sample": "first %d BiCGStab+ILU0 iterations of the same %d-dof system (%.1f s); ILU0 factor %.2f s not included" % (its, A.n, dt, t_f),
+            "factor_s": t_f}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    prob = make_problem(args, 0, 1)
+    A, b = prob["A"], prob["b"]
+    cores = O.max_threads()
+    O.set_threads(cores)
+    t = time.perf_counter(); ilu = O.ilu0(A); t_f = time.perf_counter() - t
+    r, dt = cpu_sample(O, A, b, ilu, 2)
+    per_it = dt / 2
+    total = args.steps + args.warmup
+    m = int(max(2, min(MAXIT, args.ref_budget / total / per_it)))
+    for _ in range(args.warmup):
+        cpu_sample(O, A, b, ilu, m)
+    T, its = 0.0, 0
+    for _ in range(args.steps):
+        r, dt = cpu_sample(O, A, b, ilu, m)
+        T += dt; its += min(r["iters"], m)
+    v = its / T
+    sample = "each step = first %d BiCGStab+ILU0 iterations of the same %d-dof system; ILU0 factor (%.2f s) outside the timer as in the GPU arm" % (m, A.n, t_f)
+    out = {"impl": "reference", "metric": "fp64 Krylov iterations/s x global Mdof (BiCGStab+ILU0, heat 200^3 per GPU); iters_per_s and spmv_gbs beside it",
+           "value": v * A.n / 1e6, "unit": "Mdof*iterations/s", "iters_per_s": v, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": T / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": prob["name"] + ", BiCGStab+ILU0, tol 1e-8, Linear System Scaling on", "global_dofs": int(A.n), "global_nnz": int(A.nnz)},
+           "cpu_baseline": {"value": v * A.n / 1e6, "unit": "Mdof*iterations/s", "iters_per_s": v, "cores": cores, "kind": "port", "sample": sample, "factor_s": t_f},
+           "e2e": {"value": v * A.n / 1e6, "unit": "Mdof*iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference = C++ restatement of Elmer's CPU Krylov path (no Fortran compiler in this image); single-process: the reference arm does not scale with --gpus"}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ne", type=int, default=200, help="elements per cube edge (200 = BASELINE configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--ref-budget", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

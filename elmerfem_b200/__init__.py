@@ -62,7 +62,7 @@ def lib():
         "b200_set_partition": [vpp, ip, ip, ip, ip, ip, ip, ip, ip],
         "b200_get_halo_plan": [vpp, ip, ip, ip, ip, ip, ip],
         "b200_get_stats": [vpp, dp], "b200_time_matvec": [vpp, ip, dp], "b200_time_lu_precondition": [vpp, ip, dp],
-        "b200_version": [ip, ip],
+        "b200_version": [ip, ip], "b200_vec_len": [vpp, C.POINTER(C.c_longlong)],
     }
     for name, args in sigs.items():
         f = getattr(L, name)
@@ -187,6 +187,21 @@ class Matrix:
         _check(rc, "b200_solve_device")
         return dict(info=int(ipar[29]), iters=int(ipar[30]), residual=float(dpar[9]), stats=self.stats())
 
+    def solve_host(self, b_ptr, x_ptr, method="bicgstab", precond="none", P_ptr=None, **kw):
+        """b200_solve on raw HOST addresses (e.g. pinned buffers): x in/out in place."""
+        ipar, dpar = fill_ipar_dpar(self.n, method, **kw)
+        f = lib().b200_solve
+        dpv = C.POINTER(C.c_double)
+        rc = f(self.handle, C.cast(C.c_void_p(b_ptr), dpv), C.cast(C.c_void_p(x_ptr), dpv), _ip(ipar), _dp(dpar),
+               _i(METHODS[method]), _i(PRECONDS[precond]), C.cast(C.c_void_p(P_ptr), dpv))
+        _check(rc, "b200_solve")
+        return dict(info=int(ipar[29]), iters=int(ipar[30]), residual=float(dpar[9]), stats=self.stats())
+
+    def vec_len(self):
+        v = C.c_longlong(0)
+        _check(lib().b200_vec_len(self.handle, C.byref(v)), "b200_vec_len")
+        return v.value
+
     def itersolver(self, b, x0, sif, solve_count=0):
         """IterSolver(A,x,b,Solver) through the keyword front-end; returns None when DECLINED."""
         b = np.ascontiguousarray(b, dtype=np.float64)
@@ -253,7 +268,7 @@ class Matrix:
         _check(lib().b200_get_stats(self.handle, _dp(s)), "b200_get_stats")
         return dict(solve_ms=s[0], matvec=int(s[1]), pcond=int(s[2]), factor_ms=s[3], launches=int(s[4]), h2d=int(s[5]),
                     d2h=int(s[6]), iters=int(s[7]), spmv_ms=s[8], lu_ms=s[9], residual=s[10], sell_entries=int(s[11]),
-                    levels_f=int(s[12]), levels_b=int(s[13]))
+                    levels_f=int(s[12]), levels_b=int(s[13]), factor_launches=int(s[14]))
 
     def time_matvec(self, reps=20):
         ms = C.c_double(0)

@@ -126,7 +126,7 @@ struct Handle {
   Halo *halo = nullptr; void *nccl = nullptr; int nranks = 1, rank = 0; long long gn = 0;
   // stats
   double st_solve_ms = 0, st_factor_ms = 0, st_spmv_ms = 0, st_lu_ms = 0, st_resid = 0;
-  long long st_matvec = 0, st_pcond = 0, st_launch = 0, st_launch_last = 0, st_h2d = 0, st_d2h = 0, st_iters = 0;
+  long long st_matvec = 0, st_pcond = 0, st_launch = 0, st_launch_last = 0, st_h2d = 0, st_d2h = 0, st_iters = 0, st_factor_launch = 0;
   // tuning (env overridable)
   int spmv_blocks = 0, tri_blocks_per_sm = 0, blas_blocks = NUM_SMS * 8;
   int grid_ilu = 0, grid_tri_l = 0, grid_tri_u = 0;   // co-resident grid sizes (occupancy x SMs)

@@ -154,6 +154,7 @@ void ilu0_factor(Handle &h) {
   h.st_factor_ms = ms;
   B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "ILU0 factorisation: dependency wait timed out");
   h.ilu_valid = true; h.ilu_exists = true;
+  h.st_factor_launch = h.n > 0 ? 5 : 0;   // factor, invert diag, 2 x SELL refresh, diag gather
 }
 
 // ---------------------------------------------------------------------------------------------

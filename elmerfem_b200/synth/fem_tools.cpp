@@ -1,6 +1,6 @@
-// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
-//
-// Synthetic-input generator for tests and bench.py: structured hex8 meshes numbered exactly as
+// HOST TOOL, not on the solve path: synthetic-input generator for tests and bench.py (the workloads
+// BASELINE.json names are "synthetic ElmerGrid-generated meshes").  It produces what Elmer would hand
+// to IterSolver: structured hex8 meshes numbered exactly as
 // ElmerGrid numbers a one-subcell .grd with "Numbering = Horizontal" (SURVEY.md Appendix A,
 // checked against the reference's own ElmerGrid output in tests/test_meshgen_vs_elmergrid.py),
 // the CRS structure Elmer's CreateMatrix produces for nodal dofs without bandwidth optimisation
@@ -289,6 +289,29 @@ void fem_dirichlet(int n, const int *rows, const int *cols, const int *diag, dou
     vals[diag[i] - 1] = s;
     b[i] = s * dv[i];
   }
+}
+
+// Linear System Scaling (default TRUE, SolverUtils.F90:14492-14498): what ScaleLinearSystemDiagonal
+// (SolverUtils.F90:12976-13213) leaves in A, b before IterSolver is called, for a real system without
+// constraints: D = 1/sqrt(|a_ii|), A <- D A D, b <- D b / ||D b||.  Returns ||D b||; D (times that norm)
+// is kept so that the caller can scale x back.  The drop-in never runs this: Elmer does it on the host.
+double fem_scale_system(int n, const int *rows, const int *cols, const int *diag, double *vals, double *b, double *D) {
+  const double tiny = 2.2250738585072014e-308;
+#pragma omp parallel for
+  for (int i = 0; i < n; ++i) {
+    double d = std::fabs(vals[diag[i] - 1]);
+    if (d <= tiny) { d = 0; for (int p = rows[i] - 1; p < rows[i + 1] - 1; ++p) d += std::fabs(vals[p]); }
+    D[i] = d > tiny ? 1.0 / std::sqrt(d) : 1.0;
+  }
+#pragma omp parallel for
+  for (int i = 0; i < n; ++i)
+    for (int p = rows[i] - 1; p < rows[i + 1] - 1; ++p) vals[p] = vals[p] * (D[i] * D[cols[p] - 1]);
+  double s = 0;
+  for (int i = 0; i < n; ++i) { b[i] = b[i] * D[i]; s += b[i] * b[i]; }
+  double bnorm = std::sqrt(s);
+  if (bnorm < std::sqrt(tiny)) return 1.0;
+  for (int i = 0; i < n; ++i) { D[i] = D[i] * bnorm; b[i] = b[i] / bnorm; }
+  return bnorm;
 }
 
 }  // extern "C"

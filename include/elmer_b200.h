@@ -146,12 +146,16 @@ int b200_get_halo_plan(void **handle, int *sizes, int *neigh, int *send_ptr, int
 /* stats[0] last solve device ms (CUDA events on the solve stream), [1] matvec calls, [2] precond
  * applications, [3] last factorisation device ms, [4] kernels launched by the last solve,
  * [5] last solve H2D bytes, [6] D2H bytes, [7] iterations, [8] last SpMV-only device ms (b200_time_matvec),
- * [9] last LU-solve-only device ms, [10] final residual. */
+ * [9] last LU-solve-only device ms, [10] final residual,
+ * [11] SELL entries stored, [12]/[13] forward/backward levels, [14] kernels launched by the last factorisation. */
 int b200_get_stats(void **handle, double *stats16);
 /* Time `reps` back-to-back v = A u launches on resident vectors with CUDA events; ms_out = mean ms. */
 int b200_time_matvec(void **handle, const int *reps, double *ms_out);
 int b200_time_lu_precondition(void **handle, const int *reps, double *ms_out);
 int b200_version(int *major, int *minor);
+/* Length every device vector handed to b200_solve_device must have: n owned rows + ghost entries
+ * received from the neighbours (0 on an unpartitioned handle). */
+int b200_vec_len(void **handle, long long *len);
 
 #ifdef __cplusplus
 }

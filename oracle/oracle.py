@@ -3,7 +3,7 @@
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) import this.
 Nothing under elmerfem_b200/ does.
 
-The Python side only marshals arrays; every numerical loop is in elmer_oracle.cpp / fem_tools.cpp,
+The Python side only marshals arrays; every numerical loop is in elmer_oracle.cpp,
 each citing the reference file:line it restates.
 """
 import ctypes as C
@@ -51,12 +51,6 @@ def lib():
     L.orc_backscale_system.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, C.c_double]
     L.orc_set_threads.argtypes = [C.c_int]
     L.orc_max_threads.restype = C.c_int
-    L.fem_grid_hex8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _ip]
-    L.fem_crs_count.restype = C.c_long
-    L.fem_crs_count.argtypes = [C.c_int, C.c_long, _ip, C.c_int, C.c_int, _ip]
-    L.fem_crs_fill.argtypes = [C.c_int, C.c_long, _ip, C.c_int, C.c_int, _ip, _ip, _ip]
-    L.fem_assemble.argtypes = [C.c_int, _dp, C.c_int, C.c_long, _ip, _dp, C.c_int, _ip, _ip, _dp, _dp, C.c_int]
-    L.fem_dirichlet.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, C.c_int, _ip, _dp, C.c_int]
     _LIB = L
     return L
 
@@ -69,40 +63,8 @@ def max_threads():
     return lib().orc_max_threads()
 
 
-class CRS:
-    """Elmer Matrix_t subset (Types.F90:193-283): 1-based int32 Rows/Cols/Diag, fp64 Values."""
-
-    def __init__(self, rows, cols, diag, vals, ndeg=1):
-        self.rows = np.ascontiguousarray(rows, dtype=np.int32)
-        self.cols = np.ascontiguousarray(cols, dtype=np.int32)
-        self.diag = np.ascontiguousarray(diag, dtype=np.int32)
-        self.vals = np.ascontiguousarray(vals, dtype=np.float64)
-        self.ndeg = int(ndeg)
-        self.n = self.rows.size - 1
-        self.nnz = self.cols.size
-
-    def copy(self):
-        return CRS(self.rows, self.cols, self.diag, self.vals.copy(), self.ndeg)
-
-    def to_scipy(self):
-        import scipy.sparse as sp
-        return sp.csr_matrix((self.vals, self.cols - 1, self.rows - 1), shape=(self.n, self.n))
-
-    @staticmethod
-    def from_scipy(M, ndeg=1):
-        M = M.tocsr()
-        M.sort_indices()
-        n = M.shape[0]
-        rows = (M.indptr + 1).astype(np.int32)
-        cols = (M.indices + 1).astype(np.int32)
-        diag = np.zeros(n, dtype=np.int32)
-        for i in range(n):
-            seg = cols[rows[i] - 1:rows[i + 1] - 1]
-            k = np.searchsorted(seg, i + 1)
-            if k >= seg.size or seg[k] != i + 1:
-                raise ValueError("row %d has no diagonal entry" % (i + 1))
-            diag[i] = rows[i] + k
-        return CRS(rows, cols, diag, M.data.astype(np.float64), ndeg)
+from elmerfem_b200.synth import (CRS, grid_hex8, crs_structure, assemble, dirichlet, boundary_nodes,   # noqa: E402,F401
+                                 heat_cube, elasticity_beam, cavity_flow)
 
 
 # ------------------------------------------------------------------ kernels
@@ -224,109 +186,3 @@ def solve_linear_system(A, b, x0=None, scaling=True, **kw):
     r["x"] = x
     r["norm"] = float(np.sqrt(np.sum(x * x) / A.n))   # ComputeNorm, SolverUtils.F90:10290
     return r
-
-
-# ------------------------------------------------------------------ synthetic problems
-def grid_hex8(ex, ey, ez, lx=1.0, ly=1.0, lz=1.0):
-    nn = (ex + 1) * (ey + 1) * (ez + 1)
-    ne = ex * ey * ez
-    xyz = np.empty(3 * nn)
-    elems = np.empty(8 * ne, dtype=np.int32)
-    lib().fem_grid_hex8(ex, ey, ez, lx, ly, lz, xyz, elems)
-    return xyz.reshape(nn, 3), elems.reshape(ne, 8)
-
-
-def crs_structure(nn, elems, ndof):
-    elems = np.ascontiguousarray(elems, dtype=np.int32)
-    ne, nen = elems.shape
-    n = nn * ndof
-    rows = np.empty(n + 1, dtype=np.int32)
-    nnz = lib().fem_crs_count(nn, ne, elems.reshape(-1), nen, ndof, rows)
-    if nnz < 0:
-        raise OverflowError("nnz exceeds int32")
-    cols = np.empty(nnz, dtype=np.int32)
-    diag = np.empty(n, dtype=np.int32)
-    lib().fem_crs_fill(nn, ne, elems.reshape(-1), nen, ndof, rows, cols, diag)
-    return rows, cols, diag
-
-
-def assemble(kind, par, xyz, elems, ndof, rows, cols, uniform=False):
-    nn = xyz.shape[0]
-    vals = np.empty(cols.size)
-    rhs = np.empty(nn * ndof)
-    p = np.zeros(8)
-    p[:len(par)] = par
-    elems = np.ascontiguousarray(elems, dtype=np.int32)
-    lib().fem_assemble(kind, p, nn, elems.shape[0], elems.reshape(-1), np.ascontiguousarray(xyz).reshape(-1), ndof,
-                       rows, cols, vals, rhs, 1 if uniform else 0)
-    return vals, rhs
-
-
-def dirichlet(A, b, dofs, values, symmetric=False):
-    dofs = np.ascontiguousarray(dofs, dtype=np.int32)
-    values = np.ascontiguousarray(np.broadcast_to(values, dofs.shape), dtype=np.float64)
-    lib().fem_dirichlet(A.n, A.rows, A.cols, A.diag, A.vals, b, dofs.size, dofs, values, 1 if symmetric else 0)
-
-
-def boundary_nodes(ex, ey, ez, faces="all"):
-    """1-based node ids on the requested faces of the structured grid ('all' or subset of x0,x1,y0,y1,z0,z1)."""
-    nx, ny, nz = ex + 1, ey + 1, ez + 1
-    ids = np.arange(nx * ny * nz, dtype=np.int64).reshape(nz, ny, nx)
-    sel = np.zeros_like(ids, dtype=bool)
-    f = ["x0", "x1", "y0", "y1", "z0", "z1"] if faces == "all" else list(faces)
-    if "x0" in f: sel[:, :, 0] = True
-    if "x1" in f: sel[:, :, -1] = True
-    if "y0" in f: sel[:, 0, :] = True
-    if "y1" in f: sel[:, -1, :] = True
-    if "z0" in f: sel[0, :, :] = True
-    if "z1" in f: sel[-1, :, :] = True
-    return (ids[sel] + 1).astype(np.int32)
-
-
-def heat_cube(ne, faces="all", source=1.0, symmetric=False, dims=None):
-    """Configs 1/2: steady heat/Poisson on the unit cube, ne^3 hex8, u=0 on `faces`, f=source."""
-    ex, ey, ez = dims if dims is not None else (ne, ne, ne)
-    xyz, elems = grid_hex8(ex, ey, ez)
-    rows, cols, diag = crs_structure(xyz.shape[0], elems, 1)
-    vals, rhs = assemble(0, [source], xyz, elems, 1, rows, cols, uniform=True)
-    A = CRS(rows, cols, diag, vals, 1)
-    dirichlet(A, rhs, boundary_nodes(ex, ey, ez, faces), 0.0, symmetric)
-    return A, rhs
-
-
-def elasticity_beam(ex, ey, ez, lx=8.0, ly=1.0, lz=1.0, E=1e9, nu=0.3, load=(0.0, 0.0, -1e4)):
-    """Configs 3/5: isotropic linear elasticity, 3 interleaved dofs/node, x=0 end clamped, body load."""
-    xyz, elems = grid_hex8(ex, ey, ez, lx, ly, lz)
-    rows, cols, diag = crs_structure(xyz.shape[0], elems, 3)
-    vals, rhs = assemble(1, [E, nu, load[0], load[1], load[2]], xyz, elems, 3, rows, cols, uniform=True)
-    A = CRS(rows, cols, diag, vals, 3)
-    nodes = boundary_nodes(ex, ey, ez, ["x0"]).astype(np.int64)
-    dofs = np.concatenate([3 * (nodes - 1) + c + 1 for c in range(3)]).astype(np.int32)
-    dofs.sort()
-    dirichlet(A, rhs, dofs, 0.0, False)
-    return A, rhs
-
-
-def cavity_flow(ne, visc=0.01, tau=None):
-    """Config 4: nonsymmetric 4-dof/node (u,v,w,p) Picard-linearised stabilised system on the unit cube;
-    velocity fixed on all walls (lid z=1 moving in x), pressure pinned at node 1."""
-    xyz, elems = grid_hex8(ne, ne, ne)
-    rows, cols, diag = crs_structure(xyz.shape[0], elems, 4)
-    if tau is None:
-        tau = 0.5 / ne
-    vals, rhs = assemble(2, [visc, tau, 0.0], xyz, elems, 4, rows, cols, uniform=False)
-    A = CRS(rows, cols, diag, vals, 4)
-    wall = boundary_nodes(ne, ne, ne, "all").astype(np.int64)
-    lid = set(boundary_nodes(ne, ne, ne, ["z1"]).tolist())
-    dofs, dv = [], []
-    for nd in wall:
-        for c in range(3):
-            dofs.append(4 * (nd - 1) + c + 1)
-            dv.append(1.0 if (c == 0 and nd in lid) else 0.0)
-    dofs.append(4)
-    dv.append(0.0)
-    dofs = np.array(dofs, dtype=np.int32)
-    dv = np.array(dv)
-    o = np.argsort(dofs)
-    dirichlet(A, rhs, dofs[o], dv[o], False)
-    return A, rhs
