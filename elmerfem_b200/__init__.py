@@ -42,7 +42,7 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise B200Error("libelmer_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                         "there is no CPU fallback")
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(LIB_PATH)
     vpp = C.POINTER(C.c_void_p)
     ip = C.POINTER(C.c_int)
     dp = C.POINTER(C.c_double)
@@ -62,6 +62,7 @@ def lib():
         "b200_set_partition": [vpp, ip, ip, ip, ip, ip, ip, ip, ip],
         "b200_get_halo_plan": [vpp, ip, ip, ip, ip, ip, ip],
         "b200_get_stats": [vpp, dp], "b200_time_matvec": [vpp, ip, dp], "b200_time_lu_precondition": [vpp, ip, dp],
+        "b200_partition_send_lists": [ip] * 10, "b200_partition_split": [ip] * 14,
         "b200_version": [ip, ip], "b200_vec_len": [vpp, C.POINTER(C.c_longlong)],
     }
     for name, args in sigs.items():
@@ -318,3 +319,32 @@ def spmv_hook(slot, rows, cols, vals, u, reinit=0):
     v = np.empty(n)
     lib().b200_spmv(C.byref(slot), _i(n), _ip(rows), _ip(cols), _dp(vals), _dp(u), _dp(v), _i(reinit))
     return v
+
+
+def partition_send_lists(gn, rows, cols_global, goffset, rank, index_base=1):
+    """Host-only: per-destination send lists (global 0-based row ids) of this rank, canonical form of
+    rocalution.cpp:121-156.  Returns (counts[nranks], gids concatenated by ascending rank)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32); cols = np.ascontiguousarray(cols_global, dtype=np.int32)
+    goffset = np.ascontiguousarray(goffset, dtype=np.int32)
+    nr = goffset.size - 1
+    cnt = np.zeros(nr, dtype=np.int32)
+    args = (_i(gn), _i(rows.size - 1), _ip(rows), _ip(cols), _ip(goffset), _i(index_base), _i(nr), _i(rank))
+    _check(lib().b200_partition_send_lists(*args, _ip(cnt), None), "b200_partition_send_lists")
+    gid = np.zeros(max(int(cnt.sum()), 1), dtype=np.int32)
+    _check(lib().b200_partition_send_lists(*args, _ip(cnt), _ip(gid)), "b200_partition_send_lists")
+    return cnt, gid[:int(cnt.sum())]
+
+
+def partition_split(rows, cols_global, lo, hi, ghost_gid, index_base=1):
+    """Host-only: owned x owned block and ghost block of the complete owned rows (0-based outputs)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32); cols = np.ascontiguousarray(cols_global, dtype=np.int32)
+    gg = np.ascontiguousarray(ghost_gid, dtype=np.int32)
+    n = rows.size - 1
+    sizes = np.zeros(2, dtype=np.int32)
+    ggp = _ip(gg) if gg.size else _ip(np.zeros(1, dtype=np.int32))
+    head = (_i(n), _ip(rows), _ip(cols), _i(index_base), _i(lo), _i(hi), _i(gg.size), ggp)
+    _check(lib().b200_partition_split(*head, _ip(sizes), None, None, None, None, None), "b200_partition_split")
+    oo_r = np.zeros(n + 1, dtype=np.int32); oo_c = np.zeros(max(int(sizes[0]), 1), dtype=np.int32); oo_d = np.zeros(max(n, 1), dtype=np.int32)
+    g_r = np.zeros(n + 1, dtype=np.int32); g_c = np.zeros(max(int(sizes[1]), 1), dtype=np.int32)
+    _check(lib().b200_partition_split(*head, _ip(sizes), _ip(oo_r), _ip(oo_c), _ip(oo_d), _ip(g_r), _ip(g_c)), "b200_partition_split")
+    return dict(oo_rows=oo_r, oo_cols=oo_c[:sizes[0]], oo_diag=oo_d[:n], g_rows=g_r, g_cols=g_c[:sizes[1]])

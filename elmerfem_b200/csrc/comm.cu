@@ -18,18 +18,58 @@
 #include "kernels.cuh"
 #include "krylov.h"
 #include "../../include/elmer_b200.h"
-#include <nccl.h>
+#include <nccl.h>      // types and prototypes only: the library is bound at run time (see NcclApi)
+#include <dlfcn.h>
 #include <algorithm>
 #include <unordered_map>
 
 namespace b200 {
+
+// NCCL is loaded with dlopen on first use, not linked: single-GPU users need no NCCL at all, and a host
+// process that already carries its own libnccl.so.2 (e.g. a Python process with torch imported) shares
+// that copy instead of colliding with a second one.  B200_NCCL_LIB overrides the soname.
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+static NcclApi &nccl() {
+  static NcclApi api;
+  static bool loaded = false;
+  if (loaded) return api;
+  const char *name = getenv("B200_NCCL_LIB");
+  void *lib = dlopen((name && *name) ? name : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!lib) throw Error(std::string("elmer_b200: cannot load NCCL (") + dlerror() + "); multi-GPU runs need libnccl.so.2");
+  auto sym = [&](const char *n) { void *p = dlsym(lib, n); if (!p) throw Error(std::string("elmer_b200: NCCL symbol missing: ") + n); return p; };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+  api.Send = (decltype(api.Send))sym("ncclSend");
+  api.Recv = (decltype(api.Recv))sym("ncclRecv");
+  api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+  loaded = true;
+  return api;
+}
 
 #define B200_NCCL(x)                                                                              \
   do {                                                                                            \
     ncclResult_t r__ = (x);                                                                       \
     if (r__ != ncclSuccess) {                                                                     \
       char m__[512];                                                                              \
-      snprintf(m__, sizeof m__, "NCCL error '%s' in %s at %s:%d", ncclGetErrorString(r__), #x,     \
+      snprintf(m__, sizeof m__, "NCCL error '%s' in %s at %s:%d", nccl().GetErrorString(r__), #x,     \
                __FILE__, __LINE__);                                                               \
       throw b200::Error(m__);                                                                     \
     }                                                                                             \
@@ -46,6 +86,61 @@ struct Halo {
   cudaEvent_t ev_pack = nullptr, ev_comm = nullptr;
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Host-side planning (no CUDA, no NCCL): also exported on its own so that the integer lists can be
+// checked without a GPU.
+//
+// Send lists (rocalution.cpp:121-156): owned rows ascending, de-duplicated per destination rank, as
+// GLOBAL 0-based row ids.
+static void plan_send_lists(int np, int me, int N, const int *rows, const int *cols, int base, const int *goffset, long long gn,
+                            std::vector<std::vector<int>> &boundary, long long &nnz_oo, long long &nnz_g) {
+  const int lo = goffset[me], hi = goffset[me + 1];
+  boundary.assign(np, std::vector<int>());
+  std::vector<int> last(np, -1);
+  nnz_oo = 0; nnz_g = 0;
+  for (int i = 0; i < N; ++i) {
+    for (int p = rows[i] - base; p < rows[i + 1] - base; ++p) {
+      const int c = cols[p] - base;
+      B200_REQUIRE(c >= 0 && c < gn, "global column out of range");
+      if (c >= lo && c < hi) { ++nnz_oo; continue; }
+      int r = (int)(std::upper_bound(goffset, goffset + np + 1, c) - goffset) - 1;
+      if (last[r] != i) { boundary[r].push_back(i + lo); last[r] = i; }
+      ++nnz_g;
+    }
+  }
+}
+
+// Split of the complete owned rows into the owned x owned block (local columns, diagonal positions)
+// and the ghost block (column = N + ghost slot), given the ghost ids in receive order
+// (rocalution.cpp:286-338).  *src arrays give the position of each entry in the caller's value array.
+struct SplitPlan { std::vector<int> r0, c0, d0, oosrc, gperm, gstart, glen, gcols, gsrc; };
+static void plan_split(int N, const int *rows, const int *cols, int base, int lo, int hi, const std::vector<int> &ghost_gid,
+                       long long nnz_oo, long long nnz_g, SplitPlan &S) {
+  std::unordered_map<int, int> slot_of; slot_of.reserve(ghost_gid.size() * 2 + 1);
+  for (int k = 0; k < (int)ghost_gid.size(); ++k) slot_of[ghost_gid[k]] = k;
+  S.r0.assign((size_t)N + 1, 0); S.c0.resize((size_t)nnz_oo); S.d0.assign(N, -1); S.oosrc.resize((size_t)nnz_oo);
+  S.gcols.resize((size_t)nnz_g); S.gsrc.resize((size_t)nnz_g); S.gperm.clear(); S.gstart.clear(); S.glen.clear();
+  long long l = 0, k = 0;
+  for (int i = 0; i < N; ++i) {
+    long long k_row = k;
+    for (int p = rows[i] - base; p < rows[i + 1] - base; ++p) {
+      const int c = cols[p] - base;
+      if (c >= lo && c < hi) {
+        if (c - lo == i) S.d0[i] = (int)l;
+        S.c0[l] = c - lo; S.oosrc[l] = p; ++l;
+      } else {
+        auto it = slot_of.find(c);
+        B200_REQUIRE(it != slot_of.end(), "ghost column not provided by its owner: the sparsity pattern is not structurally symmetric");
+        S.gcols[k] = N + it->second; S.gsrc[k] = p; ++k;
+      }
+    }
+    S.r0[i + 1] = (int)l;
+    B200_REQUIRE(S.d0[i] >= 0, "owned row without a diagonal entry");
+    if (k > k_row) { S.gperm.push_back(i); S.gstart.push_back((int)k_row); S.glen.push_back((int)(k - k_row)); }
+  }
+}
+
 size_t vec_len(const Handle &h) { return (size_t)h.n + (h.halo ? (size_t)h.halo->nghost : 0); }
 
 void halo_release(Handle &h) {
@@ -57,12 +152,12 @@ void halo_release(Handle &h) {
     if (H.ev_comm) cudaEventDestroy(H.ev_comm);
     delete h.halo; h.halo = nullptr;
   }
-  if (h.nccl) { ncclCommDestroy((ncclComm_t)h.nccl); h.nccl = nullptr; }
+  if (h.nccl) { nccl().CommDestroy((ncclComm_t)h.nccl); h.nccl = nullptr; }
 }
 
 void comm_allreduce_sum(Handle &h, double *d, int count) {
   B200_REQUIRE(h.nccl, "reduction over ranks requested without b200_comm_init");
-  B200_NCCL(ncclAllReduce(d, d, count, ncclDouble, ncclSum, (ncclComm_t)h.nccl, h.stream));
+  B200_NCCL(nccl().AllReduce(d, d, count, ncclDouble, ncclSum, (ncclComm_t)h.nccl, h.stream));
   h.st_launch++;
 }
 
@@ -98,13 +193,13 @@ void matvec_full(Handle &h, const double *x, double *y) {
   if (H.nsend) k_pack<<<std::max(1, std::min((H.nsend + 255) / 256, NUM_SMS * 4)), 256, 0, h.stream>>>(H.nsend, H.d_send_idx.p, x, H.d_sendbuf.p);
   B200_CUDA(cudaEventRecord(H.ev_pack, h.stream));
   B200_CUDA(cudaStreamWaitEvent(h.stream2, H.ev_pack, 0));
-  B200_NCCL(ncclGroupStart());
+  B200_NCCL(nccl().GroupStart());
   for (int q = 0; q < H.nneigh; ++q) {
     int ns = H.send_ptr[q + 1] - H.send_ptr[q], nr = H.recv_ptr[q + 1] - H.recv_ptr[q];
-    if (ns) B200_NCCL(ncclSend(H.d_sendbuf.p + H.send_ptr[q], ns, ncclDouble, H.neigh[q], comm, h.stream2));
-    if (nr) B200_NCCL(ncclRecv(xg + H.recv_ptr[q], nr, ncclDouble, H.neigh[q], comm, h.stream2));
+    if (ns) B200_NCCL(nccl().Send(H.d_sendbuf.p + H.send_ptr[q], ns, ncclDouble, H.neigh[q], comm, h.stream2));
+    if (nr) B200_NCCL(nccl().Recv(xg + H.recv_ptr[q], nr, ncclDouble, H.neigh[q], comm, h.stream2));
   }
-  B200_NCCL(ncclGroupEnd());
+  B200_NCCL(nccl().GroupEnd());
   B200_CUDA(cudaEventRecord(H.ev_comm, h.stream2));
   { SpmvArgs a; a.x = x; a.y = y; spmv_launch(h, a, EPI_NONE); }   // owned x owned, overlaps the exchange
   B200_CUDA(cudaStreamWaitEvent(h.stream, H.ev_comm, 0));
@@ -188,7 +283,7 @@ extern "C" {
 int b200_comm_unique_id(char *id128) {
   return guarded_c([&] {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
-    ncclUniqueId id; B200_NCCL(ncclGetUniqueId(&id));
+    ncclUniqueId id; B200_NCCL(nccl().GetUniqueId(&id));
     memcpy(id128, &id, 128);
   });
 }
@@ -203,7 +298,7 @@ int b200_comm_init(void **handle, const int *nranks, const int *rank, const char
     if (*nranks == 1) return;
     ncclUniqueId id; memcpy(&id, id128, 128);
     ncclComm_t comm;
-    B200_NCCL(ncclCommInitRank(&comm, *nranks, id, *rank));
+    B200_NCCL(nccl().CommInitRank(&comm, *nranks, id, *rank));
     h.nccl = comm;
   });
 }
@@ -228,20 +323,9 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
     B200_CUDA(cudaEventCreateWithFlags(&H.ev_comm, cudaEventDisableTiming));
     H.nnz_in = NNZ;
 
-    // ---- send lists (rocalution.cpp:121-156): rows ascending, de-duplicated per destination rank
-    std::vector<std::vector<int>> boundary(np);
-    std::vector<int> last(np, -1);
+    std::vector<std::vector<int>> boundary;
     long long nnz_oo = 0, nnz_g = 0;
-    for (int i = 0; i < N; ++i) {
-      for (int p = rows[i] - base; p < rows[i + 1] - base; ++p) {
-        const int c = cols[p] - base;
-        B200_REQUIRE(c >= 0 && c < *gn, "global column out of range");
-        if (c >= lo && c < hi) { ++nnz_oo; continue; }
-        int r = (int)(std::upper_bound(goffset, goffset + np + 1, c) - goffset) - 1;
-        if (last[r] != i) { boundary[r].push_back(i + lo); last[r] = i; }
-        ++nnz_g;
-      }
-    }
+    plan_send_lists(np, me, N, rows, cols, base, goffset, *gn, boundary, nnz_oo, nnz_g);
     // ---- exchange list sizes and lists
     std::vector<int> sendcnt(np, 0), allcnt((size_t)np * np, 0);
     for (int r = 0; r < np; ++r) sendcnt[r] = (int)boundary[r].size();
@@ -249,7 +333,7 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
     if (np > 1) {
       DBuf<int> d_cnt, d_all; d_cnt.ensure(np); d_all.ensure((size_t)np * np);
       B200_CUDA(cudaMemcpyAsync(d_cnt.p, sendcnt.data(), np * sizeof(int), cudaMemcpyHostToDevice, st));
-      B200_NCCL(ncclAllGather(d_cnt.p, d_all.p, np, ncclInt32, (ncclComm_t)h.nccl, st));
+      B200_NCCL(nccl().AllGather(d_cnt.p, d_all.p, np, ncclInt32, (ncclComm_t)h.nccl, st));
       B200_CUDA(cudaMemcpyAsync(allcnt.data(), d_all.p, (size_t)np * np * sizeof(int), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
       d_cnt.release(); d_all.release();
@@ -266,41 +350,21 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
     if (np > 1 && (H.nsend || H.nghost)) {
       DBuf<int> d_s, d_r; d_s.ensure(H.nsend); d_r.ensure(H.nghost);
       if (H.nsend) B200_CUDA(cudaMemcpyAsync(d_s.p, send_gid.data(), H.nsend * sizeof(int), cudaMemcpyHostToDevice, st));
-      B200_NCCL(ncclGroupStart());
+      B200_NCCL(nccl().GroupStart());
       for (int q = 0; q < H.nneigh; ++q) {
         int ns = H.send_ptr[q + 1] - H.send_ptr[q], nr = H.recv_ptr[q + 1] - H.recv_ptr[q];
-        if (ns) B200_NCCL(ncclSend(d_s.p + H.send_ptr[q], ns, ncclInt32, H.neigh[q], (ncclComm_t)h.nccl, st));
-        if (nr) B200_NCCL(ncclRecv(d_r.p + H.recv_ptr[q], nr, ncclInt32, H.neigh[q], (ncclComm_t)h.nccl, st));
+        if (ns) B200_NCCL(nccl().Send(d_s.p + H.send_ptr[q], ns, ncclInt32, H.neigh[q], (ncclComm_t)h.nccl, st));
+        if (nr) B200_NCCL(nccl().Recv(d_r.p + H.recv_ptr[q], nr, ncclInt32, H.neigh[q], (ncclComm_t)h.nccl, st));
       }
-      B200_NCCL(ncclGroupEnd());
+      B200_NCCL(nccl().GroupEnd());
       if (H.nghost) B200_CUDA(cudaMemcpyAsync(H.ghost_gid.data(), d_r.p, H.nghost * sizeof(int), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
       d_s.release(); d_r.release();
     }
-    // ---- ghost slot map (rocalution.cpp:286-297)
-    std::unordered_map<int, int> slot_of; slot_of.reserve((size_t)H.nghost * 2);
-    for (int k = 0; k < H.nghost; ++k) slot_of[H.ghost_gid[k]] = k;
-    // ---- split into the owned x owned block (local columns) and the ghost block
-    std::vector<int> r0((size_t)N + 1, 0), c0((size_t)nnz_oo), d0(N, -1), oosrc((size_t)nnz_oo);
-    std::vector<int> gperm, gstart, glen, gcols((size_t)nnz_g), gsrc((size_t)nnz_g);
-    long long l = 0, k = 0;
-    for (int i = 0; i < N; ++i) {
-      long long k_row = k;
-      for (int p = rows[i] - base; p < rows[i + 1] - base; ++p) {
-        const int c = cols[p] - base;
-        if (c >= lo && c < hi) {
-          if (c - lo == i) d0[i] = (int)l;
-          c0[l] = c - lo; oosrc[l] = p; ++l;
-        } else {
-          auto it = slot_of.find(c);
-          B200_REQUIRE(it != slot_of.end(), "ghost column not provided by its owner: the sparsity pattern is not structurally symmetric");
-          gcols[k] = N + it->second; gsrc[k] = p; ++k;
-        }
-      }
-      r0[i + 1] = (int)l;
-      B200_REQUIRE(d0[i] >= 0, "owned row without a diagonal entry");
-      if (k > k_row) { gperm.push_back(i); gstart.push_back((int)k_row); glen.push_back((int)(k - k_row)); }
-    }
+    SplitPlan sp;
+    plan_split(N, rows, cols, base, lo, hi, H.ghost_gid, nnz_oo, nnz_g, sp);
+    std::vector<int> &r0 = sp.r0, &c0 = sp.c0, &d0 = sp.d0, &oosrc = sp.oosrc, &gperm = sp.gperm, &gstart = sp.gstart, &glen = sp.glen,
+                     &gcols = sp.gcols, &gsrc = sp.gsrc;
     H.nnz_g = nnz_g;
     install_structure(h, N, nnz_oo, std::move(r0), std::move(c0), std::move(d0), ndeg ? *ndeg : 1);
     // ghost block as a SELL over the boundary rows
@@ -322,6 +386,42 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
     B200_CUDA(cudaStreamSynchronize(st));
     sell_finish(h, H.G, nslots, true, H.d_gcols.p);
     B200_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+// Host-only planning entry points (usable without a GPU; the caller does the exchange itself).
+int b200_partition_send_lists(const int *gn, const int *n_own, const int *rows, const int *cols, const int *goffset,
+                              const int *index_base, const int *nranks, const int *rank, int *send_count, int *send_gid) {
+  return guarded_c([&] {
+    std::vector<std::vector<int>> boundary; long long a = 0, b = 0;
+    plan_send_lists(*nranks, *rank, *n_own, rows, cols, *index_base, goffset, *gn, boundary, a, b);
+    int k = 0;
+    for (int r = 0; r < *nranks; ++r) {
+      send_count[r] = (int)boundary[r].size();
+      if (send_gid) for (int g : boundary[r]) send_gid[k++] = g;
+    }
+  });
+}
+
+int b200_partition_split(const int *n_own, const int *rows, const int *cols, const int *index_base, const int *lo, const int *hi,
+                         const int *nghost, const int *ghost_gid, int *sizes, int *oo_rows, int *oo_cols, int *oo_diag,
+                         int *g_rows, int *g_cols) {
+  return guarded_c([&] {
+    const int N = *n_own, base = *index_base;
+    long long nnz_oo = 0, nnz_g = 0;
+    for (int i = 0; i < N; ++i) for (int p = rows[i] - base; p < rows[i + 1] - base; ++p) {
+      const int c = cols[p] - base; if (c >= *lo && c < *hi) ++nnz_oo; else ++nnz_g;
+    }
+    sizes[0] = (int)nnz_oo; sizes[1] = (int)nnz_g;
+    if (!oo_rows) return;
+    std::vector<int> gg(ghost_gid, ghost_gid + *nghost);
+    SplitPlan S; plan_split(N, rows, cols, base, *lo, *hi, gg, nnz_oo, nnz_g, S);
+    std::copy(S.r0.begin(), S.r0.end(), oo_rows); std::copy(S.c0.begin(), S.c0.end(), oo_cols); std::copy(S.d0.begin(), S.d0.end(), oo_diag);
+    // ghost block as CRS over all owned rows
+    std::vector<int> gr((size_t)N + 1, 0);
+    for (size_t q = 0; q < S.gperm.size(); ++q) gr[S.gperm[q] + 1] = S.glen[q];
+    for (int i = 0; i < N; ++i) gr[i + 1] += gr[i];
+    std::copy(gr.begin(), gr.end(), g_rows); std::copy(S.gcols.begin(), S.gcols.end(), g_cols);
   });
 }
 

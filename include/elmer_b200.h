@@ -142,6 +142,18 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
 int b200_get_halo_plan(void **handle, int *sizes, int *neigh, int *send_ptr, int *send_idx,
                        int *recv_ptr, int *ghost_gid);
 
+/* Host-only planning steps of b200_set_partition (no GPU needed; the caller exchanges the lists itself, e.g.
+ * with MPI): send_count[nranks] and, if non-NULL, send_gid = the send lists concatenated by ascending
+ * destination rank as GLOBAL 0-based row ids (rocalution.cpp:121-156). */
+int b200_partition_send_lists(const int *gn, const int *n_own, const int *rows, const int *cols, const int *goffset,
+                              const int *index_base, const int *nranks, const int *rank, int *send_count, int *send_gid);
+/* Split of the complete owned rows given the ghost ids in receive order (rocalution.cpp:286-338): sizes[0] = nnz of the
+ * owned x owned block, sizes[1] = nnz of the ghost block (first call with NULL outputs); then oo_rows[n_own+1],
+ * oo_cols, oo_diag (0-based, local columns) and the ghost block g_rows[n_own+1], g_cols (= n_own + ghost slot). */
+int b200_partition_split(const int *n_own, const int *rows, const int *cols, const int *index_base, const int *lo, const int *hi,
+                         const int *nghost, const int *ghost_gid, int *sizes, int *oo_rows, int *oo_cols, int *oo_diag,
+                         int *g_rows, int *g_cols);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* stats[0] last solve device ms (CUDA events on the solve stream), [1] matvec calls, [2] precond
  * applications, [3] last factorisation device ms, [4] kernels launched by the last solve,
