@@ -53,12 +53,8 @@ static void ensure_runtime(Handle &h) {
   h.spmv_blocks = env_int("B200_SPMV_BLOCKS", 0);
   h.tri_blocks_per_sm = env_int("B200_TRI_BLOCKS_PER_SM", 0);
   h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 4));
-  h.tri_mode = env_int("B200_TRI_MODE", 0);
-  h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", h.tri_mode == 1 ? 256 : 100);
+  h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", 100);
   h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
-  h.tri_max_parts = env_int("B200_TRI_PARTS", 0);
-  h.tri_rows_per_part_min = std::max(32, env_int("B200_TRI_MIN_ROWS", 8192));
-  h.tri_ramp = env_int("B200_TRI_RAMP_PCT", 100) / 100.0;
   h.blas_blocks = env_int("B200_BLAS_BLOCKS", NUM_SMS * 8);
   if (h.blas_blocks > MAX_RED_BLOCKS) h.blas_blocks = MAX_RED_BLOCKS;
 }
@@ -177,7 +173,7 @@ int b200_destroy(void **handle) {
     h->d_rows_in.release(); h->d_cols_in.release(); h->d_diag_in.release();
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
     h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
-    h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release(); h->d_part_begin_f.release(); h->d_part_begin_b.release(); h->d_meta_f.release(); h->d_meta_b.release(); h->d_l2u.release(); h->d_bl.release(); h->d_bu.release(); h->d_trace.release();
+    h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
     for (auto &w : h->work) w.release();
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();

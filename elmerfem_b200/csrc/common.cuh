@@ -36,10 +36,6 @@ constexpr double AEPS = 10.0 * 2.220446049250313e-16;      // Types.F90:71
 constexpr double HUTI_EPSILON = 1.17549435E-38;            // huti_fdefs.h:14
 constexpr int SLICE = 32;                                  // SELL slice height = warp width
 constexpr int NUM_SMS = 148;                               // B200
-// part-mode triangular solve: one CTA of TRI_NW warps per row range; the last TRI_RR-1 rounds of
-// results stay in a shared-memory ring so that dependencies inside a CTA never touch L2
-constexpr int TRI_NW = 16;
-constexpr int TRI_RR = 8;
 // "not yet computed" marker of the sync-free triangular solves (a NaN payload no arithmetic produces)
 constexpr unsigned long long SENTINEL = 0x7FF4DEADBEEF0B20ULL;
 constexpr unsigned long long CANON_NAN = 0x7FF8000000000000ULL;
@@ -122,13 +118,6 @@ struct Handle {
   DBuf<int> tri_counters; int tri_maxw = 0, tri_lookahead = 2; unsigned tri_gate_sleep = 100, tri_spin_sleep = 0;
   DBuf<int> d_lvlcnt_f, d_lvlcnt_b;              // slices per level (forward / backward)
   DBuf<int> d_urhs; DBuf<double> d_yl, d_xu;     // backward rhs map (U slot -> L slot); slot-ordered solve vectors
-  int tri_mode = 0;                              // 0 = global level order, hand-off through L2 (default); 1 = experimental row-range parts, shared-memory + mbarrier hand-off
-  int tri_parts_f = 0, tri_parts_b = 0, tri_max_parts = 0; double tri_ramp = 1.0; int tri_rows_per_part_min = 8192;
-  DBuf<int> d_part_begin_f, d_part_begin_b;      // per part: first slice (P+1 entries)
-  DBuf<int> d_meta_f, d_meta_b;                  // per slice int2: pred | succ << 16, npre
-  DBuf<int> d_l2u; DBuf<double> d_bl, d_bu;       // L slot -> U slot scatter map; slot-ordered right-hand sides of the two sweeps
-  DBuf<unsigned long long> d_trace;              // optional round time stamps (B200_TRI_TRACE)
-  int n_order_f = 0;                             // slots of the factorisation order (d_order_f)
   // workspace
   std::vector<DBuf<double>> work; DBuf<double> d_b, d_x, d_tmp, d_P;
   DBuf<double> red_partials; DBuf<unsigned int> red_counters; DBuf<double> scal; DBuf<Ctrl> ctrl;

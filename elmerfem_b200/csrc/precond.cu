@@ -137,8 +137,8 @@ void ilu0_factor(Handle &h) {
     B200_CUDA(cudaMemsetAsync(&h.ctrl.p->spin_timeout, 0, sizeof(int), st));
     const double *src = h.have_prec ? h.d_prec.p : h.d_vals.p;        // CRSMatrix.F90:3480-3484
     if (!h.grid_ilu) h.grid_ilu = persistent_blocks((const void *)k_ilu0_factor, 256, 0);
-    int blocks = std::max(1, std::min(h.grid_ilu, (h.n_order_f + 7) / 8));
-    launch_coresident((const void *)k_ilu0_factor, blocks, 256, st, h.n_order_f, (const int *)h.d_order_f.p, (const int *)h.d_rows.p,
+    int blocks = std::max(1, std::min(h.grid_ilu, (h.L.nslots + 7) / 8));
+    launch_coresident((const void *)k_ilu0_factor, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, (const int *)h.d_rows.p,
                       (const int *)h.d_cols.p, (const int *)h.d_diag.p, src, h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
     int eb = std::min((h.n + 255) / 256, NUM_SMS * 8);
     k_ilu0_invert_diag<<<eb, 256, 0, st>>>(h.n, h.d_diag.p, h.d_ilu.p);
@@ -243,254 +243,6 @@ __global__ void __launch_bounds__(256, 2) k_sptrsv(SellView T, const int *__rest
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Part-mode triangular solve (default).  One CTA of TRI_NW warps per part (contiguous natural row
-// range, see part_layout in structure.cu); warp w of round rho takes slice part_begin + rho*TRI_NW + w:
-// 32 rows of ONE dependency level.  Where a row's operands come from is decided at analysis time:
-//   * produced by this CTA in the same round     -> shared-memory ring, guarded by an mbarrier token
-//   * produced by this CTA up to TRI_RR-2 rounds ago -> shared-memory ring, final since the round barrier
-//   * anything else (other CTA, or older)         -> slot-ordered solve vector in L2, "not yet" = SENTINEL
-// Same-round hand-off is dataflow: every warp owns one mbarrier; a finishing warp arrives on the
-// barriers of the warps that consume its rows (succ mask), a consumer sleeps in mbarrier.try_wait
-// (hardware suspend, no issue slots burnt) until all its producers (pred mask) have arrived.  The
-// wavefront's critical path therefore runs through shared memory + one mbarrier wake-up per level.
-// Operands are consumed strictly left to right with separate multiply/add roundings: bit-identical
-// to CRS_LUSolve (CRSMatrix.F90:4642-4660).  Entries before the first same-round operand (npre) are
-// accumulated before the warp goes to sleep, so only the tail of the row sum is on the critical path.
-// Matrix entries stream from HBM through L2 prefetches issued two rounds ahead.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar, unsigned count) {
-  unsigned long long st;
-  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1], %2;" : "=l"(st) : "r"(smem_u32(bar)), "r"(count) : "memory");
-  (void)st;
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
-  unsigned ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ double ld_ring(const double *p) {
-  double v; asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)) : "memory"); return v;
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-
-// code < 0: ~(ring index | same_round << 16)
-__device__ __forceinline__ bool code_same_round(int code) { return code < 0 && ((~code) >> 16) != 0; }
-__device__ __forceinline__ int code_ring(int code) { return (~code) & 0xffff; }
-
-// in-order row-sum tail s -= p[k] for k = k0 .. 15 (p = v*x already rounded); padded entries carry p = 0
-#define B200_TRI_STEP(k) case k: s = __dsub_rn(s, p[k]);
-__device__ __forceinline__ double tri_chain_from(double s, const double (&p)[16], int k0) {
-  switch (k0) {
-    B200_TRI_STEP(0) B200_TRI_STEP(1) B200_TRI_STEP(2) B200_TRI_STEP(3) B200_TRI_STEP(4) B200_TRI_STEP(5) B200_TRI_STEP(6) B200_TRI_STEP(7)
-    B200_TRI_STEP(8) B200_TRI_STEP(9) B200_TRI_STEP(10) B200_TRI_STEP(11) B200_TRI_STEP(12) B200_TRI_STEP(13) B200_TRI_STEP(14) B200_TRI_STEP(15)
-    default: break;
-  }
-  return s;
-}
-#undef B200_TRI_STEP
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ double lds_f64(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory"); return v; }
-__device__ __forceinline__ int lds_s32(unsigned addr) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
-
-constexpr int TRI_CH = 16;                                   // entries of an item staged in shared memory
-constexpr int TRI_STAGE_BYTES = TRI_CH * 32 * 12;            // values (8 B) then column codes (4 B)
-constexpr int TRI_SMEM_BYTES = TRI_RR * TRI_NW * 32 * 8 + 2 * TRI_NW * TRI_STAGE_BYTES + TRI_NW * 8;
-
-// what a warp needs to know about its item besides the matrix entries; fetched one round ahead
-struct TriItem { long long p0; int W, len, row, sidx, pred_succ, npre; double b, dinv; };
-
-template <bool UPPER>
-__global__ void __launch_bounds__(TRI_NW * 32, 1) k_sptrsv_tok(SellView T, const int2 *__restrict__ meta, const int *__restrict__ part_begin,
-                                                                const double *__restrict__ dinv_slot, const double *__restrict__ bslot,
-                                                                const int *__restrict__ scatter_idx, double *out, double *scatter_out,
-                                                                Ctrl *ctrl, unsigned max_backoff, unsigned long long *trace) {
-  extern __shared__ __align__(16) unsigned char tri_smem[];
-  double *ring = reinterpret_cast<double *>(tri_smem);
-  unsigned char *stages = tri_smem + TRI_RR * TRI_NW * 32 * 8;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(stages + 2 * TRI_NW * TRI_STAGE_BYTES);
-  if (ctrl->done) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < TRI_NW) mbar_init(&bar[tid], TRI_NW);
-  __syncthreads();
-  const int s0 = part_begin[blockIdx.x], s1 = part_begin[blockIdx.x + 1];
-  const unsigned ring_base = smem_u32(ring);
-  unsigned spins = 0;
-  if (trace && tid == 0) trace[(size_t)blockIdx.x * 1024] = gtime();
-
-  auto load_item = [&](int sl) {
-    TriItem it;
-    const long long a = T.ptr[sl], e = T.ptr[sl + 1];
-    const int2 m = meta[sl];
-    const int slot = sl * 32 + lane;
-    it.p0 = a; it.W = (int)((e - a) >> 5); it.pred_succ = m.x; it.npre = m.y;
-    it.len = T.len[slot]; it.row = T.perm[slot]; it.sidx = scatter_idx[slot]; it.b = bslot[slot];
-    it.dinv = UPPER ? dinv_slot[slot] : 1.0;
-    return it;
-  };
-  // asynchronous copy of the first TRI_CH entry columns of an item (32 x 8 B values, 32 x 4 B codes each) into a stage
-  auto stage_item = [&](const TriItem &it, int st) {
-    unsigned char *dst = stages + (size_t)(st * TRI_NW + warp) * TRI_STAGE_BYTES;
-    const int w = it.W < TRI_CH ? it.W : TRI_CH;
-    const char *vsrc = (const char *)(T.vals + it.p0), *csrc = (const char *)(T.cols + it.p0);
-    for (int i = lane; i < w * 16; i += 32) cp_async16(dst + i * 16, vsrc + i * 16);
-    for (int i = lane; i < w * 8; i += 32) cp_async16(dst + TRI_CH * 256 + i * 16, csrc + i * 16);
-    cp_async_commit();
-  };
-
-  TriItem cur, nxt;
-  cur.W = 0; nxt.W = 0;
-  if (s0 + warp < s1) { cur = load_item(s0 + warp); stage_item(cur, 0); }
-  if (s0 + TRI_NW + warp < s1) nxt = load_item(s0 + TRI_NW + warp);
-
-  int rho = 0;
-  for (int base = s0; base < s1; base += TRI_NW, ++rho) {
-    const int seg = rho % TRI_RR;
-    const int slice = base + warp;
-    const bool have = slice < s1;
-    cp_async_wait_all();
-    __syncwarp();
-    // next round: entries into the other stage, per-slot data of the round after into registers
-    TriItem nn; nn.W = 0;
-    if (slice + TRI_NW < s1) stage_item(nxt, (rho + 1) & 1);
-    if (slice + 2 * TRI_NW < s1) nn = load_item(slice + 2 * TRI_NW);
-    if (have) {
-      const unsigned stv = smem_u32(stages + (size_t)((rho & 1) * TRI_NW + warp) * TRI_STAGE_BYTES) + lane * 8;
-      const unsigned stc = smem_u32(stages + (size_t)((rho & 1) * TRI_NW + warp) * TRI_STAGE_BYTES) + TRI_CH * 256 + lane * 4;
-      const int W = cur.W, len = cur.len, npre = cur.npre;
-      const unsigned pred = (unsigned)cur.pred_succ & 0xffffu, succ = (unsigned)cur.pred_succ >> 16;
-      double s = cur.b;
-      // own token: NW arrivals complete the phase; the popc(pred) producers bring the rest
-      if (lane == 0) mbar_arrive(&bar[warp], TRI_NW - __popc(pred));
-      bool waited = (pred == 0);
-      {
-        // ---- staged chunk (entries 0 .. TRI_CH-1): codes from shared memory, operands gathered now unless same-round
-        int c[TRI_CH]; double p[TRI_CH];
-        unsigned pend = 0, smask = 0;
-#pragma unroll
-        for (int k = 0; k < TRI_CH; ++k) c[k] = (k < len) ? lds_s32(stc + k * 128) : 0;
-#pragma unroll
-        for (int k = 0; k < TRI_CH; ++k) {
-          double x = 0.0;
-          if (k < len) {
-            const int code = c[k];
-            if (code >= 0) { x = ld_relaxed(out + code); pend |= is_sentinel(x) ? (1u << k) : 0u; }
-            else {
-              const unsigned addr = ring_base + (unsigned)code_ring(code) * 8u;
-              if (waited || !code_same_round(code)) x = lds_f64(addr);
-              else { smask |= 1u << k; c[k] = (int)addr; }           // fetched after the token; keep its shared-memory address
-            }
-          }
-          p[k] = x;
-        }
-        if (__any_sync(0xffffffffu, pend != 0)) {         // another CTA's rows not finished yet: poll L2 with back-off
-          unsigned backoff = 32;
-          do {
-            if (pend) { __nanosleep(backoff); if (backoff < max_backoff) backoff <<= 1; }
-#pragma unroll
-            for (int k = 0; k < TRI_CH; ++k)
-              if ((pend >> k) & 1u) { double x = ld_relaxed(out + c[k]); if (!is_sentinel(x)) { p[k] = x; pend &= ~(1u << k); } }
-            if (++spins > (1u << 22)) { ctrl->spin_timeout = 1; pend = 0; }
-          } while (__any_sync(0xffffffffu, pend != 0));
-        }
-#pragma unroll
-        for (int k = 0; k < TRI_CH; ++k) p[k] = (k < len && !((smask >> k) & 1u)) ? __dmul_rn(lds_f64(stv + k * 256), p[k]) : 0.0;
-        int k0 = 0;
-        if (!waited && npre < TRI_CH) {                   // the item's first same-round operand lies in this chunk
-          k0 = npre;
-#pragma unroll
-          for (int k = 0; k < TRI_CH; ++k) { if (k >= k0) break; s = __dsub_rn(s, p[k]); }   // prefix: before going to sleep
-          while (!mbar_try_wait(&bar[warp], rho & 1)) { if (++spins > (1u << 22)) { ctrl->spin_timeout = 1; break; } }
-          waited = true;
-          // ---- critical path of the wavefront from here: same-round operands, tail of the row sum, publish
-#pragma unroll
-          for (int k = 0; k < TRI_CH; ++k)
-            if ((smask >> k) & 1u) p[k] = __dmul_rn(lds_f64(stv + k * 256), lds_f64((unsigned)c[k]));
-        }
-        s = tri_chain_from(s, p, k0);
-      }
-      // ---- rows longer than the stage: remaining entries straight from global memory (not the fast path)
-      if (W > TRI_CH) {
-        const int *__restrict__ cp = T.cols + cur.p0 + lane;
-        const double *__restrict__ vp = T.vals + cur.p0 + lane;
-        for (int j = TRI_CH; j < W; ++j) {
-          const int code = ld_stream(cp + j * 32);
-          const double v = ld_stream(vp + j * 32);
-          if (!waited && j >= npre) {
-            while (!mbar_try_wait(&bar[warp], rho & 1)) { if (++spins > (1u << 22)) { ctrl->spin_timeout = 1; break; } }
-            waited = true;
-          }
-          const bool need = j < len;
-          double x = 0.0;
-          if (need) x = code >= 0 ? ld_relaxed(out + code) : lds_f64(ring_base + (unsigned)code_ring(code) * 8u);
-          unsigned backoff = 32;
-          while (__any_sync(0xffffffffu, need && code >= 0 && is_sentinel(x))) {
-            if (need && code >= 0 && is_sentinel(x)) {
-              if (++spins > (1u << 22)) { ctrl->spin_timeout = 1; x = 0.0; }
-              else { __nanosleep(backoff); if (backoff < max_backoff) backoff <<= 1; x = ld_relaxed(out + code); }
-            }
-          }
-          if (need) s = nfms(s, v, x);
-        }
-      }
-      if (!waited) { while (!mbar_try_wait(&bar[warp], rho & 1)) { if (++spins > (1u << 22)) { ctrl->spin_timeout = 1; break; } } }
-      double res = UPPER ? __dmul_rn(cur.dinv, s) : s;
-      if (res != res) res = __longlong_as_double((long long)CANON_NAN);
-      ring[seg * TRI_NW * 32 + tid] = res;                // padded lanes store harmless values nobody reads
-      __syncwarp();
-      if (lane < TRI_NW && ((succ >> lane) & 1u)) mbar_arrive(&bar[lane], 1);
-      // ---- end of the critical path; the copies for other CTAs and for the caller follow
-      if (cur.row >= 0) { st_relaxed(out + slice * 32 + lane, res); scatter_out[cur.sidx] = res; }
-    }
-    __syncthreads();
-    cur = nxt; nxt = nn;
-    if (trace && tid == 0 && rho < 1022) trace[(size_t)blockIdx.x * 1024 + 1 + rho] = gtime();
-  }
-  if (trace && tid == 0) trace[(size_t)blockIdx.x * 1024 + 1023] = (unsigned long long)rho;
-}
-
-static void lu_launch_part(Handle &h, double *u, const double *v) {
-  cudaStream_t st = h.stream;
-  unsigned long long *tr = h.d_trace.p;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute((const void *)k_sptrsv_tok<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM_BYTES));
-    B200_CUDA(cudaFuncSetAttribute((const void *)k_sptrsv_tok<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_SMEM_BYTES));
-    attr_set = true;
-  }
-  const SellView Lv = h.L.view(), Uv = h.U.view();
-  const int2 *mf = (const int2 *)h.d_meta_f.p, *mb = (const int2 *)h.d_meta_b.p;
-  const int *pbf = h.d_part_begin_f.p, *pbb = h.d_part_begin_b.p, *l2u = h.d_l2u.p, *up = h.U.perm.p;
-  const double *nul = nullptr, *bl = h.d_bl.p, *bu = h.d_bu.p, *dinv = h.d_dinv_slot.p;
-  double *yl = h.d_yl.p, *xu = h.d_xu.p, *buw = h.d_bu.p;
-  Ctrl *ctrl = h.ctrl.p; unsigned mbk = h.tri_gate_sleep;
-  unsigned long long *tr2 = tr ? tr + (size_t)h.tri_parts_f * 1024 : tr;
-  { void *argv[] = {(void *)&Lv, (void *)&mf, (void *)&pbf, (void *)&nul, (void *)&bl, (void *)&l2u, (void *)&yl, (void *)&buw, (void *)&ctrl, (void *)&mbk, (void *)&tr};
-    B200_CUDA(cudaLaunchCooperativeKernel((const void *)k_sptrsv_tok<false>, dim3(h.tri_parts_f), dim3(TRI_NW * 32), argv, TRI_SMEM_BYTES, st)); }
-  { void *argv[] = {(void *)&Uv, (void *)&mb, (void *)&pbb, (void *)&dinv, (void *)&bu, (void *)&up, (void *)&xu, (void *)&u, (void *)&ctrl, (void *)&mbk, (void *)&tr2};
-    B200_CUDA(cudaLaunchCooperativeKernel((const void *)k_sptrsv_tok<true>, dim3(h.tri_parts_b), dim3(TRI_NW * 32), argv, TRI_SMEM_BYTES, st)); }
-}
-
-// part mode: sentinel fill of the two slot-ordered solve vectors + gather of the right-hand side into L-slot order
-__global__ void k_tri_prepare_part(int nsf, double *yl, int nsb, double *xu, const int *__restrict__ permL, const double *__restrict__ v,
-                                   double *__restrict__ bl) {
-  const double sent = __longlong_as_double((long long)SENTINEL);
-  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
-  for (int i = i0; i < nsf; i += st) { yl[i] = sent; int r = permL[i]; bl[i] = r >= 0 ? v[r] : 0.0; }
-  for (int i = i0; i < nsb; i += st) xu[i] = sent;
-}
-
 __global__ void k_tri_prepare(int na, double *a, int nb, double *b, int *counters, int ncounters) {
   const double sent = __longlong_as_double((long long)SENTINEL);
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
@@ -519,27 +271,10 @@ static void lu_launch(Handle &h, double *u, const double *v) {
 void lu_apply(Handle &h, double *u, const double *v) {
   B200_REQUIRE(h.ilu_valid, "LU preconditioner applied without a valid ILU0 factor");
   if (h.n == 0) return;
-  if (h.tri_mode == 1 && getenv("B200_TRI_TRACE") && !h.d_trace.p) {
-    h.d_trace.ensure((size_t)(h.tri_parts_f + h.tri_parts_b) * 1024);
-    B200_CUDA(cudaMemset(h.d_trace.p, 0, (size_t)(h.tri_parts_f + h.tri_parts_b) * 1024 * sizeof(unsigned long long)));
-  }
-  if (h.tri_mode == 1) {
-    k_tri_prepare_part<<<NUM_SMS * 8, 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.L.perm.p, v, h.d_bl.p);
-    lu_launch_part(h, u, v);
-  } else {
-    k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
-    if (h.tri_maxw <= 8) lu_launch<8>(h, u, v); else lu_launch<16>(h, u, v);
-  }
+  k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
+  if (h.tri_maxw <= 8) lu_launch<8>(h, u, v); else lu_launch<16>(h, u, v);
   B200_CUDA(cudaGetLastError());
   h.st_launch += 3; h.st_pcond++;
-  if (h.d_trace.p && h.tri_mode == 1) {                 // B200_TRI_TRACE=<file>: per-CTA round time stamps of the last application
-    const char *path = getenv("B200_TRI_TRACE");
-    size_t cnt = (size_t)(h.tri_parts_f + h.tri_parts_b) * 1024;
-    std::vector<unsigned long long> t(cnt);
-    B200_CUDA(cudaStreamSynchronize(h.stream));
-    B200_CUDA(cudaMemcpy(t.data(), h.d_trace.p, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (FILE *f = fopen(path, "wb")) { int hdr[2] = {h.tri_parts_f, h.tri_parts_b}; fwrite(hdr, sizeof hdr, 1, f); fwrite(t.data(), sizeof(unsigned long long), cnt, f); fclose(f); }
-  }
 }
 
 }  // namespace b200

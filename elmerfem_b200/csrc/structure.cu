@@ -8,7 +8,6 @@
 #include <thrust/execution_policy.h>
 #include <thrust/device_ptr.h>
 #include <algorithm>
-#include <climits>
 
 namespace b200 {
 
@@ -131,95 +130,6 @@ static void level_layout(int n, const std::vector<int> &level, int nlev, std::ve
   }
 }
 
-// Part layout of one sweep.  The rows are cut into P contiguous natural-order ranges ("parts", in the
-// order the sweep visits them: ascending for the forward, descending for the backward sweep); a part
-// only ever depends on itself and on parts visited earlier, so one CTA per part can walk its rows in
-// level order while the parts form a pipeline.  Inside a part the rows are sorted by (global level,
-// visiting order) and each level is padded to whole 32-row slices.  share[q] is the fraction of the
-// work (matrix entries) given to part q: earlier parts start earlier and may take more.
-static void part_layout(int n, const std::vector<int> &level, const std::vector<int> &rowlen, int P, double ramp, bool descending,
-                        std::vector<int> &perm, int &nslots, std::vector<int> &part_slice_begin) {
-  part_slice_begin.assign(P + 1, 0);
-  perm.clear();
-  if (n == 0) { nslots = 0; return; }
-  // work prefix in visiting order
-  std::vector<double> target(P + 1, 0.0);
-  { double tot = 0; for (int q = 0; q < P; ++q) { double sh = 1.0 - (1.0 - ramp) * (P > 1 ? (double)q / (P - 1) : 0.0); tot += sh; target[q + 1] = tot; }
-    for (int q = 0; q <= P; ++q) target[q] /= tot; }
-  long long total = 0; for (int i = 0; i < n; ++i) total += rowlen[i] + 2;
-  std::vector<int> cut(P + 1, 0);      // in visiting positions 0..n
-  { long long acc = 0; int q = 1;
-    for (int v = 0; v < n; ++v) {
-      int i = descending ? n - 1 - v : v;
-      acc += rowlen[i] + 2;
-      while (q < P && (double)acc >= target[q] * (double)total) cut[q++] = v + 1;
-    }
-    while (q <= P) cut[q++] = n; }
-  perm.reserve((size_t)n + (size_t)P * 64);
-  std::vector<int> cnt, pos;
-  for (int q = 0; q < P; ++q) {
-    part_slice_begin[q] = (int)(perm.size() / 32);
-    const int v0 = cut[q], v1 = cut[q + 1];
-    if (v1 <= v0) continue;
-    int lmin = INT_MAX, lmax = -1;
-    for (int v = v0; v < v1; ++v) { int i = descending ? n - 1 - v : v; lmin = std::min(lmin, level[i]); lmax = std::max(lmax, level[i]); }
-    cnt.assign((size_t)(lmax - lmin + 2), 0);
-    for (int v = v0; v < v1; ++v) { int i = descending ? n - 1 - v : v; cnt[level[i] - lmin + 1]++; }
-    // padded start of each level
-    pos.assign((size_t)(lmax - lmin + 1), 0);
-    size_t base = perm.size(), off = 0;
-    for (int l = 0; l <= lmax - lmin; ++l) { pos[l] = (int)off; off += ((size_t)cnt[l + 1] + 31) / 32 * 32; }
-    B200_REQUIRE(base + off < 2147483647ULL, "part layout exceeds int32 slots");
-    perm.resize(base + off, -1);
-    for (int v = v0; v < v1; ++v) { int i = descending ? n - 1 - v : v; perm[base + pos[level[i] - lmin]++] = i; }
-  }
-  part_slice_begin[P] = (int)(perm.size() / 32);
-  nslots = (int)perm.size();
-}
-
-// Column ids of a part-mode plan -> source codes, plus the per-slice dataflow metadata of k_sptrsv_tok.
-//   code >= 0 : slot in the global (L2-resident) solve vector
-//   code <  0 : ~(ring index | same_round << 16): the producer belongs to the same part and ran in the
-//               same round (needs the mbarrier token) or at most TRI_RR-2 rounds earlier (final)
-// meta[slice].x = pred | succ << 16: warps of the same round this slice waits for / has to wake;
-// meta[slice].y = npre: entries every lane may consume before the token (none of them is same-round).
-__global__ void k_tri_codes(int nslots, const long long *__restrict__ ptr, const int *__restrict__ len, int *cols,
-                            const int *__restrict__ slot_of_row, const int *__restrict__ part_of_slice,
-                            const int *__restrict__ part_begin, int2 *meta) {
-  int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= nslots) return;                                  // nslots is a multiple of 32: whole warps leave
-  const int lane = threadIdx.x & 31, slice = slot >> 5;
-  const long long base = ptr[slice] + lane;
-  const int l = len[slot];
-  const int part = part_of_slice[slice], b0 = part_begin[part];
-  const int kc = slice - b0, rc = kc / TRI_NW;
-  int first_same = 255; unsigned predbits = 0;
-  for (int j = 0; j < l; ++j) {
-    const int sp = slot_of_row[cols[base + (long long)j * 32]];
-    const int slp = sp >> 5;
-    int code = sp;
-    if (part_of_slice[slp] == part) {
-      const int kp = slp - b0, rp = kp / TRI_NW;
-      if (rc - rp <= TRI_RR - 2) {
-        const int same = (rp == rc) ? 1 : 0;
-        code = ~(((kp % (TRI_RR * TRI_NW)) * 32 + (sp & 31)) | (same << 16));
-        if (same) {
-          first_same = min(first_same, j);
-          predbits |= 1u << (kp % TRI_NW);
-          atomicOr(&meta[slp].x, (int)((1u << (kc % TRI_NW)) << 16));
-        }
-      }
-    }
-    cols[base + (long long)j * 32] = code;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    first_same = min(first_same, __shfl_xor_sync(0xffffffffu, first_same, o));
-    predbits |= __shfl_xor_sync(0xffffffffu, predbits, o);
-  }
-  if (lane == 0) { if (predbits) atomicOr(&meta[slice].x, (int)predbits); meta[slice].y = first_same; }
-}
-
 void tri_analyse(Handle &h) {
   if (h.tri_ready) return;
   const int n = h.n;
@@ -240,43 +150,25 @@ void tri_analyse(Handle &h) {
   h.nlev_f = nlf; h.nlev_b = nlb;
   std::vector<int> pf, pb; int nsf = 0, nsb = 0;
   std::vector<int> gf, gb, cf, cb;
-  // global level order: the order in which the factorisation visits the rows, and the plan of the level-mode solves
   level_layout(n, lf, nlf, pf, nsf, false, gf, cf);
-  h.d_order_f.ensure(nsf); h.n_order_f = nsf;
-  if (nsf) B200_CUDA(cudaMemcpyAsync(h.d_order_f.p, pf.data(), (size_t)nsf * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-  B200_CUDA(cudaStreamSynchronize(h.stream));
-  std::vector<int> pbf, pbb;           // part boundaries in slices
-  if (h.tri_mode == 1) {
-    int maxp = h.tri_max_parts > 0 ? h.tri_max_parts : NUM_SMS;
-    int P = std::max(1, std::min(maxp, (n + h.tri_rows_per_part_min - 1) / std::max(1, h.tri_rows_per_part_min)));
-    std::vector<int> ll(n), lu(n);
-    for (int i = 0; i < n; ++i) { ll[i] = diag[i] - rows[i]; lu[i] = rows[i + 1] - diag[i] - 1; }
-    part_layout(n, lf, ll, P, h.tri_ramp, false, pf, nsf, pbf);
-    part_layout(n, lb, lu, P, h.tri_ramp, true, pb, nsb, pbb);
-    h.tri_parts_f = h.tri_parts_b = P;
-    h.d_part_begin_f.ensure(P + 1); h.d_part_begin_b.ensure(P + 1);
-    B200_CUDA(cudaMemcpyAsync(h.d_part_begin_f.p, pbf.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-    B200_CUDA(cudaMemcpyAsync(h.d_part_begin_b.p, pbb.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-  } else {
-    level_layout(n, lb, nlb, pb, nsb, true, gb, cb);
-    h.L.gate.ensure(gf.size()); h.U.gate.ensure(gb.size());
-    h.d_lvlcnt_f.ensure(cf.size()); h.d_lvlcnt_b.ensure(cb.size());
-    if (!cf.empty()) B200_CUDA(cudaMemcpyAsync(h.d_lvlcnt_f.p, cf.data(), cf.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-    if (!cb.empty()) B200_CUDA(cudaMemcpyAsync(h.d_lvlcnt_b.p, cb.data(), cb.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-    if (!gf.empty()) B200_CUDA(cudaMemcpyAsync(h.L.gate.p, gf.data(), gf.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-    if (!gb.empty()) B200_CUDA(cudaMemcpyAsync(h.U.gate.p, gb.data(), gb.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-  }
+  level_layout(n, lb, nlb, pb, nsb, true, gb, cb);
   h.L.perm.ensure(nsf); h.U.perm.ensure(nsb);
+  h.L.gate.ensure(gf.size()); h.U.gate.ensure(gb.size());
+  h.d_lvlcnt_f.ensure(cf.size()); h.d_lvlcnt_b.ensure(cb.size());
   h.tri_counters.ensure(((size_t)nlf + nlb + 2) * 32);
+  if (!cf.empty()) B200_CUDA(cudaMemcpyAsync(h.d_lvlcnt_f.p, cf.data(), cf.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (!cb.empty()) B200_CUDA(cudaMemcpyAsync(h.d_lvlcnt_b.p, cb.data(), cb.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (!gf.empty()) B200_CUDA(cudaMemcpyAsync(h.L.gate.p, gf.data(), gf.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (!gb.empty()) B200_CUDA(cudaMemcpyAsync(h.U.gate.p, gb.data(), gb.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   if (nsf) B200_CUDA(cudaMemcpyAsync(h.L.perm.p, pf.data(), (size_t)nsf * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   if (nsb) B200_CUDA(cudaMemcpyAsync(h.U.perm.p, pb.data(), (size_t)nsb * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   B200_CUDA(cudaStreamSynchronize(h.stream));
   build_sell(h, h.L, 1, h.L.perm.p, nsf);
   build_sell(h, h.U, 2, h.U.perm.p, nsb);
-  // The solves keep their vectors in slot order: a warp's 32 rows store one coalesced line, and the
-  // entries it gathers sit in neighbouring slots instead of being strewn over the natural numbering.
-  // Columns of L/U are renumbered to slots (level mode) or to source codes (part mode); the backward
-  // sweep reads its right-hand side (the forward result, L-slot order) through urhs.
+  // The solves keep their vectors in level (slot) order: a warp's 32 rows store one coalesced line, and
+  // the entries it gathers from the previous levels sit in neighbouring slots instead of being strewn
+  // over the natural numbering.  Columns of L/U are renumbered to slots; the backward sweep reads its
+  // right-hand side (the forward result, L-slot order) through urhs.
   {
     std::vector<int> slotL(std::max(n, 1), 0), slotU(std::max(n, 1), 0), urhs(std::max(nsb, 1), 0);
     for (int s = 0; s < nsf; ++s) if (pf[s] >= 0) slotL[pf[s]] = s;
@@ -286,39 +178,10 @@ void tri_analyse(Handle &h) {
       B200_CUDA(cudaMemcpyAsync(dL.p, slotL.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
       B200_CUDA(cudaMemcpyAsync(dU.p, slotU.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
       B200_CUDA(cudaMemcpyAsync(h.d_urhs.p, urhs.data(), (size_t)nsb * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-      if (h.tri_mode == 1) {
-        auto part_of = [&](const std::vector<int> &pbeg, int nslices) {
-          std::vector<int> v((size_t)std::max(nslices, 1), 0);
-          for (int q = 0; q + 1 < (int)pbeg.size(); ++q) for (int sl = pbeg[q]; sl < pbeg[q + 1]; ++sl) v[sl] = q;
-          return v;
-        };
-        std::vector<int> posf = part_of(pbf, nsf / 32), posb = part_of(pbb, nsb / 32);
-        DBuf<int> dpf, dpb; dpf.ensure(posf.size()); dpb.ensure(posb.size());
-        B200_CUDA(cudaMemcpyAsync(dpf.p, posf.data(), posf.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-        B200_CUDA(cudaMemcpyAsync(dpb.p, posb.data(), posb.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-        h.d_meta_f.ensure((size_t)std::max(nsf / 32, 1) * 2); h.d_meta_b.ensure((size_t)std::max(nsb / 32, 1) * 2);
-        B200_CUDA(cudaMemsetAsync(h.d_meta_f.p, 0, (size_t)std::max(nsf / 32, 1) * 2 * sizeof(int), h.stream));
-        B200_CUDA(cudaMemsetAsync(h.d_meta_b.p, 0, (size_t)std::max(nsb / 32, 1) * 2 * sizeof(int), h.stream));
-        if (nsf) k_tri_codes<<<(nsf + 255) / 256, 256, 0, h.stream>>>(nsf, h.L.ptr.p, h.L.len.p, h.L.cols.p, dL.p, dpf.p, h.d_part_begin_f.p, (int2 *)h.d_meta_f.p);
-        if (nsb) k_tri_codes<<<(nsb + 255) / 256, 256, 0, h.stream>>>(nsb, h.U.ptr.p, h.U.len.p, h.U.cols.p, dU.p, dpb.p, h.d_part_begin_b.p, (int2 *)h.d_meta_b.p);
-        {                                                 // L slot -> U slot of the same row: the forward sweep scatters its result there
-          std::vector<int> l2u((size_t)std::max(nsf, 1), 0);
-          for (int sl = 0; sl < nsf; ++sl) if (pf[sl] >= 0) l2u[sl] = slotU[pf[sl]];
-          h.d_l2u.ensure(l2u.size());
-          B200_CUDA(cudaMemcpyAsync(h.d_l2u.p, l2u.data(), l2u.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
-          B200_CUDA(cudaStreamSynchronize(h.stream));
-        }
-        h.d_bl.ensure(std::max(nsf, 1)); h.d_bu.ensure(std::max(nsb, 1));
-        B200_CUDA(cudaMemsetAsync(h.d_bu.p, 0, (size_t)std::max(nsb, 1) * sizeof(double), h.stream));
-        B200_CUDA(cudaGetLastError());
-        B200_CUDA(cudaStreamSynchronize(h.stream));
-        dpf.release(); dpb.release();
-      } else {
-        if (h.L.nstore) k_remap_cols<<<NUM_SMS * 8, 256, 0, h.stream>>>(h.L.nstore, h.L.cols.p, dL.p);
-        if (h.U.nstore) k_remap_cols<<<NUM_SMS * 8, 256, 0, h.stream>>>(h.U.nstore, h.U.cols.p, dU.p);
-        B200_CUDA(cudaGetLastError());
-        B200_CUDA(cudaStreamSynchronize(h.stream));
-      }
+      if (h.L.nstore) k_remap_cols<<<NUM_SMS * 8, 256, 0, h.stream>>>(h.L.nstore, h.L.cols.p, dL.p);
+      if (h.U.nstore) k_remap_cols<<<NUM_SMS * 8, 256, 0, h.stream>>>(h.U.nstore, h.U.cols.p, dU.p);
+      B200_CUDA(cudaGetLastError());
+      B200_CUDA(cudaStreamSynchronize(h.stream));
     }
     dL.release(); dU.release();
   }
