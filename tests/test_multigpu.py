@@ -1,0 +1,105 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): two processes, one GPU each, NCCL halo exchange
+and allreduce inside the library.  Reference = the oracle on the GLOBAL system with the block-Jacobi
+ILU0 the reference's MPI path applies (ILU0 of InsideMatrix, the owned x owned block of every rank:
+fem/src/SParIterSolver.F90:2491-2497), i.e. the reference algorithm at the same partition count."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+EX, EY, EZ, WORLD = 14, 12, 31, 2
+TOL = 1e-8
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out_q, method, precond):
+    os.environ["LOCAL_RANK"] = str(rank)
+    import torch
+    import torch.distributed as dist
+    import elmerfem_b200 as B
+    from elmerfem_b200 import synth
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        def allsum(v):
+            t = torch.tensor([v], dtype=torch.float64); dist.all_reduce(t); return float(t.item())
+        p = synth.heat_slab(EX, EY, EZ, rank, world, allreduce_sum=allsum)
+        ids = [B.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        M = B.Matrix()
+        M.comm_init(world, rank, ids[0])
+        M.set_partition(p["gn"], p["rows"], p["cols"], p["goffset"], 1, 1)
+        M.set_values(p["vals"])
+        plan = M.halo_plan()
+        got = M.solve(p["b"], method=method, precond=precond, tol=TOL, maxit=500, bicgstabl_l=4)
+        # y = A x through the halo exchange, for a vector every rank can evaluate
+        lo, hi = p["goffset"][rank], p["goffset"][rank + 1]
+        xg = np.sin(0.37 * np.arange(lo, hi) + 1.0)
+        y = M.matvec(xg)
+        out_q.put((rank, {k: v.tolist() for k, v in plan.items()}, got["x"].tolist(), got["info"], got["iters"], y.tolist()))
+        dist.barrier()
+        M.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("method,precond", [("bicgstab", "ilu0"), ("cg", "diagonal"), ("bicgstabl", "ilu0"), ("gcr", "none")])
+def test_two_gpu_parity(oracle, b200, method, precond):
+    import ctypes as C
+    n = C.c_int(0)
+    if b200.lib().b200_device_count(C.byref(n)) != 0 or n.value < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    import torch.multiprocessing as mp
+    import scipy.sparse as sp
+    from elmerfem_b200 import synth
+    from oracle import halo_oracle as HO
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, WORLD, port, q, method, precond)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # global system, scaled exactly like the slabs
+    xyz, el = synth.grid_hex8(EX, EY, EZ, 1.0, EY / EX, EZ / EX)
+    r, c, d = synth.crs_structure(xyz.shape[0], el, 1)
+    v, rhs = synth.assemble(0, [1.0], xyz, el, 1, r, c, uniform=True)
+    A = synth.CRS(r, c, d, v, 1)
+    synth.dirichlet(A, rhs, synth.boundary_nodes(EX, EY, EZ, "all"), 0.0, False)
+    synth.scale_system(A, rhs)
+    plane = (EX + 1) * (EY + 1)
+    goff = [plane * l for l in synth.slab_layers(EZ + 1, WORLD)]
+    # integer work: the halo lists built through NCCL equal the reference construction, bit for bit
+    S = A.to_scipy()
+    ref_plan = HO.distribute([(p_[0], p_[1]) for p_ in HO.split_rows(S, goff)], goff)
+    for rank, plan, _, _, _, _ in res:
+        for k in ["neigh", "send_ptr", "send_idx", "recv_ptr", "ghost_gid"]:
+            assert np.array_equal(np.array(plan[k], dtype=np.int32), ref_plan[rank][k]), (rank, k)
+    # SpMV with halo exchange
+    xg = np.sin(0.37 * np.arange(A.n) + 1.0)
+    y = np.concatenate([np.array(r_[5]) for r_ in res])
+    yref = S @ xg
+    assert np.abs(y - yref).max() <= 1e-13 * np.abs(yref).max()
+    # Krylov parity against the reference algorithm with block-Jacobi ILU0
+    block = np.searchsorted(goff, np.arange(A.n), side="right") - 1
+    rowid = np.repeat(np.arange(A.n), np.diff(A.rows))
+    Abd = A.copy()
+    Abd.vals[block[rowid] != block[A.cols - 1]] = 0.0
+    ilu = oracle.ilu0(Abd) if precond == "ilu0" else None
+    ref = oracle.itersolve(A, rhs, method=method, precond=precond, ilu=ilu, tol=TOL, maxit=500, bicgstabl_l=4)
+    x = np.concatenate([np.array(r_[2]) for r_ in res])
+    infos = {r_[3] for r_ in res}; iters = {r_[4] for r_ in res}
+    assert infos == {1} and ref["info"] == 1
+    assert len(iters) == 1
+    it = iters.pop()
+    assert abs(it - ref["iters"]) <= max(1, int(np.ceil(0.02 * ref["iters"]))), (it, ref["iters"])
+    assert np.linalg.norm(x - ref["x"]) / np.linalg.norm(ref["x"]) <= 10 * TOL
