@@ -253,10 +253,14 @@ def run_b200(args):
         share_spmv = 3 * spmv_ms_max * ipi / (solve_ms / args.steps)
         share_lu = 2 * lu_ms_max * ipi / (solve_ms / args.steps)
         dominant = "lu" if share_lu > share_spmv else "spmv"
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(prob["name"], {})
         roof = {"spmv": {"kernel": "k_spmv_sell", "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
-                         "traffic": None, "bytes_per_launch": bs, "ms_per_launch": spmv_ms_max, "share_of_step": share_spmv, "peak_source": peak_src},
+                         "traffic": traffic.get("spmv"), "bytes_per_launch": bs, "ms_per_launch": spmv_ms_max, "share_of_step": share_spmv, "peak_source": peak_src},
                 "lu": {"kernel": "k_sptrsv (L then U sweep)", "bound": "hbm", "achieved": lu_gbs, "peak": peak, "unit": "GB/s", "frac": lu_gbs / peak,
-                       "traffic": None, "bytes_per_launch": bl, "ms_per_launch": lu_ms_max, "share_of_step": share_lu, "peak_source": peak_src}}
+                       "traffic": traffic.get("lu"), "bytes_per_launch": bl, "ms_per_launch": lu_ms_max, "share_of_step": share_lu, "peak_source": peak_src}}
         out = {
             "metric": "fp64 Krylov iterations/s x global Mdof (BiCGStab+ILU0, heat 200^3 per GPU); iters_per_s and spmv_gbs beside it",
             "value": its * gn / 1e6, "unit": "Mdof*iterations/s",
