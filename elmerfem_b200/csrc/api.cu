@@ -55,6 +55,11 @@ static void ensure_runtime(Handle &h) {
   h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 4));
   h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", 100);
   h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
+  h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", 0);   // 0 level kernel (default), 1 task kernel, -1 time both and pick
+  h.tt_rows = env_int("B200_TT_ROWS", 0);
+  h.tt_wpb = env_int("B200_TT_WPB", 0);
+  h.tt_wait_ns = (unsigned)env_int("B200_TT_WAIT_NS", 100);
+  h.tt_pf = env_int("B200_TT_PF", 16);
   h.blas_blocks = env_int("B200_BLAS_BLOCKS", NUM_SMS * 8);
   if (h.blas_blocks > MAX_RED_BLOCKS) h.blas_blocks = MAX_RED_BLOCKS;
 }
@@ -100,6 +105,7 @@ void install_structure(Handle &h, int n, long long nnz, std::vector<int> &&rows0
   if (n) B200_CUDA(cudaMemcpyAsync(h.d_diag.p, h.h_diag.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   B200_CUDA(cudaStreamSynchronize(h.stream));
   h.have_vals = h.have_prec = h.ilu_valid = h.ilu_exists = false; h.tri_ready = false;
+  tritask_release(h); h.tri_mode = h.tri_mode_cfg;
   h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0;
   structure_build(h);
   B200_CUDA(cudaStreamSynchronize(h.stream));
@@ -174,6 +180,7 @@ int b200_destroy(void **handle) {
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
     h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
     h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
+    tritask_release(*h);
     for (auto &w : h->work) w.release();
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();

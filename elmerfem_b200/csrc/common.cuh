@@ -97,6 +97,18 @@ constexpr int NSCAL = 64;
 
 struct Halo;   // multi-GPU plan (comm.cu)
 
+// Task-mode triangular solve plan (tritask.cu): one byte stream of per-step blocks per sweep.
+constexpr int TT_D = 16;     // depth (steps) of the per-warp shared-memory result ring
+constexpr int TT_CH = 16;    // operands per row requested one step ahead (registers)
+struct TriTask {
+  int ntasks = 0, rows_per_task = 0, slot_bytes = 16, maxw = 0; bool upper = false;
+  long long nsteps = 0, nfill = 0; size_t nbytes = 0;
+  DBuf<int> step0;                 // ntasks+1: first step of each task
+  DBuf<uint2> desc;                // per step: {offset, size} of its block in 16-byte units
+  DBuf<unsigned char> stream;      // the blocks
+  DBuf<unsigned> fill_dst; DBuf<int> fill_src;   // stream double index <- position in the ILU value array
+};
+
 struct Handle {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -118,6 +130,9 @@ struct Handle {
   DBuf<int> tri_counters; int tri_maxw = 0, tri_lookahead = 2; unsigned tri_gate_sleep = 100, tri_spin_sleep = 0;
   DBuf<int> d_lvlcnt_f, d_lvlcnt_b;              // slices per level (forward / backward)
   DBuf<int> d_urhs; DBuf<double> d_yl, d_xu;     // backward rhs map (U slot -> L slot); slot-ordered solve vectors
+  // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
+  TriTask TL, TU; bool tt_ready = false; int tri_mode = 0, tri_mode_cfg = 0, tt_rows = 0, tt_wpb = 0; unsigned tt_wait_ns = 100; int tt_pf = 16; DBuf<double> d_ytask, d_xtask;
+  double tt_ms_level = 0, tt_ms_task = 0;
   // workspace
   std::vector<DBuf<double>> work; DBuf<double> d_b, d_x, d_tmp, d_P;
   DBuf<double> red_partials; DBuf<unsigned int> red_counters; DBuf<double> scal; DBuf<Ctrl> ctrl;
@@ -223,6 +238,11 @@ void tri_analyse(Handle &h);                           // levels + L/U level-sor
 void ilu0_factor(Handle &h);                           // d_ilu from d_prec/d_vals, refresh L/U values
 void lu_apply(Handle &h, double *u, const double *v);  // u = (LU)^-1 v   (device pointers)
 void diag_apply(Handle &h, double *u, const double *v);
+void tritask_analyse(Handle &h);                       // task-mode plans for both sweeps (host, once per structure)
+void tritask_refresh_values(Handle &h);                // copy the ILU values into the plans' streams
+void tritask_release(Handle &h);
+bool tritask_usable(Handle &h);
+void lu_apply_task(Handle &h, double *u, const double *v);
 void halo_release(Handle &h);
 size_t vec_len(const Handle &h);                       // n + ghost entries: length every SpMV operand must have
 void matvec_full(Handle &h, const double *x, double *y);   // y = A x incl. halo exchange when partitioned

@@ -225,3 +225,33 @@ def test_empty_and_tiny_systems(oracle, b200):
             assert got["info"] == ref["info"]
             assert rel_l2(got["x"], ref["x"]) < 1e-9
         M.close()
+
+
+@pytest.mark.parametrize("mode", ["1", "-1"])
+def test_task_mode_triangular_solves_bit_exact(oracle, b200, heat, mode, monkeypatch):
+    """The task-mode kernel (csrc/tritask.cu; B200_TRI_MODE=1, or -1 = time both kernels and keep the faster) must
+    give the reference's CRS_LUSolve bit for bit: heat (13 lower entries), elasticity (rows wider than the 16-operand
+    register chunk), a nonsymmetric 4-dof pattern, and chains without any parallelism (tridiagonal)."""
+    import scipy.sparse as sp
+    monkeypatch.setenv("B200_TRI_MODE", mode)
+    cases = [heat[0]]
+    A2, b2 = oracle.elasticity_beam(10, 4, 4, lx=2.5); cases.append(A2)
+    A3, b3 = oracle.cavity_flow(5); cases.append(A3)
+    for n in [1, 2, 33, 700]:
+        Ms = sp.diags([np.full(n, 4.0)] + ([np.full(n - 1, -1.0)] * 2 if n > 1 else []), [0] + ([-1, 1] if n > 1 else [])).tocsr()
+        cases.append(oracle.CRS.from_scipy(Ms))
+    for A in cases:
+        M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, A.ndeg); M.set_values(A.vals)
+        M.factorize()
+        ilu = oracle.ilu0(A)
+        for seed in (7, 8):
+            v = np.random.RandomState(seed).standard_normal(A.n)
+            assert np.array_equal(M.lu_precondition(v), oracle.lu_precond(A, ilu, v)), (A.n, A.ndeg)
+        M.close()
+    A, b = heat
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, A.ndeg); M.set_values(A.vals)
+    ref = oracle.itersolve(A, b, method="bicgstab", precond="ilu0", tol=TOL, maxit=500)
+    got = M.solve(b, method="bicgstab", precond="ilu0", tol=TOL, maxit=500)
+    assert got["info"] == ref["info"] == 1 and got["iters"] == ref["iters"]
+    assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    M.close()
