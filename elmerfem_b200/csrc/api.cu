@@ -52,7 +52,7 @@ static void ensure_runtime(Handle &h) {
   memset(h.h_ctrl, 0, 2 * sizeof(Ctrl));
   h.spmv_blocks = env_int("B200_SPMV_BLOCKS", 0);
   h.tri_blocks_per_sm = env_int("B200_TRI_BLOCKS_PER_SM", 0);
-  h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 4));
+  h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 16));
   h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", 100);
   h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
   h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", 0);   // 0 level kernel (default), 1 task kernel, -1 time both and pick

@@ -69,7 +69,7 @@ struct Sell {
   DBuf<long long> ptr; DBuf<int> len; DBuf<int> perm; DBuf<int> cols; DBuf<double> vals;
   DBuf<int> start;                  // per slot: position in the CRS value array of entry 0
   DBuf<int> gate;                   // per slice (level plans): the slice's level
-  bool has_perm = false;
+  bool has_perm = false, ralign = false;   // ralign: rows right-aligned inside their slice (see k_sell_fill)
   SellView view() const {
     SellView v; v.nslots = nslots; v.nslices = nslices; v.ptr = ptr.p; v.len = len.p;
     v.perm = has_perm ? perm.p : nullptr; v.cols = cols.p; v.vals = vals.p; return v;

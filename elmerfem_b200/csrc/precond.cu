@@ -123,7 +123,9 @@ static int persistent_blocks(const void *kernel, int threads, int want_per_sm) {
 template <class... Args>
 static void launch_coresident(const void *kernel, int blocks, int threads, cudaStream_t st, Args... args) {
   void *argv[] = {(void *)&args...};
-  B200_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(threads), argv, 0, st));
+  static const bool coop = !(getenv("B200_TRI_COOP") && atoi(getenv("B200_TRI_COOP")) == 0);
+  if (coop) B200_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(threads), argv, 0, st));
+  else B200_CUDA(cudaLaunchKernel(kernel, dim3(blocks), dim3(threads), argv, 0, st));
 }
 
 static void tri_autotune(Handle &h);
@@ -180,6 +182,22 @@ __device__ __forceinline__ int ld_relaxed_i(const int *p) {
 // T are slot ids.  rhs_idx == nullptr: rhs is in natural order (forward sweep input); otherwise
 // rhs[rhs_idx[slot]] (backward sweep reading the forward result).  nat_out != nullptr: the result is
 // also scattered to natural order (the preconditioned vector handed back to the Krylov method).
+// guarded load of a result-vector entry: predicated in PTX, no branch
+__device__ __forceinline__ double ld_relaxed_pred(const double *p, bool pred, double old) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.relaxed.gpu.global.f64 %0, [%1]; }" : "+d"(old) : "l"(p), "r"((unsigned)pred));
+  return old;
+}
+// Rows of at most CH entries (one register chunk) take a path tuned for the critical dependency: what a
+// row still has to do AFTER its last operand became visible decides the time per level.  The operands
+// of the previous level are the entries next to the diagonal (natural FE numberings: the last TAIL
+// entries of a lower row, the first TAIL of an upper row; L is stored right-aligned so that these are
+// the same registers in every lane).  The other ("head") operands are normally there at the first
+// read: their products are formed, and for L already subtracted, while the tail is still being
+// polled; after the last arrival only TAIL multiply-subtract pairs (L) or TAIL pairs + the head
+// subtractions (U: the sum must run left to right and its first term arrives last) remain.  Every
+// guarded load is predicated and the loops are warp-uniform: no divergence bookkeeping on the path.
+// The arithmetic is unchanged: p = v*x rounded, s = s - p rounded, left to right.
+constexpr int TRI_TAIL = 6;
 template <bool UPPER, int CH>
 __global__ void __launch_bounds__(256, 2) k_sptrsv(SellView T, const int *__restrict__ slice_level, const int *__restrict__ lvl_slices,
                                                     int *lvl_done, int lookahead, unsigned gate_sleep, unsigned spin_sleep,
@@ -201,41 +219,112 @@ __global__ void __launch_bounds__(256, 2) k_sptrsv(SellView T, const int *__rest
     double s = row >= 0 ? rhs[rhs_idx ? rhs_idx[slot] : row] : 0.0;
     const double dinv = (UPPER && row >= 0) ? dinv_slot[slot] : 1.0;
     long long spins = 0;
-    bool gated = false;
-    for (int j0 = 0; j0 < W || !gated; j0 += CH) {
-      int c[CH]; double v[CH], xv[CH];
+    auto gate = [&]() {                                   // throttle: wait for the wavefront to come near
+      const int wl = slice_level[slice] - lookahead;
+      if (lane == 0 && wl >= 0) {
+        const int need = lvl_slices[wl];
+        while (ld_relaxed_i(lvl_done + wl * 32) < need) {
+          if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+          if (gate_sleep) __nanosleep(gate_sleep);
+        }
+      }
+      __syncwarp();
+    };
+    if (W <= CH) {
+      // register k <-> stored position k - sh; entry present iff lo <= k < hi
+      const int sh = UPPER ? 0 : CH - W;
+      const int lo = UPPER ? 0 : CH - len, hi = UPPER ? len : CH;
+      int c[CH]; double v[CH], x[CH];
 #pragma unroll
       for (int k = 0; k < CH; ++k) {                      // matrix entries: streamed from HBM ahead of the wavefront
-        const bool in = j0 + k < W;
-        c[k] = in ? ld_stream(cp + (j0 + k) * 32) : 0;
-        v[k] = in ? ld_stream(vp + (j0 + k) * 32) : 0.0;
+        const int pos = min(max(k - sh, 0), max(W - 1, 0));
+        c[k] = W ? ld_stream(cp + pos * 32) : 0;
+        v[k] = W ? ld_stream(vp + pos * 32) : 0.0;
       }
-      if (!gated) {                                       // throttle: wait for the wavefront to come near
-        const int wl = slice_level[slice] - lookahead;
-        if (lane == 0 && wl >= 0) {
-          const int need = lvl_slices[wl];
-          while (ld_relaxed_i(lvl_done + wl * 32) < need) {
-            if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
-            if (gate_sleep) __nanosleep(gate_sleep);
-          }
-        }
-        __syncwarp();
-        gated = true;
-      }
+      gate();
+      unsigned has = 0;
 #pragma unroll
-      for (int k = 0; k < CH; ++k) xv[k] = (j0 + k < len) ? ld_relaxed(out + c[k]) : 0.0;   // all gathers in flight
-      for (;;) {                                          // re-poll every entry still holding the sentinel, together
-        bool pending = false;
+      for (int k = 0; k < CH; ++k) has |= (unsigned)(k >= lo && k < hi) << k;
+      const double sent = __longlong_as_double((long long)SENTINEL);
 #pragma unroll
-        for (int k = 0; k < CH; ++k) pending |= is_sentinel(xv[k]);
-        if (!pending) break;
+      for (int k = 0; k < CH; ++k) x[k] = ld_relaxed_pred(out + c[k], (has >> k) & 1u, 0.0);   // all gathers in flight
+      constexpr unsigned TAILMASK = UPPER ? ((1u << TRI_TAIL) - 1u) : (((1u << TRI_TAIL) - 1u) << (CH - TRI_TAIL));
+      // head operands
+      unsigned pend = 0;
+#pragma unroll
+      for (int k = 0; k < CH; ++k) pend |= (unsigned)(is_sentinel(x[k])) << k;
+      pend &= has;
+      while (__any_sync(0xffffffffu, (pend & ~TAILMASK) != 0)) {
         if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
         if (spin_sleep) __nanosleep(spin_sleep);
 #pragma unroll
-        for (int k = 0; k < CH; ++k) if (is_sentinel(xv[k])) xv[k] = ld_relaxed(out + c[k]);
+        for (int k = 0; k < CH; ++k) {
+          if (TAILMASK & (1u << k)) continue;
+          x[k] = ld_relaxed_pred(out + c[k], (pend >> k) & 1u, x[k]);
+          if (!is_sentinel(x[k])) pend &= ~(1u << k);
+        }
       }
+      double p[CH];
 #pragma unroll
-      for (int k = 0; k < CH; ++k) if (j0 + k < len) s = nfms(s, v[k], xv[k]);
+      for (int k = 0; k < CH; ++k) p[k] = __dmul_rn(v[k], x[k]);
+      if (!UPPER) {
+#pragma unroll
+        for (int k = 0; k < CH - TRI_TAIL; ++k) { const double t = __dsub_rn(s, p[k]); s = (has >> k) & 1u ? t : s; }
+      }
+      // tail operands: the previous level
+#pragma unroll
+      for (int k = 0; k < CH; ++k) if (TAILMASK & (1u << k)) { x[k] = ld_relaxed_pred(out + c[k], (pend >> k) & 1u, x[k]); if (!is_sentinel(x[k])) pend &= ~(1u << k); }
+      while (__any_sync(0xffffffffu, pend != 0)) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        if (spin_sleep) __nanosleep(spin_sleep);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          if (!(TAILMASK & (1u << k))) continue;
+          x[k] = ld_relaxed_pred(out + c[k], (pend >> k) & 1u, x[k]);
+          if (!is_sentinel(x[k])) pend &= ~(1u << k);
+        }
+      }
+      (void)sent;
+      if (!UPPER) {
+#pragma unroll
+        for (int k = CH - TRI_TAIL; k < CH; ++k) { const double t = __dsub_rn(s, __dmul_rn(v[k], x[k])); s = (has >> k) & 1u ? t : s; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < TRI_TAIL; ++k) { const double t = __dsub_rn(s, __dmul_rn(v[k], x[k])); s = (has >> k) & 1u ? t : s; }
+#pragma unroll
+        for (int k = TRI_TAIL; k < CH; ++k) { const double t = __dsub_rn(s, p[k]); s = (has >> k) & 1u ? t : s; }
+      }
+    } else {
+      const int first = UPPER ? 0 : W - len, last = UPPER ? len : W;
+      bool gated = false;
+      for (int j0 = 0; j0 < W; j0 += CH) {
+        int c[CH]; double v[CH], xv[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          const int pos = min(j0 + k, W - 1);
+          c[k] = ld_stream(cp + pos * 32);
+          v[k] = ld_stream(vp + pos * 32);
+        }
+        if (!gated) { gate(); gated = true; }
+        unsigned has = 0;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) has |= (unsigned)(j0 + k >= first && j0 + k < last) << k;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) xv[k] = ld_relaxed_pred(out + c[k], (has >> k) & 1u, 0.0);
+        unsigned pend = 0;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) pend |= (unsigned)(is_sentinel(xv[k])) << k;
+        pend &= has;
+        while (__any_sync(0xffffffffu, pend != 0)) {
+          if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+          if (spin_sleep) __nanosleep(spin_sleep);
+#pragma unroll
+          for (int k = 0; k < CH; ++k) { xv[k] = ld_relaxed_pred(out + c[k], (pend >> k) & 1u, xv[k]); if (!is_sentinel(xv[k])) pend &= ~(1u << k); }
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) { const double t = nfms(s, v[k], xv[k]); s = (has >> k) & 1u ? t : s; }
+      }
+      if (!gated) gate();
     }
     if (row >= 0) {
       double res = UPPER ? __dmul_rn(dinv, s) : s;

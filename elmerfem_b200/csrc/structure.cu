@@ -40,14 +40,17 @@ __global__ void k_slice_entries(int nslices, const int *__restrict__ len, long l
 
 // Transposes one slice of CRS data into SELL order.  A warp walks its 32 rows entry by entry:
 // lane owns one row; reads are served from L1 (a row is 1-3 cache lines), writes are coalesced.
+// ralign: rows are pushed to the END of their slice (entry j of a row of length l at position W - l + j),
+// so that the last entries of all 32 rows sit in the same positions (forward triangular plan).
 template <class T, bool kSubBase>
 __global__ void k_sell_fill(int nslots, const long long *__restrict__ ptr, const int *__restrict__ start,
-                            const int *__restrict__ len, const T *__restrict__ src, T *__restrict__ dst) {
+                            const int *__restrict__ len, const T *__restrict__ src, T *__restrict__ dst, bool ralign) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= nslots) return;
   int lane = threadIdx.x & 31;
   long long base = ptr[slot >> 5] + lane;
   int s = start[slot], l = len[slot];
+  if (ralign) base += (long long)((int)((ptr[(slot >> 5) + 1] - ptr[slot >> 5]) >> 5) - l) * 32;
   for (int j = 0; j < l; ++j) dst[base + (long long)j * 32] = src[s + j];
 }
 
@@ -77,7 +80,7 @@ void sell_finish(Handle &h, Sell &S, int nslots, bool has_perm, const int *src_c
   if (S.nstore) {
     B200_CUDA(cudaMemsetAsync(S.cols.p, 0, S.nstore * sizeof(int), st));
     B200_CUDA(cudaMemsetAsync(S.vals.p, 0, S.nstore * sizeof(double), st));
-    k_sell_fill<int, false><<<(nslots + 255) / 256, 256, 0, st>>>(nslots, S.ptr.p, S.start.p, S.len.p, src_cols, S.cols.p);
+    k_sell_fill<int, false><<<(nslots + 255) / 256, 256, 0, st>>>(nslots, S.ptr.p, S.start.p, S.len.p, src_cols, S.cols.p, S.ralign);
   }
   B200_CUDA(cudaGetLastError());
 }
@@ -90,7 +93,7 @@ static void build_sell(Handle &h, Sell &S, int kind, const int *d_perm, int nslo
 
 void sell_refresh_values(Handle &h, Sell &S, const double *crs_vals) {
   if (S.nslots == 0 || S.nstore == 0) return;
-  k_sell_fill<double, false><<<(S.nslots + 255) / 256, 256, 0, h.stream>>>(S.nslots, S.ptr.p, S.start.p, S.len.p, crs_vals, S.vals.p);
+  k_sell_fill<double, false><<<(S.nslots + 255) / 256, 256, 0, h.stream>>>(S.nslots, S.ptr.p, S.start.p, S.len.p, crs_vals, S.vals.p, S.ralign);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -163,6 +166,7 @@ void tri_analyse(Handle &h) {
   if (nsf) B200_CUDA(cudaMemcpyAsync(h.L.perm.p, pf.data(), (size_t)nsf * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   if (nsb) B200_CUDA(cudaMemcpyAsync(h.U.perm.p, pb.data(), (size_t)nsb * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   B200_CUDA(cudaStreamSynchronize(h.stream));
+  h.L.ralign = true;
   build_sell(h, h.L, 1, h.L.perm.p, nsf);
   build_sell(h, h.U, 2, h.U.perm.p, nsb);
   // The solves keep their vectors in level (slot) order: a warp's 32 rows store one coalesced line, and
