@@ -108,6 +108,19 @@ def make_problem(args, rank, nranks, allreduce_sum=None):
     """Scaled system of this rank.  Returns dict(A=CRS local, b, gn, goffset, cols_global or None)."""
     from elmerfem_b200 import synth
     ne = args.ne
+    if args.workload == "elasticity":
+        # BASELINE configs[4] (C5): ~8M dofs per GPU, 3 dofs/node, beam along z cut into z-slabs
+        nz = args.elas_layers
+        part = synth.elasticity_slab(ne, ne, nz * nranks - 1, rank, nranks, allreduce_sum=allreduce_sum)
+        name = "elasticity_beam_%dx%dx%d_hex8_3dof_z-slabs" % (ne, ne, nz * nranks - 1)
+        if nranks > 1:
+            return dict(A=None, b=part["b"], gn=part["gn"], part=part, name=name)
+        n = part["rows"].size - 1
+        rowid = np.repeat(np.arange(1, n + 1, dtype=np.int64), np.diff(part["rows"]))
+        diag = (np.flatnonzero(part["cols"] == rowid) + 1).astype(np.int32)
+        assert diag.size == n
+        A = synth.CRS(part["rows"], part["cols"], diag, part["vals"], 3)
+        return dict(A=A, b=part["b"], gn=n, part=None, name=name)
     if nranks == 1:
         A, b = synth.workload("heat", ne)
         return dict(A=A, b=b, gn=A.n, part=None, name="heat_cube_%d^3_hex8" % ne)
@@ -150,7 +163,7 @@ def run_b200(args):
         dist.broadcast_object_list(ids, src=0)
         M.comm_init(world, rank, ids[0])
         p = prob["part"]
-        M.set_partition(p["gn"], p["rows"], p["cols"], p["goffset"], 1, 1)
+        M.set_partition(p["gn"], p["rows"], p["cols"], p["goffset"], 1, p.get("ndeg", 1))
         n, nnz = p["rows"].size - 1, p["cols"].size
         vals = p["vals"]
     t_struct = time.time() - t0
@@ -165,7 +178,12 @@ def run_b200(args):
     d_b[:n].copy_(b_host)
     d_x = torch.zeros(nvec, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
-    kw = dict(method="bicgstab", precond="ilu0", tol=TOL, maxit=MAXIT)
+    elas = args.workload == "elasticity"
+    if elas:   # C5: BiCGStab(l=4) + Jacobi; a step = the first `--elas-rounds` rounds (8 SpMV each), not a converged solve
+        kw = dict(method="bicgstabl", precond="diagonal", bicgstabl_l=4, tol=TOL, maxit=args.elas_rounds)
+    else:
+        kw = dict(method="bicgstab", precond="ilu0", tol=TOL, maxit=MAXIT)
+    label = "BiCGStab(l=4)+Jacobi, first %d rounds of 8 SpMV" % args.elas_rounds if elas else "BiCGStab+ILU0, tol 1e-8"
 
     def barrier():
         torch.cuda.synchronize()
@@ -174,7 +192,8 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        M.factorize()
+        if not elas:
+            M.factorize()
         d_x.zero_()
         torch.cuda.synchronize()
         r = M.solve_device(d_b.data_ptr(), d_x.data_ptr(), **kw)
@@ -201,7 +220,7 @@ def run_b200(args):
         r = step_resident()
         st = r["stats"]
         solve_ms += st["solve_ms"]; factor_ms += st["factor_ms"]; iters += r["iters"]; launches += st["launches"] + st["factor_launches"]
-        assert r["info"] == 1, "solve did not converge: HUTI_INFO=%d" % r["info"]
+        assert r["info"] == 1 or (elas and r["info"] == 2), "solve did not converge: HUTI_INFO=%d" % r["info"]
     barrier()
     wall = time.perf_counter() - wall0
     # ---- e2e through the host-buffer entry point
@@ -212,12 +231,12 @@ def run_b200(args):
     for _ in range(args.steps):
         r2, dt = step_e2e()
         e2e_s += dt; e2e_iters += r2["iters"]; h2d = r2["stats"]["h2d"]; d2h = r2["stats"]["d2h"] + 0
-        assert r2["info"] == 1
+        assert r2["info"] == 1 or (elas and r2["info"] == 2)
     barrier()
     clk = clocks.stop() if rank == 0 else None
     # ---- kernel rooflines, measured live with CUDA events on the solve stream
     spmv_ms = M.time_matvec(20)
-    lu_ms = M.time_lu(10)
+    lu_ms = M.time_lu(10) if not elas else 0.0
 
     def maxr(v):
         if dist is None:
@@ -247,10 +266,11 @@ def run_b200(args):
         e2e_its = e2e_iters / e2e_s
         bs, bl = spmv_bytes(n, nnz), lu_bytes(n, nnz)
         spmv_gbs = bs / (spmv_ms_max * 1e-3) / 1e9
-        lu_gbs = bl / (lu_ms_max * 1e-3) / 1e9
+        lu_gbs = bl / (lu_ms_max * 1e-3) / 1e9 if lu_ms_max > 0 else 0.0
         ipi = iters / args.steps
-        # share of the solve spent in each kernel family (per iteration: 3 SpMV + 2 LU applications)
-        share_spmv = 3 * spmv_ms_max * ipi / (solve_ms / args.steps)
+        # share of the solve spent in each kernel family (per iteration: 3 SpMV + 2 LU applications;
+        # BiCGStab(l=4): 8 SpMV per round, no triangular solves with Jacobi)
+        share_spmv = (8 if elas else 3) * spmv_ms_max * ipi / (solve_ms / args.steps)
         share_lu = 2 * lu_ms_max * ipi / (solve_ms / args.steps)
         dominant = "lu" if share_lu > share_spmv else "spmv"
         traffic = {}
@@ -262,14 +282,15 @@ def run_b200(args):
                 "lu": {"kernel": "k_sptrsv (L then U sweep)", "bound": "hbm", "achieved": lu_gbs, "peak": peak, "unit": "GB/s", "frac": lu_gbs / peak,
                        "traffic": traffic.get("lu"), "bytes_per_launch": bl, "ms_per_launch": lu_ms_max, "share_of_step": share_lu, "peak_source": peak_src}}
         out = {
-            "metric": "fp64 Krylov iterations/s x global Mdof (BiCGStab+ILU0, heat 200^3 per GPU); iters_per_s and spmv_gbs beside it",
+            "metric": ("fp64 Krylov iterations/s x global Mdof (BiCGStab(l=4)+Jacobi rounds, elasticity ~8M dof per GPU); iters_per_s and spmv_gbs beside it" if elas else
+                       "fp64 Krylov iterations/s x global Mdof (BiCGStab+ILU0, heat 200^3 per GPU); iters_per_s and spmv_gbs beside it"),
             "value": its * gn / 1e6, "unit": "Mdof*iterations/s",
             "iters_per_s": its, "spmv_gbs": spmv_gbs * world, "spmv_frac_of_hbm_peak": spmv_gbs / peak,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": solve_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": prob["name"] + ", BiCGStab+ILU0, tol 1e-8, Linear System Scaling on", "global_dofs": int(gn),
+            "config": {"workload": prob["name"] + ", " + label + ", Linear System Scaling on", "global_dofs": int(gn),
                        "global_nnz": int(nnz_tot), "dofs_per_gpu": int(n), "iterations_per_solve": ipi,
-                       "l2": "inputs (2.6 GB matrix per GPU) larger than L2; no flush", "parallelism": "row partition, z-slabs x%d" % world},
+                       "l2": "inputs (%.1f GB matrix per GPU) larger than L2; no flush" % (12.0 * nnz / 1e9), "parallelism": "row partition, z-slabs x%d" % world},
             "roofline": roof[dominant], "roofline_spmv": roof["spmv"], "roofline_lu": roof["lu"],
             "e2e": {"value": e2e_its * gn / 1e6, "unit": "Mdof*iterations/s", "iters_per_s": e2e_its, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
@@ -277,7 +298,10 @@ def run_b200(args):
             "iters_per_s_incl_factor": iters / ((solve_ms + factor_ms) / 1e3), "wall_s_timed_region": wall,
             "true_residual": res_true, "clocks": clk,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if elas:
+            out.pop("roofline_lu"); out["roofline"] = roof["spmv"]; out.pop("factor_ms"); out.pop("iters_per_s_incl_factor")
+            out["true_residual_note"] = "not converged by design (fixed number of rounds)"
+        if world == 1 and not args.no_cpu_baseline and not elas:
             out["cpu_baseline"] = cpu_baseline(prob, budget_s=args.cpu_budget)
     M.close()
     if dist is not None:
@@ -350,13 +374,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ne", type=int, default=200, help="elements per cube edge (200 = BASELINE configs[1])")
+    ap.add_argument("--ne", type=int, default=None, help="elements per edge of the cross-section (default 200 = BASELINE configs[1]; elasticity: 137)")
+    ap.add_argument("--workload", default="heat", choices=["heat", "elasticity"], help="heat = BASELINE configs[1] (default); elasticity = configs[4] (C5 weak scaling)")
+    ap.add_argument("--elas-layers", type=int, default=140, help="elasticity: node layers per GPU along the beam")
+    ap.add_argument("--elas-rounds", type=int, default=40, help="elasticity: BiCGStab(4) rounds per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.ne is None:
+        args.ne = 137 if args.workload == "elasticity" else 200
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -84,6 +84,23 @@ struct Halo {
   DBuf<double> d_vals_in, d_gvals;
   long long nnz_in = 0, nnz_g = 0;
   cudaEvent_t ev_pack = nullptr, ev_comm = nullptr;
+  // peer-memory exchange (same node): the pack kernel stores straight into the neighbours' receive buffers
+  bool p2p = false;
+  void *shm = nullptr;                                  // IPC-shared: recv[2][nghost] f64 | ready[nneigh] u64 | ack[nneigh] u64
+  double *recv[2] = {nullptr, nullptr};
+  unsigned long long *ready = nullptr, *ack = nullptr;  // ready[q]: last exchange whose data from neighbour q has landed here;
+                                                        // ack[q]: last exchange of mine neighbour q has consumed
+  std::vector<void *> peer_base;                        // opened IPC mappings, one per neighbour
+  DBuf<unsigned char> d_peers; DBuf<unsigned int> d_ticket;
+  unsigned long long seq = 0;
+};
+
+// what rank `me` needs to know about neighbour q to push into / acknowledge to its memory
+struct PeerDesc {
+  double *rdata[2];               // my segment of the neighbour's receive buffers
+  unsigned long long *rready;     // the neighbour's ready flag for me
+  unsigned long long *rack;       // the neighbour's ack flag for me
+  int begin, end;                 // my send segment [begin, end)
 };
 
 
@@ -143,6 +160,70 @@ static void plan_split(int N, const int *rows, const int *cols, int base, int lo
 
 size_t vec_len(const Handle &h) { return (size_t)h.n + (h.halo ? (size_t)h.halo->nghost : 0); }
 
+static void p2p_release(Handle &h, Halo &H) {
+  if (h.stream) cudaStreamSynchronize(h.stream);
+  for (void *b : H.peer_base) if (b) cudaIpcCloseMemHandle(b);
+  H.peer_base.clear();
+  if (H.shm) cudaFree(H.shm);
+  H.shm = nullptr; H.p2p = false; H.d_peers.release(); H.d_ticket.release();
+}
+
+// Sets up the peer-memory exchange: every rank publishes the IPC handle of its receive area; the layout of a
+// neighbour's area follows from the send-count matrix all ranks already hold.  Collective; all ranks
+// end up with the same answer (peer path on every rank, or the NCCL path on every rank).
+static void p2p_setup(Handle &h, Halo &H, const std::vector<int> &allcnt) {
+  const int np = h.nranks, me = h.rank;
+  const char *e = getenv("B200_HALO_P2P");
+  int ok = !(e && atoi(e) == 0) && H.nneigh <= 64;
+  cudaStream_t st = h.stream;
+  const size_t bytes = std::max<size_t>(64, (size_t)2 * H.nghost * sizeof(double) + (size_t)2 * H.nneigh * sizeof(unsigned long long));
+  cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof mine);
+  if (ok && (cudaMalloc(&H.shm, bytes) != cudaSuccess || cudaMemset(H.shm, 0, bytes) != cudaSuccess ||
+             cudaIpcGetMemHandle(&mine, H.shm) != cudaSuccess)) { cudaGetLastError(); ok = 0; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::vector<cudaIpcMemHandle_t> all(np);
+  DBuf<char> d_one, d_all; d_one.ensure(64); d_all.ensure((size_t)64 * np);
+  B200_CUDA(cudaMemcpyAsync(d_one.p, &mine, 64, cudaMemcpyHostToDevice, st));
+  B200_NCCL(nccl().AllGather(d_one.p, d_all.p, 64, ncclChar, (ncclComm_t)h.nccl, st));
+  B200_CUDA(cudaMemcpyAsync(all.data(), d_all.p, (size_t)64 * np, cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  std::vector<PeerDesc> peers(std::max(H.nneigh, 1));
+  H.peer_base.assign(H.nneigh, nullptr);
+  for (int q = 0; q < H.nneigh && ok; ++q) {
+    const int r = H.neigh[q];
+    // neighbour r's own plan: its neighbours ascending, receive offsets = prefix of what each sends to r
+    int qprime = -1, nneigh_r = 0; long long nghost_r = 0, off_me = 0;
+    for (int s2 = 0; s2 < np; ++s2) {
+      if (s2 == r) continue;
+      const int to_r = allcnt[(size_t)s2 * np + r], from_r = allcnt[(size_t)r * np + s2];
+      if (!(to_r || from_r)) continue;
+      if (s2 == me) { qprime = nneigh_r; off_me = nghost_r; }
+      ++nneigh_r; nghost_r += to_r;
+    }
+    if (qprime < 0 || cudaIpcOpenMemHandle(&H.peer_base[q], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); H.peer_base[q] = nullptr; ok = 0; break; }
+    double *base = (double *)H.peer_base[q];
+    unsigned long long *flags = (unsigned long long *)(base + 2 * nghost_r);
+    peers[q].rdata[0] = base + off_me; peers[q].rdata[1] = base + nghost_r + off_me;
+    peers[q].rready = flags + qprime; peers[q].rack = flags + nneigh_r + qprime;
+    peers[q].begin = H.send_ptr[q]; peers[q].end = H.send_ptr[q + 1];
+  }
+  // agree over all ranks
+  DBuf<int> d_ok; d_ok.ensure(1);
+  B200_CUDA(cudaMemcpyAsync(d_ok.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_NCCL(nccl().AllReduce(d_ok.p, d_ok.p, 1, ncclInt32, ncclMin, (ncclComm_t)h.nccl, st));
+  B200_CUDA(cudaMemcpyAsync(&ok, d_ok.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  d_one.release(); d_all.release(); d_ok.release();
+  if (!ok) { p2p_release(h, H); return; }
+  H.recv[0] = (double *)H.shm; H.recv[1] = H.recv[0] + H.nghost;
+  H.ready = (unsigned long long *)(H.recv[0] + 2 * (size_t)H.nghost); H.ack = H.ready + H.nneigh;
+  H.d_peers.ensure(peers.size() * sizeof(PeerDesc)); H.d_ticket.ensure(2);
+  B200_CUDA(cudaMemcpyAsync(H.d_peers.p, peers.data(), peers.size() * sizeof(PeerDesc), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemsetAsync(H.d_ticket.p, 0, 2 * sizeof(unsigned int), st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  H.seq = 0; H.p2p = true;
+}
+
 void halo_release(Handle &h) {
   if (h.halo) {
     Halo &H = *h.halo;
@@ -150,6 +231,7 @@ void halo_release(Handle &h) {
     H.d_oosrc.release(); H.d_vals_in.release(); H.d_gvals.release();
     if (H.ev_pack) cudaEventDestroy(H.ev_pack);
     if (H.ev_comm) cudaEventDestroy(H.ev_comm);
+    p2p_release(h, H);
     delete h.halo; h.halo = nullptr;
   }
   if (h.nccl) { nccl().CommDestroy((ncclComm_t)h.nccl); h.nccl = nullptr; }
@@ -165,6 +247,76 @@ void comm_allreduce_sum(Handle &h, double *d, int count) {
 __global__ void k_pack(int nsend, const int *__restrict__ idx, const double *__restrict__ x, double *__restrict__ buf) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nsend; k += gridDim.x * blockDim.x) buf[k] = x[idx[k]];
 }
+// ---- peer-memory exchange -------------------------------------------------------------------
+// Replaces Send_LocIf/Recv_LocIf (SParIterComm.F90:4719-4969) on one node: pack and send are ONE kernel
+// that gathers the boundary entries of x and stores them over NVLink into the receive buffer of the
+// owning neighbour, then raises that neighbour's `ready` flag (release.sys).  The receiver's ghost-block
+// kernel waits on its flags, consumes the buffer and acknowledges into the sender's memory; two
+// buffers (exchange parity) + the ack let a rank run at most two products ahead.  No second stream,
+// no NCCL kernel competing for SMs with the persistent SpMV grid, no host involvement.
+constexpr long long HALO_SPIN_LIMIT = 1LL << 28;
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool last_block(unsigned int *ticket) {
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  return last;
+}
+__global__ void __launch_bounds__(256) k_pack_push(int nsend, const int *__restrict__ idx, const double *__restrict__ x, const PeerDesc *__restrict__ peers,
+                                                    int nneigh, const unsigned long long *ack, unsigned long long seq, unsigned int *ticket, Ctrl *ctrl) {
+  // (no early exit on ctrl->done: the flag protocol must advance identically on every rank)
+  // the buffer of this parity was last filled for exchange seq-2: wait until every neighbour has consumed that one
+  if ((int)threadIdx.x < nneigh && seq > 2) {
+    long long spins = 0;
+    while (ld_acquire_sys(ack + threadIdx.x) + 2 < seq) {
+      if (++spins > HALO_SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
+  const int par = (int)(seq & 1ULL);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nsend; k += gridDim.x * blockDim.x) {
+    int q = 0;
+    while (k >= peers[q].end) ++q;
+    peers[q].rdata[par][k - peers[q].begin] = x[idx[k]];
+  }
+  __threadfence_system();
+  if (last_block(ticket) && (int)threadIdx.x < nneigh) st_release_sys(peers[threadIdx.x].rready, seq);
+}
+__global__ void __launch_bounds__(256) k_spmv_ghost_p2p(SellView G, const double *xg, double *__restrict__ y, const unsigned long long *ready,
+                                                         const PeerDesc *__restrict__ peers, int nneigh, unsigned long long seq, unsigned int *ticket, Ctrl *ctrl) {
+  if ((int)threadIdx.x < nneigh) {
+    long long spins = 0;
+    while (ld_acquire_sys(ready + threadIdx.x) < seq) {
+      if (++spins > HALO_SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = slot < G.nslots ? G.perm[slot] : -1;
+  if (row >= 0) {
+    const int lane = threadIdx.x & 31;
+    const long long p0 = G.ptr[slot >> 5];
+    const int len = G.len[slot];
+    double acc = 0.0;
+    for (int j = 0; j < len; ++j) acc = nfma(acc, __ldcg(xg + G.cols[p0 + j * 32 + lane]), G.vals[p0 + j * 32 + lane]);
+    y[row] = __dadd_rn(y[row], acc);
+  }
+  if (last_block(ticket) && (int)threadIdx.x < nneigh) st_release_sys(peers[threadIdx.x].rack, seq);
+}
+
 // y[row] += sum_j G_ij x[n_own + slot_j]   (the product the reference receives as partial sums, SParIterComm.F90:4945-4953)
 __global__ void __launch_bounds__(256) k_spmv_ghost(SellView G, const double *__restrict__ x, double *__restrict__ y) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,6 +342,18 @@ void matvec_full(Handle &h, const double *x, double *y) {
   Halo &H = *h.halo;
   ncclComm_t comm = (ncclComm_t)h.nccl;
   double *xg = const_cast<double *>(x) + h.n;                      // ghost tail of the operand
+  if (H.p2p) {
+    const unsigned long long seq = ++H.seq;
+    const PeerDesc *peers = (const PeerDesc *)H.d_peers.p;
+    k_pack_push<<<std::max(1, std::min((H.nsend + 255) / 256, NUM_SMS * 4)), 256, 0, h.stream>>>(H.nsend, H.d_send_idx.p, x, peers, H.nneigh, H.ack, seq,
+                                                                                                 H.d_ticket.p, h.ctrl.p);
+    { SpmvArgs a; a.x = x; a.y = y; spmv_launch(h, a, EPI_NONE); }   // owned x owned while the neighbours' entries arrive
+    k_spmv_ghost_p2p<<<std::max(1, (H.G.nslots + 255) / 256), 256, 0, h.stream>>>(H.G.view(), H.recv[seq & 1ULL] - h.n, y, H.ready, peers, H.nneigh, seq,
+                                                                                   H.d_ticket.p + 1, h.ctrl.p);
+    B200_CUDA(cudaGetLastError());
+    h.st_launch += 3;
+    return;
+  }
   if (H.nsend) k_pack<<<std::max(1, std::min((H.nsend + 255) / 256, NUM_SMS * 4)), 256, 0, h.stream>>>(H.nsend, H.d_send_idx.p, x, H.d_sendbuf.p);
   B200_CUDA(cudaEventRecord(H.ev_pack, h.stream));
   B200_CUDA(cudaStreamWaitEvent(h.stream2, H.ev_pack, 0));
@@ -317,7 +481,7 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
     const int lo = goffset[me], hi = goffset[me + 1];
     B200_REQUIRE(hi - lo == N, "n_own inconsistent with goffset");
     h.gn = *gn; h.index_base = base;
-    if (h.halo) { cudaStream_t s = h.stream; (void)s; Halo *old = h.halo; h.halo = nullptr; old->G.release(); delete old; }
+    if (h.halo) { Halo *old = h.halo; h.halo = nullptr; p2p_release(h, *old); old->G.release(); delete old; }
     Halo *Hp = new Halo(); h.halo = Hp; Halo &H = *Hp;
     B200_CUDA(cudaEventCreateWithFlags(&H.ev_pack, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&H.ev_comm, cudaEventDisableTiming));
@@ -386,6 +550,7 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
     B200_CUDA(cudaStreamSynchronize(st));
     sell_finish(h, H.G, nslots, true, H.d_gcols.p);
     B200_CUDA(cudaStreamSynchronize(st));
+    if (np > 1) p2p_setup(h, H, allcnt);
   });
 }
 

@@ -219,21 +219,42 @@ def heat_slab(ex, ey, ez_total, rank, nranks, allreduce_sum=None, source=1.0):
     rows with GLOBAL 1-based column ids, as b200_set_partition expects.  Only a slab two element
     layers thicker than the owned one is ever assembled.  allreduce_sum(float) sums over ranks (needed
     for the global ||D b|| of the scaling); None = single process emulation of all ranks is not done here."""
+    return _slab("heat", ex, ey, ez_total, rank, nranks, allreduce_sum, source=source)
+
+
+def elasticity_slab(ex, ey, ez_total, rank, nranks, allreduce_sum=None, E=1e9, nu=0.3, load=(0.0, -1e4, 0.0)):
+    """Configs 3/5: rank `rank`'s share of a linear-elasticity beam (3 interleaved dofs per node, long axis z,
+    cubic hex8 elements of side 1/ex, z=0 end clamped, body load), partitioned into z-slabs of node layers
+    (`ElmerGrid -partition 1 1 N`); same conventions as heat_slab."""
+    return _slab("elasticity", ex, ey, ez_total, rank, nranks, allreduce_sum, E=E, nu=nu, load=load)
+
+
+def _slab(kind, ex, ey, ez_total, rank, nranks, allreduce_sum, source=1.0, E=1e9, nu=0.3, load=(0.0, -1e4, 0.0)):
     nx, ny, NZ = ex + 1, ey + 1, ez_total + 1
     L = slab_layers(NZ, nranks)
     zlo, zhi = max(0, L[rank] - 2), min(NZ, L[rank + 1] + 2)        # local node layers [zlo, zhi)
     ezl = zhi - zlo - 1
     h = 1.0 / ex
     xyz, elems = grid_hex8(ex, ey, ezl, ex * h, ey * h, ezl * h)
-    rows, cols, diag = crs_structure(xyz.shape[0], elems, 1)
-    vals, rhs = assemble(0, [source], xyz, elems, 1, rows, cols, uniform=True)
-    A = CRS(rows, cols, diag, vals, 1)
-    faces = ["x0", "x1", "y0", "y1"] + (["z0"] if zlo == 0 else []) + (["z1"] if zhi == NZ else [])
-    dirichlet(A, rhs, boundary_nodes(ex, ey, ezl, faces), 0.0, False)
+    nd = 1 if kind == "heat" else 3
+    rows, cols, diag = crs_structure(xyz.shape[0], elems, nd)
+    if kind == "heat":
+        vals, rhs = assemble(0, [source], xyz, elems, 1, rows, cols, uniform=True)
+        A = CRS(rows, cols, diag, vals, 1)
+        faces = ["x0", "x1", "y0", "y1"] + (["z0"] if zlo == 0 else []) + (["z1"] if zhi == NZ else [])
+        dirichlet(A, rhs, boundary_nodes(ex, ey, ezl, faces), 0.0, False)
+    else:
+        vals, rhs = assemble(1, [E, nu, load[0], load[1], load[2]], xyz, elems, 3, rows, cols, uniform=True)
+        A = CRS(rows, cols, diag, vals, 3)
+        if zlo == 0:
+            nodes = boundary_nodes(ex, ey, ezl, ["z0"]).astype(np.int64)
+            dofs = np.concatenate([3 * (nodes - 1) + c + 1 for c in range(3)]).astype(np.int32)
+            dofs.sort()
+            dirichlet(A, rhs, dofs, 0.0, False)
     # scaling with D from the complete rows (the two outermost artificial layers are never referenced)
     d = np.abs(A.vals[A.diag - 1])
     D = 1.0 / np.sqrt(d)
-    plane = nx * ny
+    plane = nx * ny * nd                                            # dofs per node layer
     o0, o1 = plane * (L[rank] - zlo), plane * (L[rank + 1] - zlo)
     p0, p1 = A.rows[o0] - 1, A.rows[o1] - 1
     lrows = (A.rows[o0:o1 + 1] - A.rows[o0] + 1).astype(np.int32)
@@ -249,4 +270,4 @@ def heat_slab(ex, ey, ez_total, rank, nranks, allreduce_sum=None, source=1.0):
     gcols = (lcols.astype(np.int64) + plane * zlo).astype(np.int32)
     goffset = np.array([plane * l for l in L], dtype=np.int32)
     return dict(rows=np.ascontiguousarray(lrows), cols=np.ascontiguousarray(gcols), vals=np.ascontiguousarray(lvals),
-                b=np.ascontiguousarray(b), goffset=goffset, gn=int(plane * NZ), D=D[o0:o1] * bnorm, bnorm=bnorm)
+                b=np.ascontiguousarray(b), goffset=goffset, gn=int(plane * NZ), D=D[o0:o1] * bnorm, bnorm=bnorm, ndeg=nd)
