@@ -10,7 +10,7 @@ import pytest
 
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
-EX, EY, EZ, WORLD = 14, 12, 31, 2
+EX, EY, EZ = 14, 12, 31
 TOL = 1e-8
 
 
@@ -37,7 +37,11 @@ def _worker(rank, world, port, out_q, method, precond):
         M.set_partition(p["gn"], p["rows"], p["cols"], p["goffset"], 1, 1)
         M.set_values(p["vals"])
         plan = M.halo_plan()
-        got = M.solve(p["b"], method=method, precond=precond, tol=TOL, maxit=500, bicgstabl_l=4)
+        P = None
+        if method == "idrs":
+            from oracle import oracle as O
+            P = np.asfortranarray(O.shadow_space(p["gn"], 4)[p["goffset"][rank]:p["goffset"][rank + 1]])
+        got = M.solve(p["b"], method=method, precond=precond, tol=TOL, maxit=500, bicgstabl_l=4, P=P)
         # y = A x through the halo exchange, for a vector every rank can evaluate
         lo, hi = p["goffset"][rank], p["goffset"][rank + 1]
         xg = np.sin(0.37 * np.arange(lo, hi) + 1.0)
@@ -49,8 +53,10 @@ def _worker(rank, world, port, out_q, method, precond):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("method,precond", [("bicgstab", "ilu0"), ("cg", "diagonal"), ("bicgstabl", "ilu0"), ("gcr", "none")])
-def test_two_gpu_parity(oracle, b200, method, precond):
+@pytest.mark.parametrize("WORLD,method,precond", [(2, "bicgstab", "ilu0"), (2, "cg", "diagonal"), (2, "bicgstabl", "ilu0"), (2, "gcr", "none"),
+                                                  (3, "cg", "diagonal"), (4, "bicgstab", "ilu0"), (4, "idrs", "diagonal")])
+def test_multi_gpu_parity(oracle, b200, WORLD, method, precond):
+    """2 ranks: one neighbour each; 3 and 4 ranks: interior ranks push to / wait on two neighbours (uneven slabs for 3)."""
     import ctypes as C
     n = C.c_int(0)
     if b200.lib().b200_device_count(C.byref(n)) != 0 or n.value < WORLD:
@@ -95,7 +101,8 @@ def test_two_gpu_parity(oracle, b200, method, precond):
     Abd = A.copy()
     Abd.vals[block[rowid] != block[A.cols - 1]] = 0.0
     ilu = oracle.ilu0(Abd) if precond == "ilu0" else None
-    ref = oracle.itersolve(A, rhs, method=method, precond=precond, ilu=ilu, tol=TOL, maxit=500, bicgstabl_l=4)
+    P = oracle.shadow_space(A.n, 4) if method == "idrs" else None
+    ref = oracle.itersolve(A, rhs, method=method, precond=precond, ilu=ilu, tol=TOL, maxit=500, bicgstabl_l=4, P=P)
     x = np.concatenate([np.array(r_[2]) for r_ in res])
     infos = {r_[3] for r_ in res}; iters = {r_[4] for r_ in res}
     assert infos == {1} and ref["info"] == 1
