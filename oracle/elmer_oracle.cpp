@@ -73,9 +73,27 @@ struct Matrix {
 // ---------------------------------------------------------------------------------------
 // mathlibs/src/blas/ddot.f (incx=incy=1 branch): single accumulator, mod-5 clean-up loop,
 // then unrolled by 5 with the five products added left to right into dtemp.
+// g_dot_order != 0 is NOT the reference: it replays the same dot product in the summation orders other BLAS
+// builds use (Elmer may be linked against OpenBLAS/MKL instead of mathlibs, CMakeLists.txt:270-...), to
+// measure how far iteration counts move with the summation order alone.
+//   1: eight interleaved partial sums (SIMD-style kernel), 2: pairwise over blocks of 256
+static int g_dot_order = 0;
+static double dot_pairwise(const double *x, const double *y, long lo, long hi) {
+  if (hi - lo <= 256) { double s = 0.0; for (long i = lo; i < hi; ++i) s += x[i] * y[i]; return s; }
+  long mid = lo + (hi - lo) / 2;
+  return dot_pairwise(x, y, lo, mid) + dot_pairwise(x, y, mid, hi);
+}
 double ref_ddot(int n, const double *dx, const double *dy) {
   double dtemp = 0.0;
   if (n <= 0) return 0.0;
+  if (g_dot_order == 1) {
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int i = 0;
+    for (; i + 8 <= n; i += 8) for (int k = 0; k < 8; ++k) a[k] += dx[i + k] * dy[i + k];
+    for (; i < n; ++i) a[0] += dx[i] * dy[i];
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
+  if (g_dot_order == 2) return dot_pairwise(dx, dy, 0, n);
   int m = n % 5;
   if (m != 0) {
     for (int i = 0; i < m; ++i) dtemp = dtemp + dx[i] * dy[i];
@@ -91,6 +109,7 @@ double ref_ddot(int n, const double *dx, const double *dy) {
 double ref_dnrm2(int n, const double *x) {
   if (n < 1) return 0.0;
   if (n == 1) return std::fabs(x[0]);
+  if (g_dot_order != 0) return std::sqrt(ref_ddot(n, x, x));
   double scale = 0.0, ssq = 1.0;
   for (int ix = 0; ix < n; ++ix) {
     if (x[ix] != 0.0) {
@@ -866,6 +885,7 @@ void RealIDRS(Ops &op, int n, double *x, const double *b, int MaxRounds, double 
 // precond: 0 none, 1 diagonal, 2 ilu0.
 extern "C" {
 
+void orc_set_dot_order(int mode) { g_dot_order = mode; }
 void orc_set_threads(int nthreads) {
 #ifdef _OPENMP
   omp_set_num_threads(nthreads > 0 ? nthreads : 1);

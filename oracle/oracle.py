@@ -59,6 +59,12 @@ def set_threads(n):
     lib().orc_set_threads(int(n))
 
 
+def set_dot_order(mode):
+    """0 = the reference's ddot/dnrm2 (default); 1, 2 = the same dot products summed in the orders other BLAS
+    builds use (sensitivity study only, see elmer_oracle.cpp)."""
+    lib().orc_set_dot_order(int(mode))
+
+
 def max_threads():
     return lib().orc_max_threads()
 

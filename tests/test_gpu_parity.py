@@ -255,3 +255,56 @@ def test_task_mode_triangular_solves_bit_exact(oracle, b200, heat, mode, monkeyp
     assert got["info"] == ref["info"] == 1 and got["iters"] == ref["iters"]
     assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
     M.close()
+
+
+def test_config1_full_size_cg_jacobi(oracle, b200):
+    """BASELINE configs[0] at its full size (heat 100^3 hex8, 1,030,301 dofs, CG + Jacobi, tol 1e-8): iteration count and
+    solution against the oracle (OpenMP SpMV, a few seconds on the host)."""
+    from elmerfem_b200 import synth
+    A, b = synth.workload("heat", 100)
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 1); M.set_values(A.vals)
+    got = M.solve(b, method="cg", precond="diagonal", tol=TOL, maxit=2000)
+    ref = oracle.itersolve(oracle.CRS(A.rows, A.cols, A.diag, A.vals, 1), b, method="cg", precond="diagonal", tol=TOL, maxit=2000)
+    assert got["info"] == ref["info"] == 1
+    assert iters_close(got["iters"], ref["iters"]), (got["iters"], ref["iters"])
+    assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    u = np.random.RandomState(11).standard_normal(A.n)
+    assert np.array_equal(M.matvec(u), oracle.matvec(oracle.CRS(A.rows, A.cols, A.diag, A.vals, 1), u))
+    M.close()
+
+
+def test_config2_full_size_properties(b200):
+    """BASELINE configs[1] at its full size (heat 200^3, 8,120,601 dofs, BiCGStab + ILU0): size-independent properties.
+    SpMV is linear and matches scipy on the same CRS; L U (M^-1 v) reproduces v; the solve converges and the true
+    residual recomputed from the answer meets the tolerance.  Iteration count: at this size BiCGStab's count depends on
+    the summation order of the dot products alone -- the oracle gives 92 with the reference ddot, 90 with eight
+    interleaved partial sums, 88 with pairwise summation (oracle.set_dot_order, runs recorded in DESIGN.md section 5);
+    the GPU's tree reduction gives 86.  The assertion is that band, not the 2 % bar that holds at every size where the
+    count is insensitive (all other parity tests: identical counts)."""
+    from elmerfem_b200 import synth
+    A, b = synth.workload("heat", 200)
+    S = A.to_scipy()
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 1); M.set_values(A.vals)
+    rs = np.random.RandomState(12)
+    u, w = rs.standard_normal(A.n), rs.standard_normal(A.n)
+    yu, yw, yuw = M.matvec(u), M.matvec(w), M.matvec(2.0 * u - 0.5 * w)
+    ref = S @ u
+    assert np.abs(yu - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.abs(yuw - (2.0 * yu - 0.5 * yw)).max() <= 1e-12 * np.abs(yuw).max()
+    M.factorize()
+    lu = M.ilu_values()
+    z = M.lu_precondition(u)
+    # rebuild L (unit diagonal) and U (inverse diagonal stored) from ILUValues and check L U z = u
+    import scipy.sparse as sp
+    rows0, cols0 = np.repeat(np.arange(A.n), np.diff(A.rows)), A.cols - 1
+    low, upp = cols0 < rows0, cols0 > rows0
+    d = 1.0 / lu[A.diag - 1]
+    L = sp.csr_matrix((lu[low], (rows0[low], cols0[low])), shape=S.shape) + sp.identity(A.n, format="csr")
+    U = sp.csr_matrix((lu[upp], (rows0[upp], cols0[upp])), shape=S.shape) + sp.diags(d, format="csr")
+    back = L @ (U @ z)
+    assert np.abs(back - u).max() <= 1e-10 * np.abs(u).max()
+    got = M.solve(b, method="bicgstab", precond="ilu0", tol=TOL, maxit=2000)
+    assert got["info"] == 1 and 84 <= got["iters"] <= 94, got["iters"]
+    r = S @ got["x"] - b
+    assert np.linalg.norm(r) / np.linalg.norm(b) <= TOL
+    M.close()
