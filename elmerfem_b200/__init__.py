@@ -57,7 +57,7 @@ def lib():
         "b200_itersolver": [vpp, dp, dp, C.c_char_p, ip, ip],
         "b200_matvec": [vpp, dp, dp], "b200_diag_precondition": [vpp, dp, dp], "b200_lu_precondition": [vpp, dp, dp],
         "b200_dot": [vpp, ip, dp, dp, dp], "b200_nrm2": [vpp, ip, dp, dp],
-        "b200_get_ilu_values": [vpp, dp], "b200_get_structure": [vpp, ip, ip, ip], "b200_get_levels": [vpp, ip, ip],
+        "b200_get_ilu_values": [vpp, dp], "b200_set_ilu_order": [vpp, ip], "b200_get_ilu_structure": [vpp, ip, ip, ip, ip], "b200_get_structure": [vpp, ip, ip, ip], "b200_get_levels": [vpp, ip, ip],
         "b200_comm_unique_id": [C.c_char_p], "b200_comm_init": [vpp, ip, ip, C.c_char_p],
         "b200_set_partition": [vpp, ip, ip, ip, ip, ip, ip, ip, ip],
         "b200_get_halo_plan": [vpp, ip, ip, ip, ip, ip, ip],
@@ -246,8 +246,24 @@ class Matrix:
         _check(lib().b200_nrm2(self.handle, _i(x.size), _dp(x), C.byref(r)), "b200_nrm2")
         return r.value
 
+    def set_ilu_order(self, order):
+        """Fill level n of CRS_IncompleteLU(A, n) ("Linear System Preconditioning = ILUn"); 0 = ILU0."""
+        _check(lib().b200_set_ilu_order(self.handle, _i(order)), "b200_set_ilu_order")
+
+    def ilu_structure(self):
+        """ILURows/ILUCols/ILUDiag (caller's index base) of the current ILU order."""
+        sizes = np.zeros(2, dtype=np.int32)
+        none = C.POINTER(C.c_int)()
+        _check(lib().b200_get_ilu_structure(self.handle, _ip(sizes), none, none, none), "b200_get_ilu_structure")
+        rows = np.empty(sizes[0] + 1, dtype=np.int32); cols = np.empty(sizes[1], dtype=np.int32); diag = np.empty(sizes[0], dtype=np.int32)
+        _check(lib().b200_get_ilu_structure(self.handle, _ip(sizes), _ip(rows), _ip(cols), _ip(diag)), "b200_get_ilu_structure")
+        return rows, cols, diag
+
     def ilu_values(self):
-        out = np.empty(self.nnz)
+        sizes = np.zeros(2, dtype=np.int32)
+        none = C.POINTER(C.c_int)()
+        _check(lib().b200_get_ilu_structure(self.handle, _ip(sizes), none, none, none), "b200_get_ilu_structure")
+        out = np.empty(int(sizes[1]))
         _check(lib().b200_get_ilu_values(self.handle, _dp(out)), "b200_get_ilu_values")
         return out
 

@@ -104,9 +104,8 @@ void install_structure(Handle &h, int n, long long nnz, std::vector<int> &&rows0
   if (nnz) B200_CUDA(cudaMemcpyAsync(h.d_cols.p, h.h_cols.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   if (n) B200_CUDA(cudaMemcpyAsync(h.d_diag.p, h.h_diag.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   B200_CUDA(cudaStreamSynchronize(h.stream));
-  h.have_vals = h.have_prec = h.ilu_valid = h.ilu_exists = false; h.tri_ready = false;
-  tritask_release(h); h.tri_mode = h.tri_mode_cfg;
-  h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0;
+  h.have_vals = h.have_prec = false;
+  ilu_invalidate(h);
   structure_build(h);
   B200_CUDA(cudaStreamSynchronize(h.stream));
 }
@@ -180,7 +179,7 @@ int b200_destroy(void **handle) {
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
     h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
     h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
-    tritask_release(*h);
+    tritask_release(*h); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
     for (auto &w : h->work) w.release();
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();
@@ -354,8 +353,30 @@ int b200_get_ilu_values(void **handle, double *ilu_vals) {
   return guarded([&] {
     Handle &h = H(handle);
     B200_REQUIRE(h.ilu_valid, "no valid ILU0 factor");
-    download(h, ilu_vals, h.d_ilu.p, h.nnz);
+    download(h, ilu_vals, h.d_ilu.p, h.lnnz());
     B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+}
+int b200_set_ilu_order(void **handle, const int *order) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(order && *order >= 0 && *order <= 9, "ILU order must be 0..9");
+    if (*order == h.ilu_order) return;
+    h.ilu_order = *order;
+    ilu_invalidate(h);
+  });
+}
+int b200_get_ilu_structure(void **handle, int *sizes, int *rows, int *cols, int *diag) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    ilu_pattern_build(h);
+    sizes[0] = h.n; sizes[1] = (int)h.lnnz();
+    if (!rows) return;
+    const std::vector<int> &r = h.lrows(), &c = h.lcols(), &d = h.ldiag();
+    const int base = h.index_base;
+    for (size_t i = 0; i < r.size(); ++i) rows[i] = r[i] + base;
+    for (size_t i = 0; i < c.size(); ++i) cols[i] = c[i] + base;
+    for (size_t i = 0; i < d.size(); ++i) diag[i] = d[i] + base;
   });
 }
 int b200_get_structure(void **handle, int *rows, int *cols, int *diag) {

@@ -120,6 +120,17 @@ struct Handle {
   DBuf<int> d_rows, d_cols, d_diag;              // 0-based working copies
   // values
   DBuf<double> d_vals, d_prec, d_ilu, d_dvals; bool have_vals = false, have_prec = false, ilu_valid = false, ilu_exists = false;
+  // ILU(n > 0): the factor lives on its own pattern (CRSMatrix.F90:3488-3510); ILU0 aliases the matrix pattern
+  int ilu_order = 0; bool ilu_pat_ready = false; long long ilu_nnz = 0;
+  std::vector<int> hl_rows, hl_cols, hl_diag;    // 0-based host copies of ILURows/ILUCols/ILUDiag
+  DBuf<int> dl_rows, dl_cols, dl_diag, dl_src;   // device copies; dl_src: position of the entry in the matrix values, -1 for fill
+  const std::vector<int> &lrows() const { return ilu_order ? hl_rows : h_rows; }
+  const std::vector<int> &lcols() const { return ilu_order ? hl_cols : h_cols; }
+  const std::vector<int> &ldiag() const { return ilu_order ? hl_diag : h_diag; }
+  const int *d_lrows() const { return ilu_order ? dl_rows.p : d_rows.p; }
+  const int *d_lcols() const { return ilu_order ? dl_cols.p : d_cols.p; }
+  const int *d_ldiag() const { return ilu_order ? dl_diag.p : d_diag.p; }
+  long long lnnz() const { return ilu_order ? ilu_nnz : nnz; }
   // SpMV operand
   Sell A;
   // ILU0 + triangular solves
@@ -234,6 +245,8 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partials, u
 void structure_build(Handle &h);                       // SELL operand from the CRS mirror
 void sell_refresh_values(Handle &h, Sell &S, const double *crs_vals);
 void sell_finish(Handle &h, Sell &S, int nslots, bool has_perm, const int *src_cols);   // start/len/perm pre-filled
+void ilu_pattern_build(Handle &h);                     // ILU(n > 0): symbolic fill (host), once per structure and order
+void ilu_invalidate(Handle &h);                        // forget factor, plans and ILU(n) pattern (structure or order changed)
 void tri_analyse(Handle &h);                           // levels + L/U level-sorted SELL plans
 void ilu0_factor(Handle &h);                           // d_ilu from d_prec/d_vals, refresh L/U values
 void lu_apply(Handle &h, double *u, const double *v);  // u = (LU)^-1 v   (device pointers)

@@ -142,7 +142,7 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
       if (got) ilun = (int)lround(o);
       else ilun = pcs.size() >= 4 ? pcs[3] - '0' : -1;                  // 541-546
       if (ilun < 0 || ilun > 9) ilun = 0;
-      if (ilun != 0) throw Declined{"ILU order > 0"};
+      if (ilun != h.ilu_order) { B200_CUDA(cudaSetDevice(h.device)); h.ilu_order = ilun; ilu_invalidate(h); }
       pc = B200_PRECOND_ILU0;
     } else if (pcs.rfind("bilu", 0) == 0 || pcs == "multigrid" || pcs.rfind("vanka", 0) == 0 || pcs == "slave" || pcs == "circuit")
       throw Declined{"preconditioner '" + pcs + "'"};

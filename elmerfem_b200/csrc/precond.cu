@@ -37,7 +37,8 @@ void diag_apply(Handle &h, double *u, const double *v) {
 // One warp per row, rows taken in forward-level order (the L plan's slot order).
 __global__ void __launch_bounds__(256) k_ilu0_factor(int nslots, const int *__restrict__ perm, const int *__restrict__ rows,
                                                       const int *__restrict__ cols, const int *__restrict__ diag,
-                                                      const double *__restrict__ Avals, double *LU, int *rowdone, Ctrl *ctrl) {
+                                                      const double *__restrict__ Avals, const int *__restrict__ src, double *LU, int *rowdone,
+                                                      Ctrl *ctrl) {
   __shared__ double s_val[8][ILU_MAXROW];
   __shared__ int s_col[8][ILU_MAXROW];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int nslots, const int *__re
     const int *crow = staged ? s_col[wib] : (cols + rs);
     // CRSMatrix.F90:3614-3620: the row in "full form" (here: its own pattern, which is all that is ever touched)
     for (int t = lane; t < len; t += 32) {
-      double a = Avals[rs + t];
+      double a;                                                   // ILU(n > 0): src maps the pattern to the matrix, -1 = fill
+      if (src) { const int q = src[rs + t]; a = q >= 0 ? Avals[q] : 0.0; } else a = Avals[rs + t];
       if (staged) { s_val[wib][t] = a; s_col[wib][t] = cols[rs + t]; }
       else LU[rs + t] = a;
     }
@@ -135,7 +137,7 @@ void ilu0_factor(Handle &h) {
   tri_analyse(h);
   if (h.tri_mode != 0) tritask_analyse(h);
   cudaStream_t st = h.stream;
-  h.d_ilu.ensure(h.nnz);
+  h.d_ilu.ensure(h.lnnz());
   B200_CUDA(cudaEventRecord(h.evf0, st));
   if (h.n > 0) {
     B200_CUDA(cudaMemsetAsync(h.d_rowdone.p, 0, (size_t)h.n * sizeof(int), st));
@@ -143,13 +145,13 @@ void ilu0_factor(Handle &h) {
     const double *src = h.have_prec ? h.d_prec.p : h.d_vals.p;        // CRSMatrix.F90:3480-3484
     if (!h.grid_ilu) h.grid_ilu = persistent_blocks((const void *)k_ilu0_factor, 256, 0);
     int blocks = std::max(1, std::min(h.grid_ilu, (h.L.nslots + 7) / 8));
-    launch_coresident((const void *)k_ilu0_factor, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, (const int *)h.d_rows.p,
-                      (const int *)h.d_cols.p, (const int *)h.d_diag.p, src, h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
+    launch_coresident((const void *)k_ilu0_factor, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
+                      (const int *)(h.ilu_order ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
     int eb = std::min((h.n + 255) / 256, NUM_SMS * 8);
-    k_ilu0_invert_diag<<<eb, 256, 0, st>>>(h.n, h.d_diag.p, h.d_ilu.p);
+    k_ilu0_invert_diag<<<eb, 256, 0, st>>>(h.n, h.d_ldiag(), h.d_ilu.p);
     sell_refresh_values(h, h.L, h.d_ilu.p);
     sell_refresh_values(h, h.U, h.d_ilu.p);
-    if (h.U.nslots) k_gather_diag_slots<<<(h.U.nslots + 255) / 256, 256, 0, st>>>(h.U.nslots, h.U.perm.p, h.d_diag.p, h.d_ilu.p, h.d_dinv_slot.p);
+    if (h.U.nslots) k_gather_diag_slots<<<(h.U.nslots + 255) / 256, 256, 0, st>>>(h.U.nslots, h.U.perm.p, h.d_ldiag(), h.d_ilu.p, h.d_dinv_slot.p);
     if (h.tt_ready) tritask_refresh_values(h);
     B200_CUDA(cudaGetLastError());
   }

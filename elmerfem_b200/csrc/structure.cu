@@ -87,8 +87,9 @@ void sell_finish(Handle &h, Sell &S, int nslots, bool has_perm, const int *src_c
 
 static void build_sell(Handle &h, Sell &S, int kind, const int *d_perm, int nslots) {
   S.len.ensure(nslots); S.start.ensure(nslots);
-  if (nslots) k_slot_extent<<<(nslots + 255) / 256, 256, 0, h.stream>>>(nslots, h.n, d_perm, h.d_rows.p, h.d_diag.p, kind, S.start.p, S.len.p);
-  sell_finish(h, S, nslots, d_perm != nullptr, h.d_cols.p);
+  const int *rows = kind == 0 ? h.d_rows.p : h.d_lrows(), *diag = kind == 0 ? h.d_diag.p : h.d_ldiag();   // L/U plans live on the ILU pattern
+  if (nslots) k_slot_extent<<<(nslots + 255) / 256, 256, 0, h.stream>>>(nslots, h.n, d_perm, rows, diag, kind, S.start.p, S.len.p);
+  sell_finish(h, S, nslots, d_perm != nullptr, kind == 0 ? h.d_cols.p : h.d_lcols());
 }
 
 void sell_refresh_values(Handle &h, Sell &S, const double *crs_vals) {
@@ -133,10 +134,73 @@ static void level_layout(int n, const std::vector<int> &level, int nlev, std::ve
   }
 }
 
+// One round of InitializeILU1 (CRSMatrix.F90:3664-3795) on a 0-based pattern: row i keeps its entries and gains the
+// columns of the upper parts of the rows k < i it held BEFORE the round (fills of the round do not cascade);
+// columns ascending.
+static void ilu1_round(int n, const std::vector<int> &rows, const std::vector<int> &cols, const std::vector<int> &diag,
+                       std::vector<int> &r2, std::vector<int> &c2, std::vector<int> &d2) {
+  std::vector<unsigned char> C(n, 0);
+  r2.assign((size_t)n + 1, 0); d2.assign(n, 0); c2.clear(); c2.reserve(cols.size() * 2);
+  std::vector<int> added;
+  for (int i = 0; i < n; ++i) {
+    for (int k = rows[i]; k < rows[i + 1]; ++k) C[cols[k]] = 1;
+    added.clear();
+    for (int m = rows[i]; m < diag[i]; ++m) {              // the rows k < i of the pattern (flag 1), ascending
+      const int k = cols[m];
+      for (int l = diag[k] + 1; l < rows[k + 1]; ++l) { const int j = cols[l]; if (C[j] == 0) { C[j] = 2; added.push_back(j); } }
+    }
+    std::sort(added.begin(), added.end());
+    size_t a = 0;
+    for (int k = rows[i]; k < rows[i + 1] || a < added.size();) {   // merge, ascending
+      int c;
+      if (a < added.size() && (k >= rows[i + 1] || added[a] < cols[k])) c = added[a++]; else c = cols[k++];
+      if (c == i) d2[i] = (int)c2.size();
+      c2.push_back(c); C[c] = 0;
+    }
+    B200_REQUIRE(c2.size() < 2147483647ULL, "ILU(n) pattern exceeds int32 entries");
+    r2[i + 1] = (int)c2.size();
+  }
+}
+
+void ilu_pattern_build(Handle &h) {
+  if (h.ilu_order <= 0 || h.ilu_pat_ready) return;
+  const int n = h.n;
+  std::vector<int> r = h.h_rows, c = h.h_cols, d = h.h_diag, r2, c2, d2;
+  for (int round = 0; round < h.ilu_order; ++round) { ilu1_round(n, r, c, d, r2, c2, d2); r.swap(r2); c.swap(c2); d.swap(d2); }
+  std::vector<int> src(c.size(), -1);
+#pragma omp parallel for
+  for (int i = 0; i < n; ++i) {
+    int p = h.h_rows[i];
+    for (int q = r[i]; q < r[i + 1]; ++q) {
+      while (p < h.h_rows[i + 1] && h.h_cols[p] < c[q]) ++p;
+      if (p < h.h_rows[i + 1] && h.h_cols[p] == c[q]) src[q] = p;
+    }
+  }
+  h.ilu_nnz = (long long)c.size();
+  h.dl_rows.ensure((size_t)n + 1); h.dl_cols.ensure(c.size()); h.dl_diag.ensure(std::max(n, 1)); h.dl_src.ensure(c.size());
+  B200_CUDA(cudaMemcpyAsync(h.dl_rows.p, r.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  if (!c.empty()) {
+    B200_CUDA(cudaMemcpyAsync(h.dl_cols.p, c.data(), c.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+    B200_CUDA(cudaMemcpyAsync(h.dl_src.p, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  }
+  if (n) B200_CUDA(cudaMemcpyAsync(h.dl_diag.p, d.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h.stream));
+  B200_CUDA(cudaStreamSynchronize(h.stream));
+  h.hl_rows.swap(r); h.hl_cols.swap(c); h.hl_diag.swap(d);
+  h.ilu_pat_ready = true;
+}
+
+void ilu_invalidate(Handle &h) {
+  h.ilu_valid = h.ilu_exists = false; h.tri_ready = false; h.ilu_pat_ready = false;
+  h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0;
+  tritask_release(h);
+  h.tri_mode = h.tri_mode_cfg;
+}
+
 void tri_analyse(Handle &h) {
   if (h.tri_ready) return;
+  ilu_pattern_build(h);
   const int n = h.n;
-  const std::vector<int> &rows = h.h_rows, &cols = h.h_cols, &diag = h.h_diag;
+  const std::vector<int> &rows = h.lrows(), &cols = h.lcols(), &diag = h.ldiag();
   std::vector<int> lf(n, 0), lb(n, 0);
   int nlf = 0, nlb = 0;
   for (int i = 0; i < n; ++i) {

@@ -46,7 +46,7 @@ template <bool EMIT>
 static void build_task(const Handle &h, bool upper, int q0, int q1, TaskScratch &S, TaskSizes &sz, uint2 *desc, unsigned char *stream,
                        size_t stream_off, unsigned *fdst, int *fsrc) {
   const int n = h.n, R = q1 - q0;
-  const int *rows = h.h_rows.data(), *cols = h.h_cols.data(), *diag = h.h_diag.data();
+  const int *rows = h.lrows().data(), *cols = h.lcols().data(), *diag = h.ldiag().data();
   S.lev.resize(R); S.order.resize(R); S.slot.resize(R);
   int nl = 0;
   for (int q = q0; q < q1; ++q) {
@@ -138,9 +138,9 @@ static std::vector<int> task_bounds(const Handle &h, bool upper, int fixed_rows)
   if (fixed_rows > 0) { for (long long q = fixed_rows; q < n; q += fixed_rows) bounds.push_back((int)q); bounds.push_back(n); return bounds; }
   const int MAXLINE = 4096, MINROWS = 512;
   auto maxdep = [&](int q) -> int {                       // highest sweep position row q reads (-1: none)
-    const int i = upper ? n - 1 - q : q, d = h.h_diag[i];
-    if (!upper) return d > h.h_rows[i] ? h.h_cols[d - 1] : -1;
-    return d + 1 < h.h_rows[i + 1] ? n - 1 - h.h_cols[d + 1] : -1;
+    const int i = upper ? n - 1 - q : q, d = h.ldiag()[i];
+    if (!upper) return d > h.lrows()[i] ? h.lcols()[d - 1] : -1;
+    return d + 1 < h.lrows()[i + 1] ? n - 1 - h.lcols()[d + 1] : -1;
   };
   std::vector<int> ls;                                    // line starts; bit 30 marks a plane start
   std::vector<char> ps;

@@ -85,7 +85,12 @@ int b200_set_structure(void **handle, const int *n, const int *nnz, const int *r
 int b200_set_values(void **handle, const double *vals, const double *prec_vals);
 /* Same, but vals/prec_vals are DEVICE pointers (values assembled or kept on the GPU). */
 int b200_set_values_device(void **handle, const double *d_vals, const double *d_prec_vals);
-int b200_factorize(void **handle);                 /* ILU0 of PrecValues (if given) else Values        */
+int b200_factorize(void **handle);                 /* ILU(order) of PrecValues (if given) else Values  */
+/* Fill level of the incomplete factorisation, CRS_IncompleteLU(A, ILUn) (fem/src/CRSMatrix.F90:3445-3795; keywords
+ * "Linear System Preconditioning = ILU0..ILU9" / "Linear System ILU Order", IterSolve.F90:529-547).  0 (default)
+ * factorises on the matrix pattern; n > 0 first adds n rounds of first-order fill (InitializeILU1, 3664-3795).
+ * Changing the order drops the current factor. */
+int b200_set_ilu_order(void **handle, const int *order);
 
 /* ---- solve ----------------------------------------------------------------------------- */
 /* b[n] in, x[n] in/out (initial guess in, solution out), ipar[50] in/out, dpar[10] in.
@@ -114,7 +119,10 @@ int b200_diag_precondition(void **handle, double *u, const double *v);     /* u 
 int b200_lu_precondition(void **handle, double *u, const double *v);       /* u = (LU)^-1 v      */
 int b200_dot(void **handle, const int *n, const double *x, const double *y, double *result);
 int b200_nrm2(void **handle, const int *n, const double *x, double *result);
-int b200_get_ilu_values(void **handle, double *ilu_vals);                  /* ILUValues(nnz)     */
+int b200_get_ilu_values(void **handle, double *ilu_vals);                  /* ILUValues          */
+/* ILURows/ILUCols/ILUDiag of the current order in the caller's index base.  sizes[0] = n, sizes[1] = entries of
+ * the ILU pattern; the arrays may be NULL to query the sizes first. */
+int b200_get_ilu_structure(void **handle, int *sizes, int *rows, int *cols, int *diag);
 int b200_get_structure(void **handle, int *rows, int *cols, int *diag);    /* device mirror back */
 /* level schedule of the triangular solves: counts[0]=forward levels, [1]=backward levels,
  * [2]=forward slices, [3]=backward slices.  level_of_row may be NULL, else int[n] forward levels. */

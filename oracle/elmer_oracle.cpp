@@ -68,6 +68,7 @@ struct Matrix {
   int ndeg;
   int precond;                        // 0 none, 1 diagonal, 2 ilu
   long n_matvec, n_pcond, n_dot, n_norm;
+  const int *ILURows = nullptr, *ILUCols = nullptr, *ILUDiag = nullptr;   // null: alias Rows/Cols/Diag (ILU0, CRSMatrix.F90:3488-3491)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -253,10 +254,75 @@ int crs_ilu0(int N, const int *Rows, const int *Cols, const int *Diag, const dou
   return 1;
 }
 
+// CRSMatrix.F90:3664-3795 InitializeILU1: the pattern of one more level of fill.  Row i keeps its entries and gains
+// the columns j of the upper parts of the rows k < i it already holds (only the rows flagged 1, i.e. present BEFORE
+// this round: fills created in the round do not cascade).  Columns come out ascending.  Two calls: ILUCols == null
+// counts (3694-3717), otherwise fills (3729-3762).  1-based contents.
+long crs_ilu1_pattern(int N, const int *Rows, const int *Cols, const int *Diag, int *ILURows, int *ILUCols, int *ILUDiag) {
+  std::vector<int> C(N + 2, 0);
+  long nz = 0;
+  if (ILURows) ILURows[0] = 1;
+  for (int i = 1; i <= N; ++i) {
+    for (int k = Rows[i - 1]; k <= Rows[i] - 1; ++k) C[Cols[k - 1]] = 1;
+    int RowMin = Cols[Rows[i - 1] - 1], RowMax = Cols[Rows[i] - 2];
+    for (int k = RowMin; k <= i - 1; ++k) {
+      if (C[k] == 1) {
+        for (int l = Diag[k - 1] + 1; l <= Rows[k] - 1; ++l) {
+          int j = Cols[l - 1];
+          if (C[j] == 0) { C[j] = 2; RowMax = std::max(RowMax, j); }
+        }
+      }
+    }
+    long j = ILURows ? ILURows[i - 1] - 1 : 0;
+    for (int k = RowMin; k <= RowMax; ++k) {
+      if (C[k] > 0) {
+        ++j; ++nz;
+        C[k] = 0;
+        if (ILUCols) { ILUCols[j - 1] = k; if (k == i) ILUDiag[i - 1] = (int)j; }
+      }
+    }
+    if (ILURows) ILURows[i] = (int)(j + 1);
+  }
+  return nz;
+}
+
+// CRSMatrix.F90:3604-3661 with ILUn > 0: the same row-by-row elimination on the ILU pattern; the row is scattered
+// from A's own entries (fill positions start from 0) and only pattern positions are updated.
+int crs_ilun_factor(int N, const int *Rows, const int *Cols, const double *Values, const int *ILURows, const int *ILUCols,
+                    const int *ILUDiag, double *ILUValues) {
+  if (N == 0) return 1;
+  std::vector<char> C(N + 1, 0);
+  std::vector<double> S(N + 1, 0.0);
+  for (int i = 1; i <= N; ++i) {
+    for (int k = Rows[i - 1]; k <= Rows[i] - 1; ++k) S[Cols[k - 1]] = Values[k - 1];
+    for (int k = ILURows[i - 1]; k <= ILURows[i] - 1; ++k) C[ILUCols[k - 1]] = 1;
+    for (int m = ILURows[i - 1]; m <= ILUDiag[i - 1] - 1; ++m) {
+      int k = ILUCols[m - 1];
+      if (S[k] == 0.0) continue;
+      double ukk = ILUValues[ILUDiag[k - 1] - 1];
+      if (std::fabs(ukk) > AEPS) S[k] = S[k] / ukk;
+      for (int l = ILUDiag[k - 1] + 1; l <= ILURows[k] - 1; ++l) {
+        int j = ILUCols[l - 1];
+        if (C[j]) S[j] = S[j] - S[k] * ILUValues[l - 1];
+      }
+    }
+    for (int k = ILURows[i - 1]; k <= ILURows[i] - 1; ++k) {
+      int c = ILUCols[k - 1];
+      if (C[c]) { ILUValues[k - 1] = S[c]; S[c] = 0.0; C[c] = 0; }
+    }
+  }
+  for (int i = 1; i <= N; ++i) {
+    double &d = ILUValues[ILUDiag[i - 1] - 1];
+    if (std::fabs(d) < AEPS) d = 1.0;
+    else d = 1.0 / d;
+  }
+  return 1;
+}
+
 // CRSMatrix.F90:4590-4663 CRS_LUSolve, non-Cholesky branch (4642-4660); diagonal fallback 4610-4616.
 void crs_lusolve(const Matrix &A, double *b) {
   const int n = A.n;
-  const int *Rows = A.Rows, *Cols = A.Cols, *Diag = A.Diag;
+  const int *Rows = A.ILURows ? A.ILURows : A.Rows, *Cols = A.ILUCols ? A.ILUCols : A.Cols, *Diag = A.ILUDiag ? A.ILUDiag : A.Diag;
   const double *Values = A.ILUValues;
   double *B = b - 1;
   if (!Values) {
@@ -918,6 +984,26 @@ int orc_crs_ilu0(int n, const int *rows, const int *cols, const int *diag, const
                  double *iluvals) {
   return crs_ilu0(n, rows, cols, diag, vals, iluvals);
 }
+long orc_crs_ilu1_pattern(int n, const int *rows, const int *cols, const int *diag, int *ilurows, int *ilucols, int *iludiag) {
+  return crs_ilu1_pattern(n, rows, cols, diag, ilurows, ilucols, iludiag);
+}
+int orc_crs_ilun_factor(int n, const int *rows, const int *cols, const double *vals, const int *ilurows, const int *ilucols,
+                        const int *iludiag, double *iluvals) {
+  return crs_ilun_factor(n, rows, cols, vals, ilurows, ilucols, iludiag, iluvals);
+}
+// same as orc_itersolve with the ILU(n) factor given on its own pattern
+int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, const double *vals, int ndeg,
+                  const double *iluvals, const double *b, double *x, int *ipar, double *dpar,
+                  int method, int precond, const double *P, long *counts);
+static const int *g_ilu_rows = nullptr, *g_ilu_cols = nullptr, *g_ilu_diag = nullptr;
+int orc_itersolve_ilun(int n, const int *rows, const int *cols, const int *diag, const double *vals, int ndeg,
+                       const int *ilurows, const int *ilucols, const int *iludiag, const double *iluvals, const double *b, double *x,
+                       int *ipar, double *dpar, int method, const double *P, long *counts) {
+  g_ilu_rows = ilurows; g_ilu_cols = ilucols; g_ilu_diag = iludiag;
+  int rc = orc_itersolve(n, rows, cols, diag, vals, ndeg, iluvals, b, x, ipar, dpar, method, 2, P, counts);
+  g_ilu_rows = g_ilu_cols = g_ilu_diag = nullptr;
+  return rc;
+}
 void orc_crs_lu_precond(int n, const int *rows, const int *cols, const int *diag, const double *iluvals,
                         double *u, const double *v) {
   Matrix A{n, rows, cols, diag, nullptr, iluvals, 1, 2, 0, 0, 0, 0};
@@ -936,6 +1022,7 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
                   const double *iluvals, const double *b, double *x, int *ipar, double *dpar,
                   int method, int precond, const double *P, long *counts) {
   Matrix A{n, rows, cols, diag, vals, iluvals, ndeg, precond, 0, 0, 0, 0};
+  A.ILURows = g_ilu_rows; A.ILUCols = g_ilu_cols; A.ILUDiag = g_ilu_diag;
   Ops op{&A};
   HUTI_NDIM = n;
   if (method == 2 || method == 3) {

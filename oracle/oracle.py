@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5}
-PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2}
+PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2, "ilu1": 2, "ilu2": 2, "ilu3": 2}
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -44,6 +44,11 @@ def lib():
     L.orc_crs_diag_precond.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp]
     L.orc_crs_ilu0.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp]
     L.orc_crs_lu_precond.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp]
+    L.orc_crs_ilu1_pattern.restype = C.c_long
+    L.orc_crs_ilu1_pattern.argtypes = [C.c_int, _ip, _ip, _ip, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_crs_ilun_factor.argtypes = [C.c_int, _ip, _ip, _dp, _ip, _ip, _ip, _dp]
+    L.orc_itersolve_ilun.argtypes = [C.c_int, _ip, _ip, _ip, _dp, C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _ip, _dp, C.c_int,
+                                     C.c_void_p, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
     L.orc_itersolve.argtypes = [C.c_int, _ip, _ip, _ip, _dp, C.c_int, C.c_void_p, _dp, _dp, _ip, _dp,
                                 C.c_int, C.c_int, C.c_void_p, _lp]
     L.orc_scale_system.restype = C.c_double
@@ -92,7 +97,24 @@ def ilu0(A):
     return ilu
 
 
+def ilun(A, order):
+    """CRS_IncompleteLU(A, order) for order >= 1 (CRSMatrix.F90:3445-3795): `order` rounds of InitializeILU1 on the
+    pattern, then the row-by-row factorisation.  Returns a CRS holding ILURows/ILUCols/ILUDiag/ILUValues."""
+    rows, cols, diag = A.rows, A.cols, A.diag
+    for _ in range(order):
+        nz = lib().orc_crs_ilu1_pattern(A.n, rows, cols, diag, None, None, None)
+        r2 = np.zeros(A.n + 1, dtype=np.int32); c2 = np.zeros(nz, dtype=np.int32); d2 = np.zeros(A.n, dtype=np.int32)
+        lib().orc_crs_ilu1_pattern(A.n, rows, cols, diag, r2.ctypes.data_as(C.c_void_p), c2.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+        rows, cols, diag = r2, c2, d2
+    vals = np.zeros(cols.size)
+    lib().orc_crs_ilun_factor(A.n, A.rows, A.cols, A.vals, rows, cols, diag, vals)
+    return CRS(rows, cols, diag, vals, A.ndeg)
+
+
 def lu_precond(A, ilu, v):
+    """ilu: ILUValues on A's pattern (ILU0), or the CRS returned by ilun()."""
+    if isinstance(ilu, CRS):
+        A, ilu = ilu, ilu.vals
     u = np.empty(A.n)
     lib().orc_crs_lu_precond(A.n, A.rows, A.cols, A.diag, ilu, u, np.ascontiguousarray(v, dtype=np.float64))
     return u
@@ -147,9 +169,12 @@ def itersolve(A, b, x0=None, method="bicgstab", precond="none", ilu=None, P=None
     b = np.ascontiguousarray(b, dtype=np.float64)
     ipar, dpar = fill_ipar_dpar(n, method, **kw)
     pc = PRECONDS[precond]
+    order = {"ilu1": 1, "ilu2": 2, "ilu3": 3}.get(precond, 0)
+    if order and ilu is None:
+        ilu = ilun(A, order)
     if pc == 2 and ilu is None:
         ilu = ilu0(A)
-    ilu_p = ilu.ctypes.data_as(C.c_void_p) if (pc == 2) else None
+    ilu_p = ilu.ctypes.data_as(C.c_void_p) if (pc == 2 and not isinstance(ilu, CRS)) else None
     Pp = None
     if method == "idrs":
         s = int(ipar[18 - 1])
@@ -158,8 +183,12 @@ def itersolve(A, b, x0=None, method="bicgstab", precond="none", ilu=None, P=None
         P = np.asfortranarray(P, dtype=np.float64)
         Pp = P.ctypes.data_as(C.c_void_p)
     counts = np.zeros(4, dtype=np.int64)
-    rc = lib().orc_itersolve(n, A.rows, A.cols, A.diag, A.vals, A.ndeg, ilu_p, b, x, ipar, dpar,
-                             METHODS[method], pc, Pp, counts)
+    if isinstance(ilu, CRS):      # ILU(n) factor on its own pattern
+        rc = lib().orc_itersolve_ilun(n, A.rows, A.cols, A.diag, A.vals, A.ndeg, ilu.rows, ilu.cols, ilu.diag, ilu.vals, b, x, ipar, dpar,
+                                      METHODS[method], Pp, counts)
+    else:
+        rc = lib().orc_itersolve(n, A.rows, A.cols, A.diag, A.vals, A.ndeg, ilu_p, b, x, ipar, dpar,
+                                 METHODS[method], pc, Pp, counts)
     assert rc == 0
     return dict(x=x, info=int(ipar[30 - 1]), iters=int(ipar[31 - 1]), residual=float(dpar[9]),
                 counts=dict(matvec=int(counts[0]), pcond=int(counts[1]), dot=int(counts[2]), norm=int(counts[3])),
