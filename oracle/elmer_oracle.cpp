@@ -51,6 +51,7 @@ enum { HUTI_TRUERESIDUAL = 0, HUTI_TRESID_SCALED_BYB = 1, HUTI_PSEUDORESIDUAL = 
 #define HUTI_MAXIT IPAR(10)
 #define HUTI_MINIT IPAR(11)
 #define HUTI_STOPC IPAR(12)
+#define HUTI_GMRES_RESTART IPAR(15)
 #define HUTI_BICGSTABL_L IPAR(16)
 #define HUTI_GCR_RESTART IPAR(17)
 #define HUTI_IDRS_S IPAR(18)
@@ -360,14 +361,16 @@ void pcond_dummy(const Matrix &A, double *u, const double *v) {
 // --- the five HUTI callbacks bound to the matrix (IterSolve.F90:790-912) ---
 struct Ops {
   Matrix *A;
+  bool left = false;   // IterSolve.F90:509-525: GMRES (BiCGStab2, TFQMR) get the preconditioner in the LEFT slot, the dummy in the right one
   void matvec(const double *u, double *v) { crs_matvec(*A, u, v); A->n_matvec++; }
-  void pcondr(double *u, const double *v) {  // right preconditioner slot
+  void apply(double *u, const double *v) {
     A->n_pcond++;
     if (A->precond == 2) crs_lu_precond(*A, u, v);
     else if (A->precond == 1) crs_diag_precond(*A, u, v);
     else pcond_dummy(*A, u, v);
   }
-  void pcondl(double *u, const double *v) { pcond_dummy(*A, u, v); }  // pconddProc = 0 -> dummy
+  void pcondr(double *u, const double *v) { if (left) pcond_dummy(*A, u, v); else apply(u, v); }   // right preconditioner slot
+  void pcondl(double *u, const double *v) { if (left) apply(u, v); else pcond_dummy(*A, u, v); }   // pconddProc = 0 -> dummy
   double dot(int n, const double *x, const double *y) { A->n_dot++; return ref_ddot(n, x, y); }
   double norm(int n, const double *x) { A->n_norm++; return ref_dnrm2(n, x); }
 };
@@ -432,6 +435,150 @@ void huti_dcgsolv(Ops &op, int ndim, double *X, const double *B, int *ipar, doub
   }
   HUTI_ITERS = iter_count;
   dpar[9] = residual;  // test aid only: last residual in dpar(10) (slot unused by HUTI)
+}
+
+// fhutiter/src/huti_aux.F90:221-289 huti_dlusolve: in-place LU without pivoting (Saad, Alg. 10.4) of the
+// column-major n x n matrix, then L u = v, U u = u.
+static void huti_dlusolve(int n, double *lumat, double *u, const double *v) {
+#define LU_(i, j) lumat[((i) - 1) + (size_t)((j) - 1) * n]
+  for (int i = 2; i <= n; ++i)
+    for (int k = 1; k <= i - 1; ++k) {
+      LU_(i, k) = LU_(i, k) / LU_(k, k);
+      for (int j = k + 1; j <= n; ++j) LU_(i, j) = LU_(i, j) - LU_(i, k) * LU_(k, j);
+    }
+  for (int i = 1; i <= n; ++i) {
+    u[i - 1] = v[i - 1];
+    for (int k = 1; k <= i - 1; ++k) u[i - 1] = u[i - 1] - LU_(i, k) * u[k - 1];
+  }
+  for (int i = n; i >= 1; --i) {
+    for (int k = i + 1; k <= n; ++k) u[i - 1] = u[i - 1] - LU_(i, k) * u[k - 1];
+    u[i - 1] = u[i - 1] / LU_(i, i);
+  }
+#undef LU_
+}
+
+// fhutiter/src/huti_gmres.F90:390-822 huti_dgmressolv: restarted GMRES(m) with Givens rotations.  work(n, 7+m) =
+// W, R, S, VTMP, T1V, V(1..m+1) (macros 59-69).  S keeps the rotated right-hand side in its first m+1 entries.
+// In Elmer the preconditioner sits in the left slot (IterSolve.F90:509-525): every residual below is M^-1 (b - A x).
+void huti_dgmressolv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar, double *work) {
+  const size_t N = (size_t)ndim;
+  const int m = HUTI_GMRES_RESTART;
+  double *W = work, *R = work + N, *S = work + 2 * N, *VTMP = work + 3 * N, *T1V = work + 4 * N;
+  auto V = [&](int i) { return work + (size_t)(5 + i - 1) * N; };      // V(i), i = 1..m+1
+  std::vector<double> H((size_t)(m + 1) * (m + 1), 0.0), HLU((size_t)(m + 1) * (m + 1), 0.0), CS(m + 1, 0.0), SN(m + 1, 0.0), Y(m + 1, 0.0);
+#define H_(i, j) H[((i) - 1) + (size_t)((j) - 1) * (m + 1)]
+  int iter_count = 1;
+  double residual = 0, rhsnorm = 1.0, precrhsnorm = 1.0;
+  const double bnrm = op.norm(ndim, B);
+  if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB || HUTI_STOPC == HUTI_PRESID_SCALED_BYB) rhsnorm = bnrm;
+  if (HUTI_STOPC == HUTI_PRESID_SCALED_BYPRECB) { op.pcondl(T1V, B); precrhsnorm = op.norm(ndim, T1V); }
+  op.pcondr(T1V, X);                                                 // 475-486 (result overwritten at 300)
+  op.matvec(T1V, R);
+#pragma omp parallel for
+  for (int i = 0; i < ndim; ++i) T1V[i] = B[i] - R[i];
+  op.pcondl(R, T1V);
+  for (int j = 1; j <= m + 1; ++j) std::fill(V(j), V(j) + N, 0.0);
+  std::fill(VTMP, VTMP + N, 0.0);
+  VTMP[0] = 1.0;
+  for (;;) {                                                          // label 300
+    op.pcondr(T1V, X);
+    op.matvec(T1V, R);
+#pragma omp parallel for
+    for (int i = 0; i < ndim; ++i) T1V[i] = B[i] - R[i];
+    op.pcondl(R, T1V);
+    const double alpha = op.norm(ndim, R);
+    if (alpha == 0) { HUTI_INFO = 40; break; }                        // HUTI_GMRES_ALPHA
+#pragma omp parallel for
+    for (int i = 0; i < ndim; ++i) V(1)[i] = R[i] / alpha;
+#pragma omp parallel for
+    for (int i = 0; i < ndim; ++i) S[i] = alpha * VTMP[i];
+    bool early = false, broke = false;
+    for (int i = 1; i <= m; ++i) {
+      op.pcondr(W, V(i));
+      op.matvec(W, T1V);
+      op.pcondl(W, T1V);
+      for (int k = 1; k <= i; ++k) {
+        H_(k, i) = op.dot(ndim, W, V(k));
+        const double hki = H_(k, i); const double *vk = V(k);
+#pragma omp parallel for
+        for (int ii = 0; ii < ndim; ++ii) W[ii] = W[ii] - hki * vk[ii];
+      }
+      const double beta = op.norm(ndim, W);
+      if (beta == 0) { HUTI_INFO = 41; broke = true; break; }        // HUTI_GMRES_BETA
+      H_(i + 1, i) = beta;
+      { double *vn = V(i + 1);
+#pragma omp parallel for
+        for (int ii = 0; ii < ndim; ++ii) vn[ii] = W[ii] / beta; }
+      for (int k = 1; k <= i - 1; ++k) {                              // 600-604
+        const double temp = CS[k] * H_(k, i) + SN[k] * H_(k + 1, i);
+        H_(k + 1, i) = -1 * SN[k] * H_(k, i) + CS[k] * H_(k + 1, i);
+        H_(k, i) = temp;
+      }
+      if (H_(i + 1, i) == 0) { CS[i] = 1; SN[i] = 0; }
+      else if (std::fabs(H_(i + 1, i)) > std::fabs(H_(i, i))) {
+        const double t2 = H_(i, i) / H_(i + 1, i);
+        SN[i] = 1 / std::sqrt(1 + (t2 * t2)); CS[i] = t2 * SN[i];
+      } else {
+        const double t2 = H_(i + 1, i) / H_(i, i);
+        CS[i] = 1 / std::sqrt(1 + (t2 * t2)); SN[i] = t2 * CS[i];
+      }
+      const double temp = CS[i] * S[i - 1];
+      S[i] = -1 * SN[i] * S[i - 1];
+      S[i - 1] = temp;
+      H_(i, i) = (CS[i] * H_(i, i)) + (SN[i] * H_(i + 1, i));
+      H_(i + 1, i) = 0;
+      const double error = std::fabs(S[i]) / bnrm;
+      if ((float)error < HUTI_TOLERANCE) {                            // 628: REAL(error)
+        std::fill(HLU.begin(), HLU.end(), 0.0);
+        { size_t j = 0; for (int k = 1; k <= i; ++k) for (int l = 1; l <= i; ++l) HLU[j++] = H_(l, k); }
+        huti_dlusolve(i, HLU.data(), Y.data(), S);
+        for (int c = 1; c <= i; ++c) { const double y = Y[c - 1]; const double *vc = V(c);
+#pragma omp parallel for
+          for (int ii = 0; ii < ndim; ++ii) X[ii] = X[ii] + vc[ii] * y; }
+        early = true;
+        break;
+      }
+    }
+    if (broke) break;
+    if (!early) {                                                     // 650-664 (the test at 650 repeats the last `error`)
+      std::fill(HLU.begin(), HLU.end(), 0.0);
+      { size_t j = 0; for (int k = 1; k <= m; ++k) for (int l = 1; l <= m; ++l) HLU[j++] = H_(l, k); }
+      huti_dlusolve(m, HLU.data(), Y.data(), S);
+      for (int c = 1; c <= m; ++c) { const double y = Y[c - 1]; const double *vc = V(c);
+#pragma omp parallel for
+        for (int ii = 0; ii < ndim; ++ii) X[ii] = X[ii] + vc[ii] * y; }
+    }
+    // 500: convergence check (HUTI_TRESID_SCALED_BYB is what IterSolver sets; the other criteria are restated for completeness)
+    if (HUTI_STOPC == HUTI_PSEUDORESIDUAL || HUTI_STOPC == HUTI_PRESID_SCALED_BYB || HUTI_STOPC == HUTI_PRESID_SCALED_BYPRECB) {
+      op.matvec(X, R);
+#pragma omp parallel for
+      for (int i = 0; i < ndim; ++i) R[i] = R[i] - B[i];
+      op.pcondl(T1V, R);
+      residual = op.norm(ndim, T1V);
+      if (HUTI_STOPC == HUTI_PRESID_SCALED_BYB) residual /= rhsnorm;
+      if (HUTI_STOPC == HUTI_PRESID_SCALED_BYPRECB) residual /= precrhsnorm;
+    } else {
+      op.pcondr(T1V, X);
+      op.matvec(T1V, R);
+#pragma omp parallel for
+      for (int i = 0; i < ndim; ++i) T1V[i] = B[i] - R[i];
+      op.pcondl(R, T1V);
+      residual = op.norm(ndim, R);
+      if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB) residual /= rhsnorm;
+    }
+    S[m] = op.norm(ndim, R);                                          // 781
+    if (HUTI_DBUGLVL != 0 && HUTI_DBUGLVL != INT_MAX && iter_count % HUTI_DBUGLVL == 0)
+      printf("   gmres:%8d%11.4E\n", iter_count, residual);
+    if (residual < HUTI_TOLERANCE) { HUTI_INFO = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > HUTI_MAXTOLERANCE) { HUTI_INFO = HUTI_DIVERGENCE; break; }
+    iter_count = iter_count + 1;
+    if (iter_count > HUTI_MAXIT) { HUTI_INFO = HUTI_MAXITER; break; }
+  }
+  HUTI_ITERS = iter_count;
+  op.pcondr(T1V, X);                                                  // 815-816
+  for (int i = 0; i < ndim; ++i) X[i] = T1V[i];
+  dpar[9] = residual;
+#undef H_
 }
 
 // fhutiter/src/huti_bicgstab.F90:279-566 huti_dbicgstabsolv.  work(n,8) = RTLD,P,T1V,V,S,T2V,T,R.
@@ -1063,6 +1210,10 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
     if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
     if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;
     HUTI_ITERS = iters; dpar[9] = res;
+  } else if (method == 6) {
+    op.left = true;
+    std::vector<double> work((size_t)n * (7 + HUTI_GMRES_RESTART), 0.0);
+    huti_dgmressolv(op, n, x, b, ipar, dpar, work.data());
   } else {
     return -1;
   }

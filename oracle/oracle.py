@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5}
+METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6}
 PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2, "ilu1": 2, "ilu2": 2, "ilu3": 2}
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -130,7 +130,7 @@ def dnrm2(x):
 
 # ------------------------------------------------------------------ IterSolver
 def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residual_output=0,
-                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1):
+                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10):
     """ipar/dpar exactly as IterSolver fills them (IterSolve.F90:245-503), HUTI slots per
     fhutiter/src/huti_fdefs.h:101-155."""
     ipar = np.zeros(50, dtype=np.int32)
@@ -143,6 +143,9 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
     ipar[11 - 1] = minit
     ipar[12 - 1] = stopc              # HUTI_TRESID_SCALED_BYB (IterSolve.F90:430)
     ipar[14 - 1] = 1                  # HUTI_USERSUPPLIEDX (473)
+    if method == "gmres":             # IterSolve.F90:346-350
+        ipar[15 - 1] = gmres_restart
+        ipar[4 - 1] = 7 + gmres_restart
     if method == "bicgstabl":
         ipar[16 - 1] = max(2, bicgstabl_l)
     if method == "gcr":
