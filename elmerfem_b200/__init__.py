@@ -118,6 +118,9 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
     ipar[10] = minit
     ipar[11] = stopc
     ipar[13] = 1
+    if method == "gmres":             # IterSolve.F90:346-350
+        ipar[14] = gmres_restart
+        ipar[3] = 7 + gmres_restart
     if method == "bicgstabl":
         ipar[15] = max(2, bicgstabl_l)
     if method == "gcr":

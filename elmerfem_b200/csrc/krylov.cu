@@ -589,6 +589,97 @@ static HostResult run_gcr(Handle &h, const double *b, double *x, int pc, int Rou
   return res;
 }
 
+// fhutiter/src/huti_gmres.F90:390-822 huti_dgmressolv: restarted GMRES(m), modified Gram-Schmidt, Givens rotations.
+// IterSolver hands GMRES the preconditioner in the LEFT slot (IterSolve.F90:509-525), so every residual here is
+// M^-1 (b - A x).  Vectors stay on the device; the (m+1)^2 Hessenberg algebra and huti_dlusolve run on the host
+// exactly as in the reference.  HUTI_ITERS counts restart cycles.
+static void host_lusolve(int n, std::vector<double> &lu, double *u, const double *v) {   // huti_aux.F90:221-289
+  auto LU = [&](int i, int j) -> double & { return lu[(size_t)(i - 1) + (size_t)(j - 1) * n]; };
+  for (int i = 2; i <= n; ++i)
+    for (int k = 1; k <= i - 1; ++k) {
+      LU(i, k) = LU(i, k) / LU(k, k);
+      for (int j = k + 1; j <= n; ++j) LU(i, j) = LU(i, j) - LU(i, k) * LU(k, j);
+    }
+  for (int i = 1; i <= n; ++i) { u[i - 1] = v[i - 1]; for (int k = 1; k <= i - 1; ++k) u[i - 1] = u[i - 1] - LU(i, k) * u[k - 1]; }
+  for (int i = n; i >= 1; --i) { for (int k = i + 1; k <= n; ++k) u[i - 1] = u[i - 1] - LU(i, k) * u[k - 1]; u[i - 1] = u[i - 1] / LU(i, i); }
+}
+static HostResult run_gmres(Handle &h, const double *b, double *x, int pc, int MaxIt, double Tol, double MaxTol, int m, int stopc) {
+  HostResult res;
+  B200_REQUIRE(m >= 1, "GMRES: restart < 1");
+  Solver S(h, pc, 3 + m + 1);
+  const int n = S.n;
+  double *W = S.vec[0], *R = S.vec[1], *T1V = S.vec[2];
+  auto V = [&](int i) { return S.vec[3 + (i - 1)]; };
+  std::vector<double> H((size_t)(m + 1) * (m + 1), 0.0), HLU, CS(m + 2, 0.0), SN(m + 2, 0.0), Y(m + 1, 0.0), Sv(m + 2, 0.0);
+  auto Hh = [&](int i, int j) -> double & { return H[(size_t)(i - 1) + (size_t)(j - 1) * (m + 1)]; };
+  const double bnrm = S.norm(b);
+  const double rhsnorm = (stopc == 1 || stopc == 3) ? bnrm : 1.0;
+  // M^-1 (b - A x) into R (or the vector the preconditioner aliased it to)
+  auto prec_residual = [&]() -> double * {
+    S.matvec(x, R);
+    copy_vec(h, n, b, T1V); S.lin(R, -1.0, T1V, 1.0);            // T1V = B - R
+    return S.precond(R, T1V);
+  };
+  h.st_matvec++; h.st_pcond++;                                    // the reference's initial residual (475-486) is recomputed at 300: not repeated here
+  int iter_count = 1; double residual = 0.0;
+  auto update_x = [&](int k) {                                    // X = X + V(:,1:k) Y
+    HLU.assign((size_t)k * k, 0.0);
+    for (int c = 1, j = 0; c <= k; ++c) for (int l = 1; l <= k; ++l) HLU[j++] = Hh(l, c);
+    host_lusolve(k, HLU, Y.data(), Sv.data());
+    for (int c = 1; c <= k; ++c) S.lin(V(c), Y[c - 1], x, 1.0);
+  };
+  for (;;) {
+    double *rs = prec_residual();
+    const double alpha = S.norm(rs);
+    if (alpha == 0) { res.info = 40; break; }                     // HUTI_GMRES_ALPHA
+    copy_vec(h, n, rs, V(1)); S.lin(V(1), 0.0, V(1), 1.0 / alpha);
+    std::fill(Sv.begin(), Sv.end(), 0.0); Sv[0] = alpha;          // S = alpha * e1
+    bool early = false, broke = false;
+    for (int i = 1; i <= m; ++i) {
+      S.matvec(V(i), T1V);
+      double *ws = S.precond(W, T1V);
+      if (ws != W) copy_vec(h, n, ws, W);
+      for (int k = 1; k <= i; ++k) {
+        Hh(k, i) = S.dot(W, V(k));
+        S.lin(V(k), -Hh(k, i), W, 1.0);
+      }
+      const double beta = S.norm(W);
+      if (beta == 0) { res.info = 41; broke = true; break; }      // HUTI_GMRES_BETA
+      Hh(i + 1, i) = beta;
+      copy_vec(h, n, W, V(i + 1)); S.lin(V(i + 1), 0.0, V(i + 1), 1.0 / beta);
+      for (int k = 1; k <= i - 1; ++k) {
+        const double temp = CS[k] * Hh(k, i) + SN[k] * Hh(k + 1, i);
+        Hh(k + 1, i) = -1 * SN[k] * Hh(k, i) + CS[k] * Hh(k + 1, i);
+        Hh(k, i) = temp;
+      }
+      if (Hh(i + 1, i) == 0) { CS[i] = 1; SN[i] = 0; }
+      else if (fabs(Hh(i + 1, i)) > fabs(Hh(i, i))) { const double t2 = Hh(i, i) / Hh(i + 1, i); SN[i] = 1 / sqrt(1 + (t2 * t2)); CS[i] = t2 * SN[i]; }
+      else { const double t2 = Hh(i + 1, i) / Hh(i, i); CS[i] = 1 / sqrt(1 + (t2 * t2)); SN[i] = t2 * CS[i]; }
+      const double temp = CS[i] * Sv[i - 1];
+      Sv[i] = -1 * SN[i] * Sv[i - 1];
+      Sv[i - 1] = temp;
+      Hh(i, i) = (CS[i] * Hh(i, i)) + (SN[i] * Hh(i + 1, i));
+      Hh(i + 1, i) = 0;
+      const double error = fabs(Sv[i]) / bnrm;
+      if ((float)error < Tol) { update_x(i); early = true; break; }   // 628: REAL(error)
+    }
+    if (broke) break;
+    if (!early) update_x(m);
+    if (stopc == 2 || stopc == 3) {                                // pseudo-residual criteria (703-732)
+      S.matvec(x, R); S.lin(b, -1.0, R, 1.0);
+      residual = S.norm(S.precond(T1V, R)) / rhsnorm;
+    } else {
+      residual = S.norm(prec_residual()) / rhsnorm;
+    }
+    if (residual < Tol) { res.info = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > MaxTol) { res.info = HUTI_DIVERGENCE; break; }
+    iter_count = iter_count + 1;
+    if (iter_count > MaxIt) { res.info = HUTI_MAXITER; break; }
+  }
+  res.iters = iter_count; res.residual = residual;
+  return res;
+}
+
 // counter-based uniform [0,1) generator for the IDR(s) shadow space when the caller passes none
 __global__ void k_shadow_space(long long n, double *P, unsigned long long seed) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -730,7 +821,7 @@ static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int Ma
 // parsing and the error mapping (fem/src/IterSolve.F90:470-471, 913, 964-1005).
 void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *dpar, int method, int pc, const double *d_P) {
   B200_REQUIRE(h.have_vals, "b200_solve before b200_set_values");
-  B200_REQUIRE(method >= 1 && method <= 5, "unknown iterative method");
+  B200_REQUIRE(method >= 1 && method <= 6, "unknown iterative method");
   B200_REQUIRE(pc >= 0 && pc <= 2, "unknown preconditioner");
   const int n = h.n;
   cudaStream_t st = h.stream;
@@ -752,6 +843,8 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
     case B200_M_BICGSTABL: hr = run_bicgstabl(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(16)); break;
     case B200_M_GCR: hr = run_gcr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(17), IPAR(11)); break;
     case B200_M_IDRS: hr = run_idrs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(18), IPAR(28) == 1, d_P, h.rank); break;
+    case B200_M_GMRES: hr = run_gmres(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(15), stopc); break;
+    default: B200_REQUIRE(false, "unknown iterative method code");
   }
   B200_CUDA(cudaEventRecord(h.ev_end, st));
   B200_CUDA(cudaStreamSynchronize(st));

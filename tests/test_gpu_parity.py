@@ -209,7 +209,7 @@ def test_itersolver_keywords(oracle, heat, heat_gpu):
     assert rel_l2(got["x"], ref["x"]) <= 1e-7
     declined = heat_gpu.itersolver(b, None, sif.replace("ILU0", "ILUT"), 0)
     assert declined is None
-    assert heat_gpu.itersolver(b, None, sif.replace("BiCGStab", "GMRES"), 0) is None
+    assert heat_gpu.itersolver(b, None, sif.replace("BiCGStab", "TFQMR"), 0) is None
 
 
 def test_empty_and_tiny_systems(oracle, b200):
@@ -364,3 +364,40 @@ def test_ilun_task_mode(oracle, b200, heat, monkeypatch):
     v = np.random.RandomState(22).standard_normal(A.n)
     assert np.array_equal(M.lu_precondition(v), oracle.lu_precond(A, F, v))
     M.close()
+
+
+@pytest.mark.parametrize("precond,restart", [("none", 10), ("diagonal", 5), ("ilu0", 5), ("ilu0", 30)])
+def test_gmres_parity(oracle, b200, heat, heat_gpu, precond, restart):
+    """GMRES(m), huti_dgmressolv (fhutiter/src/huti_gmres.F90:390-822), left-preconditioned as IterSolver calls it
+    (IterSolve.F90:509-525): restart-cycle counts and solution against the oracle; nonsymmetric 4-dof system; SIF path."""
+    A, b = heat
+    ref = oracle.itersolve(A, b, method="gmres", precond=precond, tol=TOL, maxit=500, gmres_restart=restart)
+    got = heat_gpu.solve(b, method="gmres", precond=precond, tol=TOL, maxit=500, gmres_restart=restart)
+    assert got["info"] == ref["info"] == 1, (got["info"], ref["info"])
+    assert iters_close(got["iters"], ref["iters"]), (got["iters"], ref["iters"])
+    assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    if precond == "ilu0" and restart == 5:
+        A3, b3 = oracle.cavity_flow(6)
+        A3 = A3.copy(); x = np.zeros(A3.n); oracle.scale_system(A3, b3, x)
+        M = b200.Matrix(); M.set_structure(A3.rows, A3.cols, A3.diag, 1, 4); M.set_values(A3.vals)
+        ref = oracle.itersolve(A3, b3, method="gmres", precond="ilu0", tol=TOL, maxit=300, gmres_restart=20)
+        got = M.solve(b3, method="gmres", precond="ilu0", tol=TOL, maxit=300, gmres_restart=20)
+        assert got["info"] == ref["info"] and iters_close(got["iters"], ref["iters"]), (got["info"], ref["info"], got["iters"], ref["iters"])
+        if ref["info"] == 1:
+            assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+        M.close()
+        sif = """
+          Linear System Solver = Iterative
+          Linear System Iterative Method = GMRES
+          Linear System GMRES Restart = 5
+          Linear System Preconditioning = ILU0
+          Linear System Max Iterations = 500
+          Linear System Convergence Tolerance = 1.0e-8
+        """
+        ref = oracle.itersolve(A, b, method="gmres", precond="ilu0", tol=TOL, maxit=500, gmres_restart=5)
+        got = heat_gpu.itersolver(b, None, sif, 0)
+        assert got is not None and got["info"] == 1 and iters_close(got["iters"], ref["iters"])
+        # maxiter: one cycle only
+        ref = oracle.itersolve(A, b, method="gmres", precond="none", tol=1e-14, maxit=2, gmres_restart=3)
+        got = heat_gpu.solve(b, method="gmres", precond="none", tol=1e-14, maxit=2, gmres_restart=3)
+        assert got["info"] == ref["info"] == 2 and got["iters"] == ref["iters"]
