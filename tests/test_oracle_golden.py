@@ -164,3 +164,46 @@ def test_scaling_roundtrip(oracle):
     assert np.isclose(np.linalg.norm(b2), 1.0)
     oracle.backscale_system(A2, b2, x, D, bn)
     assert np.allclose(A2.vals, A.vals, rtol=1e-13) and np.allclose(b2, b, rtol=1e-13) and np.allclose(x, 1.0, rtol=1e-13)
+
+
+@pytest.mark.parametrize("precond,restart", [("none", 100), ("diagonal", 50), ("ilu0", 10), ("ilu1", 10)])
+def test_testmat_known_answer_gmres(oracle, testmat, precond, restart):
+    """huti_dgmressolv restatement and the ILU(n) factor against the reference's known answer (fhutiter/examples/ex1)."""
+    A, xref = testmat
+    r = oracle.itersolve(A, np.ones(100), method="gmres", precond=precond, tol=1e-10, maxit=1000, gmres_restart=restart)
+    assert r["info"] == 1, (precond, r["info"])
+    assert np.abs(r["x"] - xref).max() < 1e-6
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_ilun_against_dense(oracle, order):
+    """ILU(n) (CRS_IncompleteLU with InitializeILU1 rounds, CRSMatrix.F90:3445-3795): the pattern is the level-of-fill
+    pattern built from first-order fills per round, the values are the dense IKJ elimination restricted to it."""
+    A, _ = oracle.heat_cube(5, faces=["x0"])
+    F = oracle.ilun(A, order)
+    n = A.n
+    # pattern: independent set-based construction of `order` rounds of "add the upper parts of the rows already present"
+    pat = [set((A.cols[A.rows[i] - 1:A.rows[i + 1] - 1] - 1).tolist()) for i in range(n)]
+    for _ in range(order):
+        new = []
+        for i in range(n):
+            s = set(pat[i])
+            for k in sorted(pat[i]):
+                if k < i:
+                    s |= {j for j in pat[k] if j > k}
+            new.append(s)
+        pat = new
+    for i in range(n):
+        assert sorted(pat[i]) == (F.cols[F.rows[i] - 1:F.rows[i + 1] - 1] - 1).tolist(), i
+        assert F.cols[F.diag[i] - 1] == i + 1
+    D = A.to_scipy().toarray()
+    P = np.zeros((n, n), dtype=bool)
+    for i in range(n):
+        P[i, sorted(pat[i])] = True
+    LU = dense_ilu0(D, P)
+    r0 = np.repeat(np.arange(n), np.diff(F.rows))
+    vals = F.vals.copy(); vals[F.diag - 1] = 1.0 / vals[F.diag - 1]
+    assert np.abs(vals - LU[r0, F.cols - 1]).max() <= 1e-12
+    v = np.random.RandomState(3).standard_normal(n)
+    u = oracle.lu_precond(A, F, v)
+    assert np.abs((np.tril(LU, -1) * P + np.eye(n)) @ ((np.triu(LU) * P) @ u) - v).max() <= 1e-11 * np.abs(v).max()
