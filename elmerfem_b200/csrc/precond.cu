@@ -339,6 +339,129 @@ __global__ void __launch_bounds__(256, 2) k_sptrsv(SellView T, const int *__rest
   }
 }
 
+// Rows of 17 .. 16*NCH entries (3-dof elasticity: ~40 per triangle; ILU(1) of a 27-point stencil: ~31).  The generic chunk loop
+// of k_sptrsv pays an HBM + L2 round trip per chunk AFTER the chunk before it is complete, and the upper sweep starts with
+// the operands that arrive last: 2.6 us per level on the elasticity operand.  Here the TAIL (the TRI_TAIL entries next to
+// the diagonal = the previous level) is requested first and polled last; the head chunks are consumed while the tail is
+// still in flight -- subtracted straight away for L (they precede the tail in column order), kept as rounded products
+// for U (they follow it, and the sum must run left to right) -- so that after the last arrival only the tail pairs and,
+// for U, a chain of subtractions remain.  One block per SM: the product registers need the whole register file.
+template <bool UPPER, int NCH>
+__global__ void __launch_bounds__(256, 1) k_sptrsv_wide(SellView T, const int *__restrict__ slice_level, const int *__restrict__ lvl_slices,
+                                                         int *lvl_done, int lookahead, unsigned gate_sleep, unsigned spin_sleep,
+                                                         const double *__restrict__ dinv_slot, const double *__restrict__ rhs,
+                                                         const int *__restrict__ rhs_idx, double *out, double *__restrict__ nat_out,
+                                                         Ctrl *ctrl) {
+  if (ctrl->done) return;
+  constexpr int WT = 16 * NCH;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slice = gwarp; slice < T.nslices; slice += nwarps) {
+    const long long p0 = T.ptr[slice];
+    const int W = (int)((T.ptr[slice + 1] - p0) >> 5);
+    const int slot = slice * 32 + lane;
+    const int row = T.perm[slot];
+    const int len = T.len[slot];
+    const int *__restrict__ cp = T.cols + p0 + lane;
+    const double *__restrict__ vp = T.vals + p0 + lane;
+    double s = row >= 0 ? rhs[rhs_idx ? rhs_idx[slot] : row] : 0.0;
+    const double dinv = (UPPER && row >= 0) ? dinv_slot[slot] : 1.0;
+    long long spins = 0;
+    // register position k <-> stored position k - sh; entry present iff lo <= k < hi
+    const int sh = UPPER ? 0 : WT - W;
+    const int lo = UPPER ? 0 : WT - len, hi = UPPER ? len : WT;
+    const int wl = max(W - 1, 0);
+    constexpr int K0 = UPPER ? 0 : WT - TRI_TAIL;                    // first tail position
+    int ct[TRI_TAIL]; double vt[TRI_TAIL], xt[TRI_TAIL];
+#pragma unroll
+    for (int t = 0; t < TRI_TAIL; ++t) {
+      const int pos = min(max(K0 + t - sh, 0), wl);
+      ct[t] = W ? ld_stream(cp + pos * 32) : 0;
+      vt[t] = W ? ld_stream(vp + pos * 32) : 0.0;
+    }
+    {                                                             // throttle: wait for the wavefront to come near
+      const int wlv = slice_level[slice] - lookahead;
+      if (lane == 0 && wlv >= 0) {
+        const int need = lvl_slices[wlv];
+        while (ld_relaxed_i(lvl_done + wlv * 32) < need) {
+          if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+          if (gate_sleep) __nanosleep(gate_sleep);
+        }
+      }
+      __syncwarp();
+    }
+    unsigned tpend = 0;
+#pragma unroll
+    for (int t = 0; t < TRI_TAIL; ++t) {
+      const bool has = (K0 + t >= lo) && (K0 + t < hi);
+      xt[t] = ld_relaxed_pred(out + ct[t], has, 0.0);
+      tpend |= (unsigned)has << t;
+    }
+    const unsigned thas = tpend;
+    double p[UPPER ? WT : 1];
+#pragma unroll
+    for (int k = 0; k < (UPPER ? WT : 1); ++k) p[k] = 0.0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (UPPER ? (ch * 16 >= W) : (ch * 16 + 15 < WT - W)) continue;   // (warp-uniform) nothing stored in this chunk
+      int c[16]; double v[16], x[16];
+      unsigned has = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = ch * 16 + j;
+        const bool tail = UPPER ? (k < TRI_TAIL) : (k >= WT - TRI_TAIL);
+        const int pos = min(max(k - sh, 0), wl);
+        c[j] = W ? ld_stream(cp + pos * 32) : 0;
+        v[j] = W ? ld_stream(vp + pos * 32) : 0.0;
+        has |= (unsigned)(!tail && k >= lo && k < hi) << j;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = ld_relaxed_pred(out + c[j], (has >> j) & 1u, 0.0);
+      unsigned pend = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pend |= (unsigned)(is_sentinel(x[j])) << j;
+      pend &= has;
+      while (__any_sync(0xffffffffu, pend != 0)) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        if (spin_sleep) __nanosleep(spin_sleep);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = ld_relaxed_pred(out + c[j], (pend >> j) & 1u, x[j]); if (!is_sentinel(x[j])) pend &= ~(1u << j); }
+      }
+      if (!UPPER) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const double t = __dsub_rn(s, __dmul_rn(v[j], x[j])); s = (has >> j) & 1u ? t : s; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[ch * 16 + j] = (has >> j) & 1u ? __dmul_rn(v[j], x[j]) : 0.0;
+      }
+    }
+    // tail operands: the previous level
+#pragma unroll
+    for (int t = 0; t < TRI_TAIL; ++t) if (!is_sentinel(xt[t])) tpend &= ~(1u << t);
+    while (__any_sync(0xffffffffu, tpend != 0)) {
+      if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+      if (spin_sleep) __nanosleep(spin_sleep);
+#pragma unroll
+      for (int t = 0; t < TRI_TAIL; ++t) { xt[t] = ld_relaxed_pred(out + ct[t], (tpend >> t) & 1u, xt[t]); if (!is_sentinel(xt[t])) tpend &= ~(1u << t); }
+    }
+#pragma unroll
+    for (int t = 0; t < TRI_TAIL; ++t) { const double u = __dsub_rn(s, __dmul_rn(vt[t], xt[t])); s = (thas >> t) & 1u ? u : s; }
+    if (UPPER) {
+#pragma unroll
+      for (int k = TRI_TAIL; k < WT; ++k) { const double u = __dsub_rn(s, p[k]); s = (k < hi) ? u : s; }   // absent entries hold +0.0 and are skipped
+    }
+    if (row >= 0) {
+      double res = UPPER ? __dmul_rn(dinv, s) : s;
+      if (res != res) res = __longlong_as_double((long long)CANON_NAN);
+      st_relaxed(out + slot, res);
+      if (nat_out) nat_out[row] = res;
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(lvl_done + slice_level[slice] * 32, 1);
+  }
+}
+
 __global__ void k_tri_prepare(int na, double *a, int nb, double *b, int *counters, int ncounters) {
   const double sent = __longlong_as_double((long long)SENTINEL);
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
@@ -347,19 +470,18 @@ __global__ void k_tri_prepare(int na, double *a, int nb, double *b, int *counter
   for (int i = i0; i < ncounters; i += st) counters[i * 32] = 0;
 }
 
-template <int CH>
-static void lu_launch(Handle &h, double *u, const double *v) {
+static void lu_launch_kernels(Handle &h, const void *kl, const void *ku, double *u, const double *v) {
   cudaStream_t st = h.stream;
   if (!h.grid_tri_l) {
-    h.grid_tri_l = persistent_blocks((const void *)k_sptrsv<false, CH>, 256, h.tri_blocks_per_sm);
-    h.grid_tri_u = persistent_blocks((const void *)k_sptrsv<true, CH>, 256, h.tri_blocks_per_sm);
+    h.grid_tri_l = persistent_blocks(kl, 256, h.tri_blocks_per_sm);
+    h.grid_tri_u = persistent_blocks(ku, 256, h.tri_blocks_per_sm);
   }
   int bl = std::max(1, std::min(h.grid_tri_l, (h.L.nslices + 7) / 8));
   int bu = std::max(1, std::min(h.grid_tri_u, (h.U.nslices + 7) / 8));
   const int la = h.tri_lookahead; const unsigned gs = h.tri_gate_sleep, ss = h.tri_spin_sleep;
-  launch_coresident((const void *)k_sptrsv<false, CH>, bl, 256, st, h.L.view(), (const int *)h.L.gate.p, (const int *)h.d_lvlcnt_f.p, h.tri_counters.p, la, gs, ss,
+  launch_coresident(kl, bl, 256, st, h.L.view(), (const int *)h.L.gate.p, (const int *)h.d_lvlcnt_f.p, h.tri_counters.p, la, gs, ss,
                     (const double *)nullptr, v, (const int *)nullptr, h.d_yl.p, (double *)nullptr, h.ctrl.p);
-  launch_coresident((const void *)k_sptrsv<true, CH>, bu, 256, st, h.U.view(), (const int *)h.U.gate.p, (const int *)h.d_lvlcnt_b.p,
+  launch_coresident(ku, bu, 256, st, h.U.view(), (const int *)h.U.gate.p, (const int *)h.d_lvlcnt_b.p,
                     h.tri_counters.p + (size_t)(h.nlev_f + 1) * 32, la, gs, ss,
                     (const double *)h.d_dinv_slot.p, (const double *)h.d_yl.p, (const int *)h.d_urhs.p, h.d_xu.p, u, h.ctrl.p);
 }
@@ -369,7 +491,11 @@ void lu_apply(Handle &h, double *u, const double *v) {
   if (h.n == 0) return;
   if (h.tri_mode == 1) { lu_apply_task(h, u, v); return; }
   k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
-  if (h.tri_maxw <= 8) lu_launch<8>(h, u, v); else lu_launch<16>(h, u, v);
+  static const bool wide_ok = !(getenv("B200_TRI_WIDE") && atoi(getenv("B200_TRI_WIDE")) == 0);
+  if (h.tri_maxw <= 8) lu_launch_kernels(h, (const void *)k_sptrsv<false, 8>, (const void *)k_sptrsv<true, 8>, u, v);
+  else if (h.tri_maxw <= 16 || !wide_ok || h.tri_maxw > 48) lu_launch_kernels(h, (const void *)k_sptrsv<false, 16>, (const void *)k_sptrsv<true, 16>, u, v);
+  else if (h.tri_maxw <= 32) lu_launch_kernels(h, (const void *)k_sptrsv_wide<false, 2>, (const void *)k_sptrsv_wide<true, 2>, u, v);
+  else lu_launch_kernels(h, (const void *)k_sptrsv_wide<false, 3>, (const void *)k_sptrsv_wide<true, 3>, u, v);
   B200_CUDA(cudaGetLastError());
   h.st_launch += 3; h.st_pcond++;
 }
