@@ -10,6 +10,10 @@ Workload (config.workload):
   N > 1 : the same problem weak-scaled: 200 x 200 x 200*N elements, slab-partitioned along z (ElmerGrid
           `-partition 1 1 N`), one slab of ~8.1M dofs per GPU, block-Jacobi ILU0 as in Elmer's MPI path.
 
+  --workload elasticity : BASELINE.json configs[4] (C5): linear elasticity, 3 dofs/node, 137 x 137 x (140 N - 1) hex8 beam cut into z-slabs,
+          7,998,480 dofs per GPU, BiCGStab(l=4) + Jacobi; a step = the first --elas-rounds rounds (8 SpMV each), NOT a converged
+          solve (config.workload says so); the dominant kernel is then the SpMV.  The reference arm always runs the heat workload.
+
 A step is one IterSolver call on resident data: x = 0, BiCGStab+ILU0 to convergence.  `value` is
 Krylov iterations x global dofs / second (so that it aggregates over GPUs under weak scaling);
 `iters_per_s` is the plain BASELINE.json figure.  The ILU0 factorisation is done (and timed, `factor_ms`)
@@ -234,8 +238,12 @@ def run_b200(args):
         assert r2["info"] == 1 or (elas and r2["info"] == 2)
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    # ---- kernel rooflines, measured live with CUDA events on the solve stream
+    # ---- kernel rooflines, measured live with CUDA events on the solve stream.  The barrier matters for N > 1: the halo
+    # product waits for its neighbours, so a rank entering late (rank 0 has just stopped the clock sampler) would be
+    # timed as SpMV time by the others (measured: 17.7 ms "per SpMV" at N = 8 without it).
+    barrier()
     spmv_ms = M.time_matvec(20)
+    barrier()
     lu_ms = M.time_lu(10) if not elas else 0.0
 
     def maxr(v):

@@ -51,7 +51,7 @@ def lib():
         "b200_create": [vpp], "b200_destroy": [vpp], "b200_device_count": [ip], "b200_set_device": [vpp, ip],
         "b200_set_structure": [vpp, ip, ip, ip, ip, ip, ip, ip],
         "b200_set_values": [vpp, dp, dp], "b200_set_values_device": [vpp, C.c_void_p, C.c_void_p],
-        "b200_factorize": [vpp],
+        "b200_factorize": [vpp], "b200_scale_system": [vpp], "b200_get_values": [vpp, dp],
         "b200_solve": [vpp, dp, dp, ip, dp, ip, ip, dp],
         "b200_solve_device": [vpp, C.c_void_p, C.c_void_p, ip, dp, ip, ip, C.c_void_p],
         "b200_itersolver": [vpp, dp, dp, C.c_char_p, ip, ip],
@@ -171,6 +171,15 @@ class Matrix:
 
     def set_values_device(self, d_vals_ptr, d_prec_ptr=None):
         _check(lib().b200_set_values_device(self.handle, C.c_void_p(d_vals_ptr), C.c_void_p(d_prec_ptr)), "b200_set_values_device")
+
+    def scale_system(self):
+        """Linear System Scaling on the device (ScaleLinearSystemDiagonal); b/x of later solves are scaled and back-scaled inside."""
+        _check(lib().b200_scale_system(self.handle), "b200_scale_system")
+
+    def values(self):
+        out = np.empty(self.nnz)
+        _check(lib().b200_get_values(self.handle, _dp(out)), "b200_get_values")
+        return out
 
     def factorize(self):
         _check(lib().b200_factorize(self.handle), "b200_factorize")

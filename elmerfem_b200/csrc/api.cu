@@ -116,7 +116,7 @@ void values_changed(Handle &h) {
   h.d_dvals.ensure(h.n);
   if (h.n) k_extract_diag<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.n, h.d_diag.p, h.d_vals.p, h.d_dvals.p);
   B200_CUDA(cudaGetLastError());
-  h.have_vals = true; h.ilu_valid = false;
+  h.have_vals = true; h.ilu_valid = false; h.scaled = false;
 }
 
 static void upload(Handle &h, double *dst, const double *src, size_t n) {
@@ -124,6 +124,51 @@ static void upload(Handle &h, double *dst, const double *src, size_t n) {
   B200_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h.stream));
   h.st_h2d += n * sizeof(double);
 }
+// ---- Linear System Scaling on the device (SolverUtils.F90:12976-13213, 13515-13643) ---------------------------
+__global__ void k_scale_diag(int n, const int *__restrict__ rows, const int *__restrict__ diag, const double *__restrict__ vals, double *__restrict__ D) {
+  const double tiny = 2.2250738585072014e-308;                      // TINY(1._dp)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double d = vals[diag[i]];
+    if (fabs(d) <= tiny) { double s = 0.0; for (int j = rows[i]; j < rows[i + 1]; ++j) s += fabs(vals[j]); d = s; }   // 13040-13058
+    D[i] = (fabs(d) > tiny) ? __ddiv_rn(1.0, __dsqrt_rn(fabs(d))) : 1.0;
+  }
+}
+__global__ void k_scale_values(int n, const int *__restrict__ rows, const int *__restrict__ cols, const double *__restrict__ D, double *vals) {
+  const int lane = threadIdx.x & 31;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+    const double di = D[i];
+    for (int j = rows[i] + lane; j < rows[i + 1]; j += 32) vals[j] = __dmul_rn(vals[j], __dmul_rn(di, D[cols[j]]));   // Values(j) * (Diag(i) * Diag(Cols(j)))
+  }
+}
+__global__ void k_scale_b(int n, const double *__restrict__ D, double *b) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b[i] = __dmul_rn(b[i], D[i]);
+}
+// bn2 = sum (b D)^2 on the device; DoRhs unless ||b|| < sqrt(tiny): Dr = D * bnorm, b /= bnorm, x /= Dr
+__global__ void k_scale_rhs_x(int n, const double *__restrict__ D, const double *__restrict__ bn2, double *Dr, double *b, double *x) {
+  double bnorm = sqrt(*bn2);
+  if (bnorm < 1.4916681462400413e-154) bnorm = 1.0;                 // SQRT(TINY(bnorm)): DoRhs = .FALSE.
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double dr = __dmul_rn(D[i], bnorm);
+    Dr[i] = dr; b[i] = __ddiv_rn(b[i], bnorm); x[i] = __ddiv_rn(x[i], dr);
+  }
+}
+__global__ void k_backscale_x(int n, const double *__restrict__ Dr, double *x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = __dmul_rn(x[i], Dr[i]);
+}
+static void scale_in(Handle &h, double *d_b, double *d_x) {
+  const int n = h.n, blocks = std::max(1, std::min((n + 255) / 256, NUM_SMS * 8));
+  h.d_scale_rhs.ensure(std::max(n, 1));
+  k_scale_b<<<blocks, 256, 0, h.stream>>>(n, h.d_scale.p, d_b);
+  dot1(h, n, d_b, d_b, h.scal.p + NSCAL - 1);
+  k_scale_rhs_x<<<blocks, 256, 0, h.stream>>>(n, h.d_scale.p, h.scal.p + NSCAL - 1, h.d_scale_rhs.p, d_b, d_x);
+  B200_CUDA(cudaGetLastError());
+}
+static void scale_out(Handle &h, double *d_x) {
+  const int n = h.n, blocks = std::max(1, std::min((n + 255) / 256, NUM_SMS * 8));
+  k_backscale_x<<<blocks, 256, 0, h.stream>>>(n, h.d_scale_rhs.p, d_x);
+  B200_CUDA(cudaGetLastError());
+}
+
 static void download(Handle &h, double *dst, const double *src, size_t n) {
   if (!n) return;
   B200_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h.stream));
@@ -284,12 +329,43 @@ int b200_solve(void **handle, const double *b, double *x, int *ipar, double *dpa
       size_t np = (size_t)h.n * (size_t)ipar[17];
       h.d_P.ensure(np); upload(h, h.d_P.p, P, np); dP = h.d_P.p;
     }
+    if (h.scaled && h.n) scale_in(h, h.d_b.p, h.d_x.p);
     solve_device(h, h.d_b.p, h.d_x.p, ipar, dpar, *method, *precond, dP);
+    if (h.scaled && h.n) scale_out(h, h.d_x.p);
     download(h, x, h.d_x.p, h.n);
     B200_CUDA(cudaStreamSynchronize(h.stream));
   });
   if (rc && ipar) ipar[29] = B200_INFO_HALTED;
   return rc;
+}
+
+int b200_scale_system(void **handle) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.have_vals, "b200_scale_system before b200_set_values");
+    B200_REQUIRE(!h.scaled, "values are already scaled (call b200_set_values first)");
+    B200_REQUIRE(h.nranks == 1 && !h.halo, "device-side scaling is implemented for single-rank handles only");
+    B200_REQUIRE(!h.have_prec, "device-side scaling with separate PrecValues is not supported");
+    const int n = h.n;
+    h.d_scale.ensure(std::max(n, 1));
+    if (n) {
+      const int blocks = std::max(1, std::min((n + 255) / 256, NUM_SMS * 8));
+      k_scale_diag<<<blocks, 256, 0, h.stream>>>(n, h.d_rows.p, h.d_diag.p, h.d_vals.p, h.d_scale.p);
+      k_scale_values<<<NUM_SMS * 8, 256, 0, h.stream>>>(n, h.d_rows.p, h.d_cols.p, h.d_scale.p, h.d_vals.p);
+      B200_CUDA(cudaGetLastError());
+    }
+    values_changed(h);
+    h.scaled = true;
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
+}
+int b200_get_values(void **handle, double *vals) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(h.have_vals, "no values");
+    download(h, vals, h.d_vals.p, h.nnz);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+  });
 }
 
 // ---- callbacks on host vectors --------------------------------------------------------------

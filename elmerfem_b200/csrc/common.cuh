@@ -131,6 +131,8 @@ struct Handle {
   const int *d_lcols() const { return ilu_order ? dl_cols.p : d_cols.p; }
   const int *d_ldiag() const { return ilu_order ? dl_diag.p : d_diag.p; }
   long long lnnz() const { return ilu_order ? ilu_nnz : nnz; }
+  // device-side Linear System Scaling (b200_scale_system): D, and D * bnorm of the running solve
+  bool scaled = false; DBuf<double> d_scale, d_scale_rhs;
   // SpMV operand
   Sell A;
   // ILU0 + triangular solves

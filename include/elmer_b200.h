@@ -86,6 +86,14 @@ int b200_set_structure(void **handle, const int *n, const int *nnz, const int *r
 int b200_set_values(void **handle, const double *vals, const double *prec_vals);
 /* Same, but vals/prec_vals are DEVICE pointers (values assembled or kept on the GPU). */
 int b200_set_values_device(void **handle, const double *d_vals, const double *d_prec_vals);
+/* `Linear System Scaling` on the device: ScaleLinearSystemDiagonal (fem/src/SolverUtils.F90:12976-13213; real, no
+ * Mass/Damp/PrecValues).  Call after b200_set_values with the UNSCALED values: the device copy becomes
+ * Values(j) * (D(i) * D(Cols(j))), D(i) = 1/sqrt(|a_ii|) (row abs-sum when a_ii is tiny).  From then on b200_solve /
+ * b200_itersolver scale b and x on the way in (b *= D; bnorm = ||b||; b /= bnorm; D *= bnorm; x /= D) and back-scale x on
+ * the way out (BackScaleLinearSystemDiagonal, 13515-13643): the caller passes and receives unscaled vectors and never has
+ * to scale or un-scale its own matrix.  The next b200_set_values clears the state.  Single-rank handles only. */
+int b200_scale_system(void **handle);
+int b200_get_values(void **handle, double *vals);   /* device copy of Values (after scaling, if any) */
 int b200_factorize(void **handle);                 /* ILU(order) of PrecValues (if given) else Values  */
 /* Fill level of the incomplete factorisation, CRS_IncompleteLU(A, ILUn) (fem/src/CRSMatrix.F90:3445-3795; keywords
  * "Linear System Preconditioning = ILU0..ILU9" / "Linear System ILU Order", IterSolve.F90:529-547).  0 (default)

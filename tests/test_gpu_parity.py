@@ -401,3 +401,27 @@ def test_gmres_parity(oracle, b200, heat, heat_gpu, precond, restart):
         ref = oracle.itersolve(A, b, method="gmres", precond="none", tol=1e-14, maxit=2, gmres_restart=3)
         got = heat_gpu.solve(b, method="gmres", precond="none", tol=1e-14, maxit=2, gmres_restart=3)
         assert got["info"] == ref["info"] == 2 and got["iters"] == ref["iters"]
+
+
+def test_device_scaling(oracle, b200):
+    """b200_scale_system = ScaleLinearSystemDiagonal on the device (SolverUtils.F90:12976-13213): scaled values bit-exact
+    against the oracle's restatement; a solve on the UNSCALED b/x through the scaled handle returns the unscaled solution
+    the reference obtains by scaling, solving and back-scaling (13515-13643), in the same number of iterations."""
+    A0, b0 = oracle.heat_cube(16, faces=["x0", "y1"], source=3.0)
+    rs = np.random.RandomState(31)
+    sc = rs.uniform(0.5, 20.0, A0.n)                               # badly scaled, still symmetric: A <- S A S
+    A0 = A0.copy(); A0.vals *= np.repeat(sc, np.diff(A0.rows)) * sc[A0.cols - 1]; b0 = b0 * sc
+    A = A0.copy(); b = b0.copy(); x = np.zeros(A.n)
+    D, bnorm = oracle.scale_system(A, b, x)
+    M = b200.Matrix(); M.set_structure(A0.rows, A0.cols, A0.diag, 1, 1); M.set_values(A0.vals)
+    M.scale_system()
+    assert np.array_equal(M.values(), A.vals)
+    for method, pc in [("bicgstab", "ilu0"), ("cg", "diagonal"), ("gmres", "ilu0")]:
+        ref = oracle.itersolve(A, b, method=method, precond=pc, tol=TOL, maxit=500)
+        xref = ref["x"] * D                                        # BackScale: x = x * Diag
+        got = M.solve(b0, method=method, precond=pc, tol=TOL, maxit=500)
+        assert got["info"] == ref["info"] == 1 and iters_close(got["iters"], ref["iters"]), (method, got["iters"], ref["iters"])
+        assert rel_l2(got["x"], xref) <= 10 * TOL
+    M.set_values(A0.vals)                                          # new values clear the scaled state
+    assert np.array_equal(M.values(), A0.vals)
+    M.close()
