@@ -62,7 +62,7 @@ def lib():
         "b200_set_partition": [vpp, ip, ip, ip, ip, ip, ip, ip, ip],
         "b200_get_halo_plan": [vpp, ip, ip, ip, ip, ip, ip],
         "b200_get_stats": [vpp, dp], "b200_time_matvec": [vpp, ip, dp], "b200_time_lu_precondition": [vpp, ip, dp],
-        "b200_partition_send_lists": [ip] * 10, "b200_partition_split": [ip] * 14,
+        "b200_partition_send_lists": [ip] * 10, "b200_partition_peer_layout": [ip, ip, ip, ip, C.POINTER(C.c_longlong)], "b200_partition_split": [ip] * 14,
         "b200_version": [ip, ip], "b200_vec_len": [vpp, C.POINTER(C.c_longlong)],
     }
     for name, args in sigs.items():
@@ -361,6 +361,15 @@ def partition_send_lists(gn, rows, cols_global, goffset, rank, index_base=1):
     gid = np.zeros(max(int(cnt.sum()), 1), dtype=np.int32)
     _check(lib().b200_partition_send_lists(*args, _ip(cnt), _ip(gid)), "b200_partition_send_lists")
     return cnt, gid[:int(cnt.sum())]
+
+
+def partition_peer_layout(nranks, me, r, cnt):
+    """Host-only: (index of `me` among r's neighbours, r's neighbour count, r's ghost count, offset of me's segment in r's
+    receive area) as the peer-memory halo path derives them from the nranks x nranks send-count matrix."""
+    cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+    out = (C.c_longlong * 4)()
+    _check(lib().b200_partition_peer_layout(_i(nranks), _i(me), _i(r), _ip(cnt), out), "b200_partition_peer_layout")
+    return tuple(int(v) for v in out)
 
 
 def partition_split(rows, cols_global, lo, hi, ghost_gid, index_base=1):

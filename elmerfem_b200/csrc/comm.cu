@@ -160,6 +160,21 @@ static void plan_split(int N, const int *rows, const int *cols, int base, int lo
 
 size_t vec_len(const Handle &h) { return (size_t)h.n + (h.halo ? (size_t)h.halo->nghost : 0); }
 
+// Where rank `me` finds its segment in the receive area of rank r, derived from the send-count matrix cnt[s*np + d]
+// (entries rank s sends to rank d) with the rules b200_set_partition applies on rank r itself: r's neighbours are the ranks
+// it exchanges anything with, ascending; its receive offsets are the prefix sums of what each of them sends to r.
+// qprime = index of `me` in r's neighbour list (-1: not a neighbour), off_me = r.recv_ptr[qprime].
+static void peer_layout(int np, int me, int r, const int *cnt, int &qprime, int &nneigh_r, long long &nghost_r, long long &off_me) {
+  qprime = -1; nneigh_r = 0; nghost_r = 0; off_me = 0;
+  for (int s2 = 0; s2 < np; ++s2) {
+    if (s2 == r) continue;
+    const int to_r = cnt[(size_t)s2 * np + r], from_r = cnt[(size_t)r * np + s2];
+    if (!(to_r || from_r)) continue;
+    if (s2 == me) { qprime = nneigh_r; off_me = nghost_r; }
+    ++nneigh_r; nghost_r += to_r;
+  }
+}
+
 static void p2p_release(Handle &h, Halo &H) {
   if (h.stream) cudaStreamSynchronize(h.stream);
   for (void *b : H.peer_base) if (b) cudaIpcCloseMemHandle(b);
@@ -191,15 +206,8 @@ static void p2p_setup(Handle &h, Halo &H, const std::vector<int> &allcnt) {
   H.peer_base.assign(H.nneigh, nullptr);
   for (int q = 0; q < H.nneigh && ok; ++q) {
     const int r = H.neigh[q];
-    // neighbour r's own plan: its neighbours ascending, receive offsets = prefix of what each sends to r
     int qprime = -1, nneigh_r = 0; long long nghost_r = 0, off_me = 0;
-    for (int s2 = 0; s2 < np; ++s2) {
-      if (s2 == r) continue;
-      const int to_r = allcnt[(size_t)s2 * np + r], from_r = allcnt[(size_t)r * np + s2];
-      if (!(to_r || from_r)) continue;
-      if (s2 == me) { qprime = nneigh_r; off_me = nghost_r; }
-      ++nneigh_r; nghost_r += to_r;
-    }
+    peer_layout(np, me, r, allcnt.data(), qprime, nneigh_r, nghost_r, off_me);
     if (qprime < 0 || cudaIpcOpenMemHandle(&H.peer_base[q], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); H.peer_base[q] = nullptr; ok = 0; break; }
     double *base = (double *)H.peer_base[q];
     unsigned long long *flags = (unsigned long long *)(base + 2 * nghost_r);
@@ -587,6 +595,16 @@ int b200_partition_split(const int *n_own, const int *rows, const int *cols, con
     for (size_t q = 0; q < S.gperm.size(); ++q) gr[S.gperm[q] + 1] = S.glen[q];
     for (int i = 0; i < N; ++i) gr[i + 1] += gr[i];
     std::copy(gr.begin(), gr.end(), g_rows); std::copy(S.gcols.begin(), S.gcols.end(), g_cols);
+  });
+}
+
+/* host-only: layout of rank r's receive area as rank `me` derives it (out[0] = index of me among r's neighbours or -1,
+ * out[1] = r's neighbour count, out[2] = r's ghost count, out[3] = offset of me's segment); cnt = np x np send counts */
+int b200_partition_peer_layout(const int *nranks, const int *me, const int *r, const int *cnt, long long *out) {
+  return guarded_c([&] {
+    int q, nn; long long ng, off;
+    peer_layout(*nranks, *me, *r, cnt, q, nn, ng, off);
+    out[0] = q; out[1] = nn; out[2] = ng; out[3] = off;
   });
 }
 

@@ -156,6 +156,10 @@ int b200_comm_init(void **handle, const int *nranks, const int *rank, const char
 int b200_set_partition(void **handle, const int *gn, const int *n_own, const int *nnz, const int *rows,
                        const int *cols, const int *goffset, const int *index_base, const int *ndeg);
 /* sizes[0]=nneigh, [1]=nsend, [2]=nghost; then arrays sized by a first call with NULL pointers. */
+/* Host-only: where rank `me` writes inside rank r's receive area on the peer-memory halo path, derived from the np x np
+ * send-count matrix cnt[s*np + d] every rank holds after b200_set_partition's count exchange.  out[0] = index of `me`
+ * among r's neighbours (-1: none), out[1] = r's neighbour count, out[2] = r's ghost count, out[3] = offset of the segment. */
+int b200_partition_peer_layout(const int *nranks, const int *me, const int *r, const int *cnt, long long *out);
 int b200_get_halo_plan(void **handle, int *sizes, int *neigh, int *send_ptr, int *send_idx,
                        int *recv_ptr, int *ghost_gid);
 

@@ -32,6 +32,21 @@ def plan_all(b200, parts, goffset):
         rp_ = np.concatenate([[0], np.cumsum([len(send[q][r]) for q in neigh])]).astype(np.int32)
         split = b200.partition_split(rows, cols, int(goffset[r]), int(goffset[r + 1]), ghost, index_base=0)
         plans.append(dict(neigh=np.array(neigh, dtype=np.int32), send_ptr=sp_, send_idx=send_idx, recv_ptr=rp_, ghost_gid=ghost, **split))
+    # peer-memory halo path: what a sender derives about a neighbour's receive area from the send-count matrix alone
+    # must be that neighbour's actual plan (its neighbour order, its receive offsets)
+    cnt = np.array([[len(send[s_][d]) for d in range(nr)] for s_ in range(nr)], dtype=np.int32)
+    for me in range(nr):
+        for r in range(nr):
+            if r == me:
+                continue
+            q, nn, ng, off = b200.partition_peer_layout(nr, me, r, cnt)
+            nb = plans[r]["neigh"].tolist()
+            assert nn == len(nb) and ng == len(plans[r]["ghost_gid"])
+            if me in nb:
+                assert q == nb.index(me) and off == int(plans[r]["recv_ptr"][q])
+                assert int(plans[r]["recv_ptr"][q + 1]) - off == cnt[me, r]
+            else:
+                assert q == -1
     return plans
 
 
