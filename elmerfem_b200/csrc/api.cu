@@ -60,6 +60,7 @@ static void ensure_runtime(Handle &h) {
   h.tt_wpb = env_int("B200_TT_WPB", 0);
   h.tt_wait_ns = (unsigned)env_int("B200_TT_WAIT_NS", 100);
   h.tt_pf = env_int("B200_TT_PF", 16);
+  h.pin_values = env_int("B200_PIN_VALUES", 0);
   h.blas_blocks = env_int("B200_BLAS_BLOCKS", NUM_SMS * 8);
   if (h.blas_blocks > MAX_RED_BLOCKS) h.blas_blocks = MAX_RED_BLOCKS;
 }
@@ -119,6 +120,18 @@ void values_changed(Handle &h) {
   h.have_vals = true; h.ilu_valid = false; h.scaled = false;
 }
 
+static void unpin_values(Handle &h) {
+  if (h.pinned_ptr) { cudaHostUnregister(const_cast<void *>(h.pinned_ptr)); cudaGetLastError(); }
+  h.pinned_ptr = nullptr; h.pinned_bytes = 0;
+}
+// page-locks the caller's array once (same pointer and size on later calls: nothing to do); failure is not an error,
+// the copy then takes the pageable path
+static void pin_values(Handle &h, const void *p, size_t bytes) {
+  if (!h.pin_values || !p || !bytes || (p == h.pinned_ptr && bytes == h.pinned_bytes)) return;
+  unpin_values(h);
+  if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) { h.pinned_ptr = p; h.pinned_bytes = bytes; }
+  else cudaGetLastError();
+}
 static void upload(Handle &h, double *dst, const double *src, size_t n) {
   if (!n) return;
   B200_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h.stream));
@@ -219,6 +232,7 @@ int b200_destroy(void **handle) {
     Handle *h = static_cast<Handle *>(*handle);
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    unpin_values(*h);
     halo_release(*h);
     h->d_rows_in.release(); h->d_cols_in.release(); h->d_diag_in.release();
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
@@ -270,6 +284,7 @@ int b200_set_values(void **handle, const double *vals, const double *prec_vals) 
       return;
     }
     h.d_vals.ensure(h.nnz);
+    pin_values(h, vals, (size_t)h.nnz * sizeof(double));
     upload(h, h.d_vals.p, vals, h.nnz);
     h.have_prec = prec_vals != nullptr;
     if (prec_vals) { h.d_prec.ensure(h.nnz); upload(h, h.d_prec.p, prec_vals, h.nnz); }

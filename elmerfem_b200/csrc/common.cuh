@@ -158,6 +158,9 @@ struct Handle {
   // tuning (env overridable)
   int spmv_blocks = 0, tri_blocks_per_sm = 0, blas_blocks = NUM_SMS * 8;
   int grid_ilu = 0, grid_tri_l = 0, grid_tri_u = 0;   // co-resident grid sizes (occupancy x SMs)
+  // B200_PIN_VALUES=1: the caller's value array is page-locked (cudaHostRegister) the first time it is seen, so the
+  // once-per-nonlinear-iteration upload runs at PCIe speed instead of through a staging copy
+  int pin_values = 0; const void *pinned_ptr = nullptr; size_t pinned_bytes = 0;
   // hook-1 state
   const double *hook_vals_ptr = nullptr; double hook_checksum = 0;
 };
