@@ -320,6 +320,15 @@ def run_b200(args):
             "true_residual": res_true, "clocks": clk,
         }
         if elas:
+            # ndeg = 3: the SpMV reads one column index per group of 3 entries (as the reference's ndeg loop does), so it moves
+            # fewer bytes than the CRS-equivalent figure `achieved` is defined on: say so, with the real figure beside it
+            real = (8.0 + 4.0 / 3.0) * nnz + 20.0 * n + 4
+            for key in ("spmv",):
+                roof[key]["real_bytes_estimate"] = real
+                roof[key]["achieved_real"] = real / (spmv_ms_max * 1e-3) / 1e9
+                roof[key]["frac_real"] = roof[key]["achieved_real"] / peak
+                roof[key]["note"] = ("achieved/frac use the CRS-equivalent algorithmic bytes (12 nnz + 20 n); the block-column kernel reads one index per 3 entries, "
+                                     "so the bytes it really moves are ~(8 + 4/3) nnz + 20 n: achieved_real / frac_real")
             out.pop("roofline_lu"); out["roofline"] = roof["spmv"]; out.pop("factor_ms"); out.pop("iters_per_s_incl_factor")
             out["true_residual_note"] = "not converged by design (fixed number of rounds)"
         if world == 1 and not args.no_cpu_baseline and not elas:

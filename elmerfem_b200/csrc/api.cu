@@ -98,7 +98,17 @@ void install_structure(Handle &h, int n, long long nnz, std::vector<int> &&rows0
   int nacc = 1;
   if (ndeg == 2) nacc = 2; else if (ndeg == 3 || ndeg == 6) nacc = 3; else if (ndeg == 4 || ndeg == 8) nacc = 4; else if (ndeg == 5 || ndeg == 10) nacc = 5;
   if (nacc > 1) for (int i = 0; i < n; ++i) if ((rows0[i + 1] - rows0[i]) % nacc) { nacc = 1; break; }
-  h.n = n; h.nnz = nnz; h.ndeg = ndeg; h.nacc = nacc;
+  // The ndeg variants of CRS_MatrixVectorProd read ONE column index per group of ndeg entries and address u(k), u(k+1), ...
+  // (CRSMatrix.F90:4794-4856): when the groups really are runs of consecutive columns the kernel does the same and skips
+  // the other index loads (a third of the index traffic for 3 dofs per node).
+  bool blocked = nacc > 1;
+  if (blocked) {
+#pragma omp parallel for reduction(&& : blocked)
+    for (int i = 0; i < n; ++i)
+      for (int p = rows0[i]; p < rows0[i + 1]; p += nacc)
+        for (int k = 1; k < nacc; ++k) blocked = blocked && (cols0[p + k] == cols0[p] + k);
+  }
+  h.n = n; h.nnz = nnz; h.ndeg = ndeg; h.nacc = nacc; h.nacc_blocked = blocked;
   h.h_rows = std::move(rows0); h.h_cols = std::move(cols0); h.h_diag = std::move(diag0);
   h.d_rows.ensure((size_t)n + 1); h.d_cols.ensure(nnz); h.d_diag.ensure(n);
   B200_CUDA(cudaMemcpyAsync(h.d_rows.p, h.h_rows.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, h.stream));

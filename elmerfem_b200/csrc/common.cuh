@@ -114,7 +114,7 @@ struct Handle {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev_end = nullptr, evf0 = nullptr, evf1 = nullptr;
   // structure
-  int n = 0; long long nnz = 0; int ndeg = 1; int index_base = 1; int nacc = 1;
+  int n = 0; long long nnz = 0; int ndeg = 1; int index_base = 1; int nacc = 1; bool nacc_blocked = false;
   std::vector<int> h_rows, h_cols, h_diag;       // 0-based host copies (level analysis)
   DBuf<int> d_rows_in, d_cols_in, d_diag_in;     // bit-exact mirrors of the caller's arrays
   DBuf<int> d_rows, d_cols, d_diag;              // 0-based working copies

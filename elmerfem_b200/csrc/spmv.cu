@@ -16,10 +16,12 @@
 
 namespace b200 {
 
-template <int NACC, int EPI>
+// BLK: every group of NACC entries is a run of consecutive columns (checked at set_structure): one index load per group,
+// operands at c, c+1, ..., as the reference's ndeg loops address them; two groups in flight.
+template <int NACC, int EPI, bool BLK>
 __global__ void __launch_bounds__(256) k_spmv_sell(SellView A, int n, SpmvArgs a) {
   if (a.ctrl && a.ctrl->done) return;
-  constexpr int U = (NACC == 1) ? 4 : ((NACC == 2) ? 4 : NACC);   // loads in flight per thread
+  constexpr int U = (NACC == 1) ? 4 : ((NACC == 2) ? 4 : (BLK ? 2 * NACC : NACC));   // loads in flight per thread
   constexpr int NV = (EPI == EPI_NONE) ? 1 : ((EPI == EPI_DOT2) ? 2 : 1);
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -43,16 +45,21 @@ __global__ void __launch_bounds__(256) k_spmv_sell(SellView A, int n, SpmvArgs a
     for (; j + U <= W; j += U) {
       int c[U]; double v[U], xv[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) { c[k] = ld_stream(cp + (j + k) * 32); v[k] = ld_stream(vp + (j + k) * 32); }
+      for (int k = 0; k < U; ++k) {
+        if (!BLK || k % NACC == 0) c[k] = ld_stream(cp + (j + k) * 32); else c[k] = c[k - k % NACC] + k % NACC;
+        v[k] = ld_stream(vp + (j + k) * 32);
+      }
 #pragma unroll
       for (int k = 0; k < U; ++k) xv[k] = __ldg(x + c[k]);
 #pragma unroll
       for (int k = 0; k < U; ++k) if (j + k < len) acc[k % NACC] = nfma(acc[k % NACC], xv[k], v[k]);
     }
     for (; j < W; j += NACC) {            // tail: W is a multiple of NACC (checked at set_structure)
+      int c0 = 0;
 #pragma unroll
       for (int k = 0; k < NACC; ++k) {
-        int c = ld_stream(cp + (j + k) * 32); double v = ld_stream(vp + (j + k) * 32);
+        int c = (!BLK || k == 0) ? ld_stream(cp + (j + k) * 32) : c0 + k; double v = ld_stream(vp + (j + k) * 32);
+        if (k == 0) c0 = c;
         double xv = __ldg(x + c);
         if (j + k < len) acc[k] = nfma(acc[k], xv, v);
       }
@@ -91,17 +98,22 @@ __global__ void __launch_bounds__(256) k_spmv_sell(SellView A, int n, SpmvArgs a
   }
 }
 
-template <int NACC>
-static void launch_epi(Handle &h, int blocks, const SellView &A, const SpmvArgs &a, int epi) {
+template <int NACC, bool BLK>
+static void launch_epi2(Handle &h, int blocks, const SellView &A, const SpmvArgs &a, int epi) {
   cudaStream_t st = h.stream;
   switch (epi) {
-    case EPI_NONE:   k_spmv_sell<NACC, EPI_NONE><<<blocks, 256, 0, st>>>(A, h.n, a); break;
-    case EPI_DOT1:   k_spmv_sell<NACC, EPI_DOT1><<<blocks, 256, 0, st>>>(A, h.n, a); break;
-    case EPI_DOT2:   k_spmv_sell<NACC, EPI_DOT2><<<blocks, 256, 0, st>>>(A, h.n, a); break;
-    case EPI_RESID:  k_spmv_sell<NACC, EPI_RESID><<<blocks, 256, 0, st>>>(A, h.n, a); break;
-    case EPI_BMINUS: k_spmv_sell<NACC, EPI_BMINUS><<<blocks, 256, 0, st>>>(A, h.n, a); break;
+    case EPI_NONE:   k_spmv_sell<NACC, EPI_NONE, BLK><<<blocks, 256, 0, st>>>(A, h.n, a); break;
+    case EPI_DOT1:   k_spmv_sell<NACC, EPI_DOT1, BLK><<<blocks, 256, 0, st>>>(A, h.n, a); break;
+    case EPI_DOT2:   k_spmv_sell<NACC, EPI_DOT2, BLK><<<blocks, 256, 0, st>>>(A, h.n, a); break;
+    case EPI_RESID:  k_spmv_sell<NACC, EPI_RESID, BLK><<<blocks, 256, 0, st>>>(A, h.n, a); break;
+    case EPI_BMINUS: k_spmv_sell<NACC, EPI_BMINUS, BLK><<<blocks, 256, 0, st>>>(A, h.n, a); break;
     default: throw Error("spmv: bad epilogue");
   }
+}
+template <int NACC>
+static void launch_epi(Handle &h, int blocks, const SellView &A, const SpmvArgs &a, int epi) {
+  if (NACC > 1 && h.nacc_blocked) launch_epi2<NACC, true>(h, blocks, A, a, epi);
+  else launch_epi2<NACC, false>(h, blocks, A, a, epi);
 }
 
 void spmv_launch(Handle &h, SpmvArgs a, int epi) {
