@@ -69,24 +69,45 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int nslots, const int *__re
       }
     }
     __syncwarp();
-    // 3624-3637: IKJ elimination, lower entries in column order
-    for (int m = 0; m < nlow; ++m) {
-      double skm = vrow[m];
-      if (skm == 0.0) continue;                                   // 3626
-      const int k = crow[m];
-      const int kd = diag[k];
-      const double ukk = __ldcg(LU + kd);
-      if (fabs(ukk) > AEPS) skm = __ddiv_rn(skm, ukk);           // 3628-3629
-      __syncwarp();
-      if (lane == 0) vrow[m] = skm;
-      const int ke = rows[k + 1];
-      for (int l = kd + 1 + lane; l < ke; l += 32) {              // 3631-3636
-        const int j = cols[l];
-        int lo = m + 1, hi = len;                                 // columns > k live right of position m
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (crow[mid] < j) lo = mid + 1; else hi = mid; }
-        if (lo < len && crow[lo] == j) vrow[lo] = nfms(vrow[lo], skm, __ldcg(LU + l));
+    // 3624-3637: IKJ elimination, lower entries in column order.  The pivot rows are complete, so everything the
+    // elimination reads from them (the pivots u_kk and the upper parts of the rows k) is fetched for a
+    // batch of MB lower entries at once -- one L2 round trip per batch instead of two dependent ones per entry
+    // (35 ms -> the factorisation of C2 was 13 x 2 round trips per row) -- and the arithmetic then runs from registers
+    // in the reference's order.
+    constexpr int MB = 8;
+    for (int m0 = 0; m0 < nlow; m0 += MB) {
+      int mkd = 0, mke = 0; double mukk = 0.0;
+      if (lane < MB && m0 + lane < nlow) { const int k = crow[m0 + lane]; mkd = diag[k]; mke = rows[k + 1]; mukk = __ldcg(LU + mkd); }
+      int pj0[MB], pj1[MB]; double pv0[MB], pv1[MB];
+#pragma unroll
+      for (int t = 0; t < MB; ++t) {
+        const int kd = __shfl_sync(0xffffffffu, mkd, t), ke = __shfl_sync(0xffffffffu, mke, t);
+        const int l0 = kd + 1 + lane, l1 = l0 + 32;
+        const bool in0 = (m0 + t < nlow) && l0 < ke, in1 = (m0 + t < nlow) && l1 < ke;
+        pj0[t] = in0 ? cols[l0] : -1; pv0[t] = in0 ? __ldcg(LU + l0) : 0.0;
+        pj1[t] = in1 ? cols[l1] : -1; pv1[t] = in1 ? __ldcg(LU + l1) : 0.0;
       }
-      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < MB; ++t) {
+        const int m = m0 + t;
+        if (m >= nlow) break;
+        double skm = vrow[m];
+        const double ukk = __shfl_sync(0xffffffffu, mukk, t);
+        const int kd = __shfl_sync(0xffffffffu, mkd, t), ke = __shfl_sync(0xffffffffu, mke, t);
+        if (skm == 0.0) continue;                                   // 3626
+        if (fabs(ukk) > AEPS) skm = __ddiv_rn(skm, ukk);           // 3628-3629
+        __syncwarp();
+        if (lane == 0) vrow[m] = skm;
+        auto update = [&](int j, double ukj) {                      // 3631-3636
+          int lo = m + 1, hi = len;                                 // columns > k live right of position m
+          while (lo < hi) { int mid = (lo + hi) >> 1; if (crow[mid] < j) lo = mid + 1; else hi = mid; }
+          if (lo < len && crow[lo] == j) vrow[lo] = nfms(vrow[lo], skm, ukj);
+        };
+        if (pj0[t] >= 0) update(pj0[t], pv0[t]);
+        if (pj1[t] >= 0) update(pj1[t], pv1[t]);
+        for (int l = kd + 1 + 64 + lane; l < ke; l += 32) update(cols[l], __ldcg(LU + l));   // pivot rows wider than 64 upper entries
+        __syncwarp();
+      }
     }
     if (staged) for (int t = lane; t < len; t += 32) __stcg(LU + rs + t, s_val[wib][t]);   // 3643-3649
     __threadfence();
