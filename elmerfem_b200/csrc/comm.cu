@@ -20,6 +20,7 @@
 #include "../../include/elmer_b200.h"
 #include <nccl.h>      // types and prototypes only: the library is bound at run time (see NcclApi)
 #include <dlfcn.h>
+#include <time.h>
 #include <algorithm>
 #include <unordered_map>
 
@@ -177,6 +178,18 @@ static void peer_layout(int np, int me, int r, const int *cnt, int &qprime, int 
 
 static void p2p_release(Handle &h, Halo &H) {
   if (h.stream) cudaStreamSynchronize(h.stream);
+  // Neighbours write into this rank's area until they have acknowledged its last exchange (the ack is their last
+  // store here): wait for those acks (bounded) before the memory goes away.
+  if (H.p2p && H.seq > 0 && H.nneigh > 0) {
+    std::vector<unsigned long long> ack(H.nneigh);
+    for (int tries = 0; tries < 2000; ++tries) {
+      if (cudaMemcpy(ack.data(), H.ack, ack.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); break; }
+      bool all = true;
+      for (unsigned long long a : ack) all = all && a >= H.seq;
+      if (all) break;
+      struct timespec ts = {0, 1000000}; nanosleep(&ts, nullptr);
+    }
+  }
   for (void *b : H.peer_base) if (b) cudaIpcCloseMemHandle(b);
   H.peer_base.clear();
   if (H.shm) cudaFree(H.shm);

@@ -858,11 +858,11 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
     const bool true_resid = (stopc == 0 || stopc == 1);
     if (method == B200_M_CG) { h.st_matvec = 1 + (true_resid ? 2 : 1) * performed; h.st_pcond = performed; }
     else { h.st_matvec = 1 + (true_resid ? 3 : 2) * performed; h.st_pcond = 2 * performed; }
-    if (h.h_ctrl->spin_timeout) { IPAR(30) = HUTI_HALTED; fprintf(stderr, "[elmer_b200] triangular solve dependency wait timed out\n"); }
+    if (h.h_ctrl->spin_timeout) { IPAR(30) = HUTI_HALTED; fprintf(stderr, "[elmer_b200] a device-side dependency wait timed out (triangular solve wavefront or halo exchange flags)\n"); }
   } else {
     read_ctrl(h);
     IPAR(30) = hr.info; IPAR(31) = hr.iters; h.st_resid = hr.residual;
-    if (h.h_ctrl->spin_timeout) { IPAR(30) = HUTI_HALTED; fprintf(stderr, "[elmer_b200] triangular solve dependency wait timed out\n"); }
+    if (h.h_ctrl->spin_timeout) { IPAR(30) = HUTI_HALTED; fprintf(stderr, "[elmer_b200] a device-side dependency wait timed out (triangular solve wavefront or halo exchange flags)\n"); }
   }
   dpar[9] = h.st_resid;
   h.st_iters = IPAR(31);

@@ -55,3 +55,20 @@ def test_fails_loudly_without_gpu(b200):
 def _which(x):
     import shutil
     return shutil.which(x)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs on the host alone (oracle + workload generator) and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--ne", "16", "--steps", "1", "--warmup", "3",
+                          "--ref-budget", "2"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "Mdof*iterations/s" and d["value"] > 0
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
