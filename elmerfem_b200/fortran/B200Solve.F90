@@ -46,6 +46,10 @@ MODULE B200Interface
       REAL(C_DOUBLE) :: vals(*)
       TYPE(C_PTR), VALUE :: prec_vals
     END FUNCTION
+    ! int b200_scale_system(void **handle);   ScaleLinearSystemDiagonal on the device copy (after b200_set_values)
+    INTEGER(C_INT) FUNCTION b200_scale_system(handle) BIND(C, NAME="b200_scale_system")
+      IMPORT; INTEGER(C_INTPTR_T) :: handle
+    END FUNCTION
     INTEGER(C_INT) FUNCTION b200_factorize(handle) BIND(C, NAME="b200_factorize")
       IMPORT; INTEGER(C_INTPTR_T) :: handle
     END FUNCTION
@@ -127,7 +131,7 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   TYPE(ValueList_t), POINTER :: Params
   CHARACTER(LEN=4096) :: sif
   CHARACTER(:), ALLOCATABLE :: str
-  LOGICAL :: Found, ScaleSystem, L
+  LOGICAL :: Found, ScaleSystem, DeviceScaling, L
   INTEGER :: rc, info(2), nnz, ival, base, ndeg
   REAL(KIND=dp) :: rval
   INTEGER(C_INTPTR_T) :: handle
@@ -156,6 +160,7 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   CALL AddInt( 'Linear System Min Iterations' )
   CALL AddInt( 'Linear System Residual Output' )
   CALL AddInt( 'Linear System GCR Restart' )
+  CALL AddInt( 'Linear System GMRES Restart' )
   CALL AddInt( 'BiCGstabl polynomial degree' )
   CALL AddInt( 'IDRS parameter' )
   CALL AddInt( 'Linear System Precondition Recompute' )
@@ -179,7 +184,12 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   ScaleSystem = ListGetLogical( Params, 'Linear System Scaling', Found )
   IF ( .NOT. Found ) ScaleSystem = .TRUE.
   IF ( ALL( b(1:n) == 0.0_dp ) ) RETURN        ! zero rhs shortcut stays with Elmer (14717-14736)
-  IF ( ScaleSystem ) CALL ScaleLinearSystem( Solver, A, b, x )
+  ! 'B200 Device Scaling = True': the device copy is scaled by b200_scale_system (bit-identical values), b and x are
+  ! scaled / back-scaled inside b200_itersolver, and the host matrix is never touched (no ScaleLinearSystem /
+  ! BackScaleLinearSystem passes over A % Values).  Not with a separate preconditioning matrix.
+  DeviceScaling = ScaleSystem .AND. ListGetLogical( Params, 'B200 Device Scaling', Found ) .AND. &
+                  .NOT. ASSOCIATED( A % PrecValues )
+  IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL ScaleLinearSystem( Solver, A, b, x )
 
   ! ---- device mirror: structure once per matrix, values every call (once per nonlinear iteration)
   handle = A % SpMV
@@ -200,13 +210,17 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   END IF
   rc = b200_set_values( handle, A % Values, prec )
   IF ( rc /= 0 ) CALL Fatal( Caller, 'b200_set_values failed' )
+  IF ( DeviceScaling ) THEN
+    rc = b200_scale_system( handle )
+    IF ( rc /= 0 ) CALL Fatal( Caller, 'b200_scale_system failed' )
+  END IF
 
   ! ---- IterSolver on the device
   rc = b200_itersolver( handle, b, x, TRIM(sif)//C_NULL_CHAR, A % SolveCount, info )
 
   IF ( rc == B200_DECLINED ) THEN
     ! undo the scaling and let Elmer's own path run
-    IF ( ScaleSystem ) CALL BackScaleLinearSystem( Solver, A, b, x )
+    IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL BackScaleLinearSystem( Solver, A, b, x )
     RETURN
   END IF
   IF ( rc /= 0 ) CALL Fatal( Caller, 'b200_itersolver failed' )
@@ -228,7 +242,7 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   CALL Info( Caller, Message, Level=5 )
 
   ! ---- what SolveLinearSystem does after IterSolver (14925-14927, 14965)
-  IF ( ScaleSystem ) CALL BackScaleLinearSystem( Solver, A, b, x )
+  IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL BackScaleLinearSystem( Solver, A, b, x )
   CALL ComputeChange( Solver, .FALSE., n, x )
   Norm = Solver % Variable % Norm
   stat = 1
