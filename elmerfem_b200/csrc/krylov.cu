@@ -680,6 +680,109 @@ static HostResult run_gmres(Handle &h, const double *b, double *x, int pc, int M
   return res;
 }
 
+// fhutiter/src/huti_cgs.F90:283-470 huti_dcgssolv (right-oriented preconditioning; the dummy left preconditioner is a copy).
+static HostResult run_cgs(Handle &h, const double *b, double *x, int pc, int MaxIt, double Tol, double MaxTol, int stopc) {
+  HostResult res;
+  Solver S(h, pc, 7);
+  const int n = S.n;
+  double *RTLD = S.vec[0], *P = S.vec[1], *Q = S.vec[2], *U = S.vec[3], *T1V = S.vec[4], *T2V = S.vec[5], *R = S.vec[6];
+  const double rhsnorm = (stopc == 1 || stopc == 3) ? S.norm(b) : 1.0;
+  S.matvec(x, R); S.lin(b, 1.0, R, -1.0);                          // R = B - A X
+  copy_vec(h, n, R, RTLD);
+  double rho = 0, oldrho = 0, alpha = 0, beta = 0, residual = 0;
+  int iter_count = 1;
+  for (;;) {
+    rho = S.dot(RTLD, R);
+    if (rho == 0) { res.info = 25; break; }                        // HUTI_CGS_RHO
+    if (iter_count == 1) { copy_vec(h, n, R, U); copy_vec(h, n, U, P); }
+    else {
+      beta = rho / oldrho;
+      copy_vec(h, n, R, U); S.lin(Q, beta, U, 1.0);                // U = R + beta Q
+      S.lin(U, 1.0, P, beta * beta); S.lin(Q, beta, P, 1.0);       // P = U + beta Q + beta^2 P
+    }
+    double *t1 = S.precond(T1V, P);                                // pcondl = copy, pcondr = M^-1
+    S.matvec(t1, T2V);
+    alpha = rho / S.dot(RTLD, T2V);
+    copy_vec(h, n, U, Q); S.lin(T2V, -alpha, Q, 1.0);              // Q = U - alpha T2V
+    S.lin(Q, 1.0, U, 1.0);                                         // U := U + Q  (T2V = U + Q; pcondl(U, T2V) copies it into U)
+    t1 = S.precond(T1V, U);
+    S.lin(t1, alpha, x, 1.0);
+    S.matvec(t1, T2V);
+    S.lin(T2V, -alpha, R, 1.0);
+    if (stopc == 2 || stopc == 3) residual = S.norm(R) / rhsnorm;
+    else { S.matvec(x, T1V); S.lin(b, -1.0, T1V, 1.0); residual = S.norm(T1V) / rhsnorm; }
+    if (residual < Tol) { res.info = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > MaxTol) { res.info = HUTI_DIVERGENCE; break; }
+    oldrho = rho;
+    iter_count = iter_count + 1;
+    if (iter_count > MaxIt) { res.info = HUTI_MAXITER; break; }
+  }
+  res.iters = iter_count; res.residual = residual;
+  return res;
+}
+
+// fhutiter/src/huti_tfqmr.F90:455-803 huti_dtfqmrsolv; preconditioner in the left slot as IterSolver passes it (IterSolve.F90:509-525).
+static HostResult run_tfqmr(Handle &h, const double *b, double *x, int pc, int MaxIt, double Tol, double MaxTol, int stopc) {
+  HostResult res;
+  Solver S(h, pc, 10);
+  const int n = S.n;
+  double *V = S.vec[0], *Y = S.vec[1], *YNEW = S.vec[2], *RTLD = S.vec[3], *T1V = S.vec[4], *T2V = S.vec[5], *W = S.vec[6], *D = S.vec[7],
+         *R = S.vec[8], *TRV = S.vec[9];
+  const double rhsnorm = (stopc == 1 || stopc == 3) ? S.norm(b) : 1.0;
+  double rho = 0, oldrho = 0, eta = 0, tau = 0, gamma = 0, oldgamma = 0, alpha = 0, beta = 0, c = 0, residual = 0;
+  int iter_count = 1;
+  // dst = M^-1 A src (through tmp): pcondr is the dummy, pcondl the preconditioner
+  auto apply = [&](const double *src, double *tmp, double *dst) { S.matvec(src, tmp); double *r = S.precond(dst, tmp); if (r != dst) copy_vec(h, n, r, dst); };
+  auto check = [&]() {
+    if (stopc == 2 || stopc == 3) { S.matvec(x, R); S.lin(b, -1.0, R, 1.0); residual = S.norm(S.precond(TRV, R)) / rhsnorm; }
+    else { S.matvec(x, R); copy_vec(h, n, R, TRV); S.lin(b, -1.0, TRV, 1.0); residual = S.norm(S.precond(R, TRV)) / rhsnorm; }
+  };
+  auto half = [&](const double *yv, const double *av) {
+    S.lin(av, -alpha, W, 1.0);
+    gamma = S.norm(W) / tau;
+    c = 1 / sqrt(1 + gamma * gamma);
+    tau = tau * gamma * c;
+    S.lin(yv, 1.0, D, (oldgamma * oldgamma * eta) / alpha);        // D = y + f D
+    eta = c * c * alpha;
+    S.lin(D, eta, x, 1.0);
+    oldgamma = gamma;
+  };
+  S.matvec(x, R); copy_vec(h, n, b, D); S.lin(R, -1.0, D, 1.0);    // D = B - A X
+  { double *r = S.precond(R, D); if (r != R) copy_vec(h, n, r, R); }
+  copy_vec(h, n, R, Y); copy_vec(h, n, R, W);
+  apply(Y, D, V);
+  copy_vec(h, n, V, T2V);
+  fill_vec(h, n, D, 0.0);
+  tau = S.norm(R);
+  copy_vec(h, n, R, RTLD);
+  oldrho = S.dot(RTLD, R);
+  if (oldrho == 0) res.info = 30;                                    // HUTI_TFQMR_RHO
+  else for (;;) {
+    alpha = oldrho / S.dot(RTLD, V);
+    copy_vec(h, n, Y, YNEW); S.lin(V, -alpha, YNEW, 1.0);
+    half(Y, T2V);
+    check();
+    if (residual < Tol) { res.info = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > MaxTol) { res.info = HUTI_DIVERGENCE; break; }
+    apply(YNEW, R, T1V);
+    half(YNEW, T1V);
+    check();
+    if (residual < Tol) { res.info = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > MaxTol) { res.info = HUTI_DIVERGENCE; break; }
+    rho = S.dot(RTLD, W);
+    beta = rho / oldrho;
+    S.lin(W, 1.0, YNEW, beta);                                       // YNEW = W + beta YNEW
+    apply(YNEW, R, T2V);
+    S.lin(T2V, 1.0, V, beta * beta); S.lin(T1V, beta, V, 1.0);      // V = T2V + beta T1V + beta^2 V
+    copy_vec(h, n, YNEW, Y);
+    oldrho = rho;
+    iter_count = iter_count + 1;
+    if (iter_count > MaxIt) { res.info = HUTI_MAXITER; break; }
+  }
+  res.iters = iter_count; res.residual = residual;
+  return res;
+}
+
 // counter-based uniform [0,1) generator for the IDR(s) shadow space when the caller passes none
 __global__ void k_shadow_space(long long n, double *P, unsigned long long seed) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -821,7 +924,7 @@ static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int Ma
 // parsing and the error mapping (fem/src/IterSolve.F90:470-471, 913, 964-1005).
 void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *dpar, int method, int pc, const double *d_P) {
   B200_REQUIRE(h.have_vals, "b200_solve before b200_set_values");
-  B200_REQUIRE(method >= 1 && method <= 6, "unknown iterative method");
+  B200_REQUIRE(method >= 1 && method <= 8, "unknown iterative method");
   B200_REQUIRE(pc >= 0 && pc <= 2, "unknown preconditioner");
   const int n = h.n;
   cudaStream_t st = h.stream;
@@ -844,6 +947,8 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
     case B200_M_GCR: hr = run_gcr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(17), IPAR(11)); break;
     case B200_M_IDRS: hr = run_idrs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(18), IPAR(28) == 1, d_P, h.rank); break;
     case B200_M_GMRES: hr = run_gmres(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(15), stopc); break;
+    case B200_M_CGS: hr = run_cgs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
+    case B200_M_TFQMR: hr = run_tfqmr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
     default: B200_REQUIRE(false, "unknown iterative method code");
   }
   B200_CUDA(cudaEventRecord(h.ev_end, st));

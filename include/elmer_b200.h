@@ -55,6 +55,8 @@ extern "C" {
 #define B200_METHOD_BICGSTABL 3   /* itermethod_bicgstabl*/
 #define B200_METHOD_GCR       4   /* itermethod_gcr      */
 #define B200_METHOD_IDRS      5   /* itermethod_idrs     */
+#define B200_METHOD_CGS       7   /* huti_dcgssolv (right-oriented preconditioning)   */
+#define B200_METHOD_TFQMR     8   /* huti_dtfqmrsolv (preconditioner in the LEFT slot) */
 #define B200_METHOD_GMRES     6   /* huti_dgmressolv; restart in ipar(15); preconditioner in the LEFT slot as IterSolver does (IterSolve.F90:509-525) */
 
 /* Linear System Preconditioning (IterSolve.F90:529-547) */

@@ -581,6 +581,126 @@ void huti_dgmressolv(Ops &op, int ndim, double *X, const double *B, int *ipar, d
 #undef H_
 }
 
+// fhutiter/src/huti_cgs.F90:283-470 huti_dcgssolv.  work(n,7) = RTLD,P,Q,U,T1V,T2V,R.  Right-oriented preconditioning.
+void huti_dcgssolv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar, double *work) {
+  const size_t N = (size_t)ndim;
+  double *RTLD = work, *P = work + N, *Q = work + 2 * N, *U = work + 3 * N, *T1V = work + 4 * N, *T2V = work + 5 * N, *R = work + 6 * N;
+  double rho = 0, oldrho = 0, alpha = 0, beta = 0, residual = 0, rhsnorm = 1.0;
+  int iter_count = 1;
+  if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB || HUTI_STOPC == HUTI_PRESID_SCALED_BYB) rhsnorm = op.norm(ndim, B);
+  op.matvec(X, R);
+  for (int i = 0; i < ndim; ++i) { R[i] = B[i] - R[i]; RTLD[i] = R[i]; }
+  for (;;) {
+    rho = op.dot(ndim, RTLD, R);
+    if (rho == 0) { HUTI_INFO = 25; break; }                        // HUTI_CGS_RHO
+    if (iter_count == 1) {
+      for (int i = 0; i < ndim; ++i) { U[i] = R[i]; P[i] = U[i]; }
+    } else {
+      beta = rho / oldrho;
+      for (int i = 0; i < ndim; ++i) U[i] = R[i] + beta * Q[i];
+      for (int i = 0; i < ndim; ++i) P[i] = U[i] + beta * Q[i] + beta * beta * P[i];
+    }
+    op.pcondl(T2V, P); op.pcondr(T1V, T2V);
+    op.matvec(T1V, T2V);
+    alpha = rho / op.dot(ndim, RTLD, T2V);
+    for (int i = 0; i < ndim; ++i) Q[i] = U[i] - alpha * T2V[i];
+    for (int i = 0; i < ndim; ++i) T2V[i] = U[i] + Q[i];
+    op.pcondl(U, T2V); op.pcondr(T1V, U);
+    for (int i = 0; i < ndim; ++i) X[i] = X[i] + alpha * T1V[i];
+    op.matvec(T1V, T2V);
+    for (int i = 0; i < ndim; ++i) R[i] = R[i] - alpha * T2V[i];
+    if (HUTI_STOPC == HUTI_PSEUDORESIDUAL) residual = op.norm(ndim, R);
+    else if (HUTI_STOPC == HUTI_PRESID_SCALED_BYB) residual = op.norm(ndim, R) / rhsnorm;
+    else {
+      op.matvec(X, T1V);
+      for (int i = 0; i < ndim; ++i) T1V[i] = T1V[i] - B[i];
+      residual = op.norm(ndim, T1V);
+      if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB) residual /= rhsnorm;
+    }
+    if (residual < HUTI_TOLERANCE) { HUTI_INFO = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > HUTI_MAXTOLERANCE) { HUTI_INFO = HUTI_DIVERGENCE; break; }
+    oldrho = rho;
+    iter_count = iter_count + 1;
+    if (iter_count > HUTI_MAXIT) { HUTI_INFO = HUTI_MAXITER; break; }
+  }
+  HUTI_ITERS = iter_count;
+  dpar[9] = residual;
+}
+
+// fhutiter/src/huti_tfqmr.F90:455-803 huti_dtfqmrsolv.  work(n,10) = V,Y,YNEW,RTLD,T1V,T2V,W,D,R,TRV.  Elmer puts the
+// preconditioner in the left slot (IterSolve.F90:509-525).  Two half steps per iteration, each with its own stopping test.
+void huti_dtfqmrsolv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar, double *work) {
+  const size_t N = (size_t)ndim;
+  double *V = work, *Y = work + N, *YNEW = work + 2 * N, *RTLD = work + 3 * N, *T1V = work + 4 * N, *T2V = work + 5 * N, *W = work + 6 * N,
+         *D = work + 7 * N, *R = work + 8 * N, *TRV = work + 9 * N;
+  double rho = 0, oldrho = 0, eta = 0, tau = 0, gamma = 0, oldgamma = 0, alpha = 0, beta = 0, c = 0, residual = 0, rhsnorm = 1.0;
+  int iter_count = 1;
+  if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB || HUTI_STOPC == HUTI_PRESID_SCALED_BYB) rhsnorm = op.norm(ndim, B);
+  auto check = [&]() {                                              // the stopping test of either half step
+    if (HUTI_STOPC == HUTI_PSEUDORESIDUAL || HUTI_STOPC == HUTI_PRESID_SCALED_BYB) {
+      op.matvec(X, R);
+      for (int i = 0; i < ndim; ++i) R[i] = R[i] - B[i];
+      op.pcondl(TRV, R);
+      residual = op.norm(ndim, TRV);
+      if (HUTI_STOPC == HUTI_PRESID_SCALED_BYB) residual /= rhsnorm;
+    } else {
+      op.pcondr(TRV, X);
+      op.matvec(TRV, R);
+      for (int i = 0; i < ndim; ++i) TRV[i] = R[i] - B[i];
+      op.pcondl(R, TRV);
+      residual = op.norm(ndim, R);
+      if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB) residual /= rhsnorm;
+    }
+  };
+  auto half = [&](const double *yv, const double *av) {            // W -= alpha*av ; rotations ; D, X updates
+    for (int i = 0; i < ndim; ++i) W[i] = W[i] - alpha * av[i];
+    gamma = op.norm(ndim, W) / tau;
+    c = 1 / std::sqrt(1 + gamma * gamma);
+    tau = tau * gamma * c;
+    const double f = (oldgamma * oldgamma * eta) / alpha;
+    for (int i = 0; i < ndim; ++i) D[i] = yv[i] + f * D[i];
+    eta = c * c * alpha;
+    for (int i = 0; i < ndim; ++i) X[i] = X[i] + eta * D[i];
+    oldgamma = gamma;
+  };
+  op.pcondr(D, X); op.matvec(D, R);
+  for (int i = 0; i < ndim; ++i) D[i] = B[i] - R[i];
+  op.pcondl(R, D);
+  for (int i = 0; i < ndim; ++i) { Y[i] = R[i]; W[i] = R[i]; }
+  op.pcondr(V, Y); op.matvec(V, D); op.pcondl(V, D);
+  for (int i = 0; i < ndim; ++i) { T2V[i] = V[i]; D[i] = 0; }
+  tau = op.norm(ndim, R);
+  for (int i = 0; i < ndim; ++i) RTLD[i] = R[i];
+  oldrho = op.dot(ndim, RTLD, R);
+  if (oldrho == 0) { HUTI_INFO = 30; }                               // HUTI_TFQMR_RHO
+  else for (;;) {
+    alpha = oldrho / op.dot(ndim, RTLD, V);
+    for (int i = 0; i < ndim; ++i) YNEW[i] = Y[i] - alpha * V[i];
+    half(Y, T2V);
+    check();
+    if (residual < HUTI_TOLERANCE) { HUTI_INFO = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > HUTI_MAXTOLERANCE) { HUTI_INFO = HUTI_DIVERGENCE; break; }
+    op.pcondr(T1V, YNEW); op.matvec(T1V, R); op.pcondl(T1V, R);
+    half(YNEW, T1V);
+    check();
+    if (residual < HUTI_TOLERANCE) { HUTI_INFO = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > HUTI_MAXTOLERANCE) { HUTI_INFO = HUTI_DIVERGENCE; break; }
+    rho = op.dot(ndim, RTLD, W);
+    beta = rho / oldrho;
+    for (int i = 0; i < ndim; ++i) YNEW[i] = W[i] + beta * YNEW[i];
+    op.pcondr(T2V, YNEW); op.matvec(T2V, R); op.pcondl(T2V, R);
+    for (int i = 0; i < ndim; ++i) V[i] = T2V[i] + beta * T1V[i] + beta * beta * V[i];
+    for (int i = 0; i < ndim; ++i) Y[i] = YNEW[i];
+    oldrho = rho;
+    iter_count = iter_count + 1;
+    if (iter_count > HUTI_MAXIT) { HUTI_INFO = HUTI_MAXITER; break; }
+  }
+  op.pcondr(TRV, X);
+  for (int i = 0; i < ndim; ++i) X[i] = TRV[i];
+  HUTI_ITERS = iter_count;
+  dpar[9] = residual;
+}
+
 // fhutiter/src/huti_bicgstab.F90:279-566 huti_dbicgstabsolv.  work(n,8) = RTLD,P,T1V,V,S,T2V,T,R.
 void huti_dbicgstabsolv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar,
                         double *work) {
@@ -1210,6 +1330,13 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
     if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
     if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;
     HUTI_ITERS = iters; dpar[9] = res;
+  } else if (method == 7) {
+    std::vector<double> work((size_t)n * 7, 0.0);
+    huti_dcgssolv(op, n, x, b, ipar, dpar, work.data());
+  } else if (method == 8) {
+    op.left = true;
+    std::vector<double> work((size_t)n * 10, 0.0);
+    huti_dtfqmrsolv(op, n, x, b, ipar, dpar, work.data());
   } else if (method == 6) {
     op.left = true;
     std::vector<double> work((size_t)n * (7 + HUTI_GMRES_RESTART), 0.0);

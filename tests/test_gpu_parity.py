@@ -209,7 +209,7 @@ def test_itersolver_keywords(oracle, heat, heat_gpu):
     assert rel_l2(got["x"], ref["x"]) <= 1e-7
     declined = heat_gpu.itersolver(b, None, sif.replace("ILU0", "ILUT"), 0)
     assert declined is None
-    assert heat_gpu.itersolver(b, None, sif.replace("BiCGStab", "TFQMR"), 0) is None
+    assert heat_gpu.itersolver(b, None, sif.replace("BiCGStab", "BiCGStab2"), 0) is None
 
 
 def test_empty_and_tiny_systems(oracle, b200):
@@ -425,3 +425,36 @@ def test_device_scaling(oracle, b200):
     M.set_values(A0.vals)                                          # new values clear the scaled state
     assert np.array_equal(M.values(), A0.vals)
     M.close()
+
+
+@pytest.mark.parametrize("method", ["cgs", "tfqmr"])
+@pytest.mark.parametrize("precond", ["none", "diagonal", "ilu0"])
+def test_cgs_tfqmr_parity(oracle, b200, heat, heat_gpu, method, precond):
+    """huti_dcgssolv (fhutiter/src/huti_cgs.F90:283-470, right-oriented) and huti_dtfqmrsolv (huti_tfqmr.F90:455-803, left-oriented as
+    IterSolver calls it): iteration counts and solutions against the oracle; nonsymmetric system; keyword path."""
+    A, b = heat
+    ref = oracle.itersolve(A, b, method=method, precond=precond, tol=TOL, maxit=500)
+    got = heat_gpu.solve(b, method=method, precond=precond, tol=TOL, maxit=500)
+    assert got["info"] == ref["info"] == 1, (got["info"], ref["info"])
+    assert iters_close(got["iters"], ref["iters"]), (got["iters"], ref["iters"])
+    assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    if precond == "ilu0":
+        A3, b3 = oracle.cavity_flow(6)
+        A3 = A3.copy(); x = np.zeros(A3.n); oracle.scale_system(A3, b3, x)
+        M = b200.Matrix(); M.set_structure(A3.rows, A3.cols, A3.diag, 1, 4); M.set_values(A3.vals)
+        ref = oracle.itersolve(A3, b3, method=method, precond="ilu0", tol=TOL, maxit=300)
+        got = M.solve(b3, method=method, precond="ilu0", tol=TOL, maxit=300)
+        assert got["info"] == ref["info"], (got["info"], ref["info"])
+        if ref["info"] == 1:
+            assert iters_close(got["iters"], ref["iters"]) and rel_l2(got["x"], ref["x"]) <= 10 * TOL
+        M.close()
+        sif = """
+          Linear System Solver = Iterative
+          Linear System Iterative Method = %s
+          Linear System Preconditioning = ILU0
+          Linear System Max Iterations = 500
+          Linear System Convergence Tolerance = 1.0e-8
+        """ % method.upper()
+        ref = oracle.itersolve(A, b, method=method, precond="ilu0", tol=TOL, maxit=500)
+        got = heat_gpu.itersolver(b, None, sif, 0)
+        assert got is not None and got["info"] == 1 and iters_close(got["iters"], ref["iters"])

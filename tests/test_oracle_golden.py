@@ -207,3 +207,13 @@ def test_ilun_against_dense(oracle, order):
     v = np.random.RandomState(3).standard_normal(n)
     u = oracle.lu_precond(A, F, v)
     assert np.abs((np.tril(LU, -1) * P + np.eye(n)) @ ((np.triu(LU) * P) @ u) - v).max() <= 1e-11 * np.abs(v).max()
+
+
+@pytest.mark.parametrize("method", ["cgs", "tfqmr"])
+@pytest.mark.parametrize("precond", ["none", "diagonal", "ilu0"])
+def test_testmat_known_answer_cgs_tfqmr(oracle, testmat, method, precond):
+    """TFQMR is the method the reference's own ex1 driver used to write testmat.out (fhutiter/examples/ex1/huti-ex.F90)."""
+    A, xref = testmat
+    r = oracle.itersolve(A, np.ones(100), method=method, precond=precond, tol=1e-10, maxit=2000)
+    assert r["info"] == 1, (method, precond, r["info"])
+    assert np.abs(r["x"] - xref).max() < 1e-6
