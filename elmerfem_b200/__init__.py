@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libelmer_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "elmer_b200.h")
 
-METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8}
+METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8, "bicgstab2": 9}
 PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2}
 DECLINED = 100
 
@@ -112,7 +112,7 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
     ipar = np.zeros(50, dtype=np.int32)
     dpar = np.zeros(10, dtype=np.float64)
     ipar[2] = n
-    ipar[3] = {"cg": 4, "bicgstab": 8, "cgs": 7, "tfqmr": 10}.get(method, 1)
+    ipar[3] = {"cg": 4, "bicgstab": 8, "cgs": 7, "tfqmr": 10, "bicgstab2": 8}.get(method, 1)
     ipar[4] = residual_output
     ipar[9] = maxit
     ipar[10] = minit

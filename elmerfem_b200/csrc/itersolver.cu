@@ -94,7 +94,8 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     else if (m == "gmres") method = B200_METHOD_GMRES;
     else if (m == "cgs") method = B200_METHOD_CGS;
     else if (m == "tfqmr") method = B200_METHOD_TFQMR;
-    else if (m == "bicgstab2" || m == "sgs" || m == "jacobi" || m == "richardson")
+    else if (m == "bicgstab2") method = B200_METHOD_BICGSTAB2;
+    else if (m == "sgs" || m == "jacobi" || m == "richardson")
       throw Declined{"iterative method '" + m + "' is not on the accelerated path"};
     else method = B200_METHOD_BICGSTAB;                                  // CASE DEFAULT (313-314)
     if (P.logical("Linear System Complex") || P.logical("Linear System Pseudo Complex"))
@@ -104,6 +105,7 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     ipar[3] = internal ? 1 : (method == B200_METHOD_CG ? 4 : 8);
     if (method == B200_METHOD_CGS) ipar[3] = 7;                         // HUTI_CGS_WORKSIZE
     if (method == B200_METHOD_TFQMR) ipar[3] = 10;                      // HUTI_TFQMR_WORKSIZE
+    if (method == B200_METHOD_BICGSTAB2) ipar[3] = 8;                   // HUTI_BICGSTAB_2_WORKSIZE
     if (method == B200_METHOD_GMRES) {                                  // 346-350
       int r = P.integer("Linear System GMRES Restart", 10, &found);
       B200_REQUIRE(r >= 1, "'Linear System GMRES Restart' < 1");
@@ -141,7 +143,7 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     ipar[27] = P.logical("IDRS Smoothing") ? 1 : 0;
     // ---- preconditioner (506-577)
     // GMRES is left-preconditioned by IterSolver itself (509-525) and so is run_gmres; for CG/BiCGStab the keyword is declined
-    if (!internal && method != B200_METHOD_GMRES && method != B200_METHOD_TFQMR && P.logical("Linear System Left Preconditioning"))
+    if (!internal && method != B200_METHOD_GMRES && method != B200_METHOD_TFQMR && method != B200_METHOD_BICGSTAB2 && P.logical("Linear System Left Preconditioning"))
       throw Declined{"left-oriented preconditioning"};
     std::string pcs = P.str("Linear System Preconditioning", "none");
     int pc;

@@ -783,6 +783,64 @@ static HostResult run_tfqmr(Handle &h, const double *b, double *x, int pc, int M
   return res;
 }
 
+// fhutiter/src/huti_bicgstab_2.F90:339-578 huti_dbicgstab_2solv; preconditioner in the left slot (IterSolve.F90:509-525).
+static HostResult run_bicgstab2(Handle &h, const double *b, double *x, int pc, int MaxIt, double Tol, double MaxTol, int stopc) {
+  HostResult res;
+  Solver S_(h, pc, 8);
+  const int n = S_.n;
+  double *RTLD = S_.vec[0], *U = S_.vec[1], *T1V = S_.vec[2], *V = S_.vec[3], *S = S_.vec[4], *W = S_.vec[5], *T = S_.vec[6], *R = S_.vec[7];
+  const double rhsnorm = (stopc == 1 || stopc == 3) ? S_.norm(b) : 1.0;
+  double rho = 0, oldrho = 1, alpha = 0, beta = 0, omega1 = 0, omega2 = 1, residual = 0;
+  int iter_count = 1;
+  auto apply = [&](double *dst, const double *src) { S_.matvec(src, T1V); double *r = S_.precond(dst, T1V); if (r != dst) copy_vec(h, n, r, dst); };
+  S_.matvec(x, R); copy_vec(h, n, b, U); S_.lin(R, -1.0, U, 1.0);
+  { double *r = S_.precond(R, U); if (r != R) copy_vec(h, n, r, R); }
+  copy_vec(h, n, R, RTLD); fill_vec(h, n, U, 0.0);
+  for (;;) {
+    oldrho = -omega2 * oldrho;
+    rho = S_.dot(RTLD, R);
+    if (rho == 0) { res.info = 45; break; }                        // HUTI_BICGSTAB_2_RHO
+    beta = (rho * alpha) / oldrho; oldrho = rho;
+    S_.lin(R, 1.0, U, -beta);                                      // U = R - beta U
+    apply(V, U);
+    alpha = oldrho / S_.dot(RTLD, V);
+    S_.lin(V, -alpha, R, 1.0);
+    apply(S, R);
+    S_.lin(U, alpha, x, 1.0);
+    rho = S_.dot(RTLD, S);
+    if (rho == 0) { res.info = 45; break; }
+    beta = (rho * alpha) / oldrho; oldrho = rho;
+    S_.lin(S, 1.0, V, -beta);                                      // V = S - beta V
+    apply(W, V);
+    alpha = oldrho / S_.dot(RTLD, W);
+    S_.lin(R, 1.0, U, -beta);                                      // U = R - beta U
+    S_.lin(V, -alpha, R, 1.0);
+    S_.lin(W, -alpha, S, 1.0);
+    apply(T, S);
+    double o[5];
+    { const double *xs[5] = {R, S, S, T, R}, *ys[5] = {S, S, T, T, T}; S_.dots(5, xs, ys, o); }
+    double myy = o[1], delta = o[2], tau = o[3];
+    omega1 = o[0]; omega2 = o[4];
+    tau = tau - (delta * delta) / myy;
+    omega2 = (omega2 - (delta * omega1) / myy) / tau;
+    omega1 = (omega1 - delta * omega2) / myy;
+    { LinOp ops[3] = {LinOp{R, x, omega1, 1.0}, LinOp{S, x, omega2, 1.0}, LinOp{U, x, alpha, 1.0}}; for (auto &op : ops) axpby_batch(h, n, 1, &op); }
+    S_.lin(S, -omega1, R, 1.0); S_.lin(T, -omega2, R, 1.0);
+    if (stopc == 2 || stopc == 3) residual = S_.norm(R) / rhsnorm;
+    else {
+      S_.matvec(x, T1V); S_.lin(b, -1.0, T1V, 1.0);
+      residual = S_.norm(S_.precond(S, T1V)) / rhsnorm;
+    }
+    if (residual < Tol) { res.info = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > MaxTol) { res.info = HUTI_DIVERGENCE; break; }
+    S_.lin(V, -omega1, U, 1.0); S_.lin(W, -omega2, U, 1.0);
+    iter_count = iter_count + 1;
+    if (iter_count > MaxIt) { res.info = HUTI_MAXITER; break; }
+  }
+  res.iters = iter_count; res.residual = residual;
+  return res;
+}
+
 // counter-based uniform [0,1) generator for the IDR(s) shadow space when the caller passes none
 __global__ void k_shadow_space(long long n, double *P, unsigned long long seed) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -924,7 +982,7 @@ static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int Ma
 // parsing and the error mapping (fem/src/IterSolve.F90:470-471, 913, 964-1005).
 void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *dpar, int method, int pc, const double *d_P) {
   B200_REQUIRE(h.have_vals, "b200_solve before b200_set_values");
-  B200_REQUIRE(method >= 1 && method <= 8, "unknown iterative method");
+  B200_REQUIRE(method >= 1 && method <= 9, "unknown iterative method");
   B200_REQUIRE(pc >= 0 && pc <= 2, "unknown preconditioner");
   const int n = h.n;
   cudaStream_t st = h.stream;
@@ -937,7 +995,7 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
   B200_CUDA(cudaEventRecord(h.ev0, st));
   k_init_ctrl<<<1, 1, 0, st>>>(h.ctrl.p, h.scal.p, DPAR(1), DPAR(2), IPAR(10), IPAR(11), stopc);
   h.st_launch++;
-  if (method == B200_M_BICGSTAB || method == B200_M_BICGSTABL) fill_if_all_zero(h, n, d_x, 1.0e-8);   // IterSolve.F90:470-471
+  if (method == B200_M_BICGSTAB || method == B200_M_BICGSTABL || method == B200_M_BICGSTAB2) fill_if_all_zero(h, n, d_x, 1.0e-8);   // IterSolve.F90:470-471
   HostResult hr;
   if (n == 0) { IPAR(30) = HUTI_CONVERGENCE; IPAR(31) = 0; return; }
   switch (method) {
@@ -949,6 +1007,7 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
     case B200_M_GMRES: hr = run_gmres(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(15), stopc); break;
     case B200_M_CGS: hr = run_cgs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
     case B200_M_TFQMR: hr = run_tfqmr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
+    case B200_M_BICGSTAB2: hr = run_bicgstab2(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
     default: B200_REQUIRE(false, "unknown iterative method code");
   }
   B200_CUDA(cudaEventRecord(h.ev_end, st));

@@ -701,6 +701,70 @@ void huti_dtfqmrsolv(Ops &op, int ndim, double *X, const double *B, int *ipar, d
   dpar[9] = residual;
 }
 
+// fhutiter/src/huti_bicgstab_2.F90:339-578 huti_dbicgstab_2solv.  work(n,8) = RTLD,U,T1V,V,S,W,T,R.  Left-oriented in Elmer.
+void huti_dbicgstab_2solv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar, double *work) {
+  const size_t N = (size_t)ndim;
+  double *RTLD = work, *U = work + N, *T1V = work + 2 * N, *V = work + 3 * N, *S = work + 4 * N, *W = work + 5 * N, *T = work + 6 * N, *R = work + 7 * N;
+  double rho = 0, oldrho = 1, alpha = 0, beta = 0, omega1 = 0, omega2 = 1, tau = 0, delta = 0, myy = 0, residual = 0, rhsnorm = 1.0;
+  int iter_count = 1;
+  if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB || HUTI_STOPC == HUTI_PRESID_SCALED_BYB) rhsnorm = op.norm(ndim, B);
+  auto apply = [&](double *dst, const double *src) { op.pcondr(dst, src); op.matvec(dst, T1V); op.pcondl(dst, T1V); };   // dst = M^-1 A src
+  op.pcondr(U, X); op.matvec(U, R);
+  for (int i = 0; i < ndim; ++i) U[i] = B[i] - R[i];
+  op.pcondl(R, U);
+  for (int i = 0; i < ndim; ++i) { RTLD[i] = R[i]; U[i] = 0; }
+  for (;;) {
+    oldrho = -omega2 * oldrho;
+    rho = op.dot(ndim, RTLD, R);
+    if (rho == 0) { HUTI_INFO = 45; break; }                        // HUTI_BICGSTAB_2_RHO
+    beta = (rho * alpha) / oldrho;
+    oldrho = rho;
+    for (int i = 0; i < ndim; ++i) U[i] = R[i] - beta * U[i];
+    apply(V, U);
+    alpha = oldrho / op.dot(ndim, RTLD, V);
+    for (int i = 0; i < ndim; ++i) R[i] = R[i] - alpha * V[i];
+    apply(S, R);
+    for (int i = 0; i < ndim; ++i) X[i] = X[i] + alpha * U[i];
+    rho = op.dot(ndim, RTLD, S);
+    if (rho == 0) { HUTI_INFO = 45; break; }
+    beta = (rho * alpha) / oldrho;
+    oldrho = rho;
+    for (int i = 0; i < ndim; ++i) V[i] = S[i] - beta * V[i];
+    apply(W, V);
+    alpha = oldrho / op.dot(ndim, RTLD, W);
+    for (int i = 0; i < ndim; ++i) U[i] = R[i] - beta * U[i];
+    for (int i = 0; i < ndim; ++i) R[i] = R[i] - alpha * V[i];
+    for (int i = 0; i < ndim; ++i) S[i] = S[i] - alpha * W[i];
+    apply(T, S);
+    omega1 = op.dot(ndim, R, S);
+    myy = op.dot(ndim, S, S);
+    delta = op.dot(ndim, S, T);
+    tau = op.dot(ndim, T, T);
+    omega2 = op.dot(ndim, R, T);
+    tau = tau - (delta * delta) / myy;
+    omega2 = (omega2 - (delta * omega1) / myy) / tau;
+    omega1 = (omega1 - delta * omega2) / myy;
+    for (int i = 0; i < ndim; ++i) X[i] = X[i] + omega1 * R[i] + omega2 * S[i] + alpha * U[i];
+    for (int i = 0; i < ndim; ++i) R[i] = R[i] - omega1 * S[i] - omega2 * T[i];
+    if (HUTI_STOPC == HUTI_PSEUDORESIDUAL) residual = op.norm(ndim, R);
+    else if (HUTI_STOPC == HUTI_PRESID_SCALED_BYB) residual = op.norm(ndim, R) / rhsnorm;
+    else {
+      op.pcondr(S, X); op.matvec(S, T1V);
+      for (int i = 0; i < ndim; ++i) T1V[i] = T1V[i] - B[i];
+      op.pcondl(S, T1V);
+      residual = op.norm(ndim, S);
+      if (HUTI_STOPC == HUTI_TRESID_SCALED_BYB) residual /= rhsnorm;
+    }
+    if (residual < HUTI_TOLERANCE) { HUTI_INFO = HUTI_CONVERGENCE; break; }
+    if (residual != residual || residual > HUTI_MAXTOLERANCE) { HUTI_INFO = HUTI_DIVERGENCE; break; }
+    for (int i = 0; i < ndim; ++i) U[i] = U[i] - omega1 * V[i] - omega2 * W[i];
+    iter_count = iter_count + 1;
+    if (iter_count > HUTI_MAXIT) { HUTI_INFO = HUTI_MAXITER; break; }
+  }
+  HUTI_ITERS = iter_count;
+  dpar[9] = residual;
+}
+
 // fhutiter/src/huti_bicgstab.F90:279-566 huti_dbicgstabsolv.  work(n,8) = RTLD,P,T1V,V,S,T2V,T,R.
 void huti_dbicgstabsolv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar,
                         double *work) {
@@ -1292,7 +1356,7 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
   A.ILURows = g_ilu_rows; A.ILUCols = g_ilu_cols; A.ILUDiag = g_ilu_diag;
   Ops op{&A};
   HUTI_NDIM = n;
-  if (method == 2 || method == 3) {
+  if (method == 2 || method == 3 || method == 9) {
     bool allz = true;
     for (int i = 0; i < n; ++i) if (x[i] != 0.0) { allz = false; break; }
     if (allz) for (int i = 0; i < n; ++i) x[i] = 1.0e-8;
@@ -1330,6 +1394,10 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
     if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
     if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;
     HUTI_ITERS = iters; dpar[9] = res;
+  } else if (method == 9) {
+    op.left = true;
+    std::vector<double> work((size_t)n * 8, 0.0);
+    huti_dbicgstab_2solv(op, n, x, b, ipar, dpar, work.data());
   } else if (method == 7) {
     std::vector<double> work((size_t)n * 7, 0.0);
     huti_dcgssolv(op, n, x, b, ipar, dpar, work.data());

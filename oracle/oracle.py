@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8}
+METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8, "bicgstab2": 9}
 PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2, "ilu1": 2, "ilu2": 2, "ilu3": 2}
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -135,7 +135,7 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
     fhutiter/src/huti_fdefs.h:101-155."""
     ipar = np.zeros(50, dtype=np.int32)
     dpar = np.zeros(10, dtype=np.float64)
-    wrk = {"cg": 4, "bicgstab": 8, "cgs": 7, "tfqmr": 10}.get(method, 1)
+    wrk = {"cg": 4, "bicgstab": 8, "cgs": 7, "tfqmr": 10, "bicgstab2": 8}.get(method, 1)
     ipar[3 - 1] = n
     ipar[4 - 1] = wrk
     ipar[5 - 1] = residual_output

@@ -209,7 +209,7 @@ def test_itersolver_keywords(oracle, heat, heat_gpu):
     assert rel_l2(got["x"], ref["x"]) <= 1e-7
     declined = heat_gpu.itersolver(b, None, sif.replace("ILU0", "ILUT"), 0)
     assert declined is None
-    assert heat_gpu.itersolver(b, None, sif.replace("BiCGStab", "BiCGStab2"), 0) is None
+    assert heat_gpu.itersolver(b, None, sif.replace("BiCGStab", "SGS"), 0) is None
 
 
 def test_empty_and_tiny_systems(oracle, b200):
@@ -427,11 +427,11 @@ def test_device_scaling(oracle, b200):
     M.close()
 
 
-@pytest.mark.parametrize("method", ["cgs", "tfqmr"])
+@pytest.mark.parametrize("method", ["cgs", "tfqmr", "bicgstab2"])
 @pytest.mark.parametrize("precond", ["none", "diagonal", "ilu0"])
 def test_cgs_tfqmr_parity(oracle, b200, heat, heat_gpu, method, precond):
-    """huti_dcgssolv (fhutiter/src/huti_cgs.F90:283-470, right-oriented) and huti_dtfqmrsolv (huti_tfqmr.F90:455-803, left-oriented as
-    IterSolver calls it): iteration counts and solutions against the oracle; nonsymmetric system; keyword path."""
+    """huti_dcgssolv (fhutiter/src/huti_cgs.F90:283-470, right-oriented), huti_dtfqmrsolv (huti_tfqmr.F90:455-803) and
+    huti_dbicgstab_2solv (huti_bicgstab_2.F90:339-578), the latter two left-oriented as IterSolver calls them: iteration counts and solutions against the oracle; nonsymmetric system; keyword path."""
     A, b = heat
     ref = oracle.itersolve(A, b, method=method, precond=precond, tol=TOL, maxit=500)
     got = heat_gpu.solve(b, method=method, precond=precond, tol=TOL, maxit=500)
@@ -454,7 +454,7 @@ def test_cgs_tfqmr_parity(oracle, b200, heat, heat_gpu, method, precond):
           Linear System Preconditioning = ILU0
           Linear System Max Iterations = 500
           Linear System Convergence Tolerance = 1.0e-8
-        """ % method.upper()
+        """ % {"cgs": "CGS", "tfqmr": "TFQMR", "bicgstab2": "BiCGStab2"}[method]
         ref = oracle.itersolve(A, b, method=method, precond="ilu0", tol=TOL, maxit=500)
         got = heat_gpu.itersolver(b, None, sif, 0)
         assert got is not None and got["info"] == 1 and iters_close(got["iters"], ref["iters"])

@@ -209,7 +209,7 @@ def test_ilun_against_dense(oracle, order):
     assert np.abs((np.tril(LU, -1) * P + np.eye(n)) @ ((np.triu(LU) * P) @ u) - v).max() <= 1e-11 * np.abs(v).max()
 
 
-@pytest.mark.parametrize("method", ["cgs", "tfqmr"])
+@pytest.mark.parametrize("method", ["cgs", "tfqmr", "bicgstab2"])
 @pytest.mark.parametrize("precond", ["none", "diagonal", "ilu0"])
 def test_testmat_known_answer_cgs_tfqmr(oracle, testmat, method, precond):
     """TFQMR is the method the reference's own ex1 driver used to write testmat.out (fhutiter/examples/ex1/huti-ex.F90)."""
