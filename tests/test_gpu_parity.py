@@ -458,3 +458,25 @@ def test_cgs_tfqmr_parity(oracle, b200, heat, heat_gpu, method, precond):
         ref = oracle.itersolve(A, b, method=method, precond="ilu0", tol=TOL, maxit=500)
         got = heat_gpu.itersolver(b, None, sif, 0)
         assert got is not None and got["info"] == 1 and iters_close(got["iters"], ref["iters"])
+
+
+def test_reference_linearsolvers_case_gpu(oracle, b200):
+    """fem/tests/linearsolvers/TempDist.sif through the C ABI: the reference's mesh, every Krylov method of the SIF + ILU0, tol 1e-12,
+    device-side Linear System Scaling; answer = the constant k, `Reference Norm = k`; iteration counts as the oracle's."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from linearsolvers_case import tempdist_system, compute_norm
+    from test_oracle_golden import LINSOLVERS
+    for k, (method, kw) in enumerate(LINSOLVERS):
+        k = float(k + 5)
+        S, b, x0 = tempdist_system(k)
+        A = oracle.CRS.from_scipy(S)
+        M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 1); M.set_values(A.vals)
+        M.scale_system()
+        P = oracle.shadow_space(A.n, 4) if method == "idrs" else None
+        got = M.solve(b, x0=x0, method=method, precond="ilu0", tol=1e-12, maxit=3500, P=P, **kw)
+        ref = oracle.solve_linear_system(A, b, x0=x0, method=method, precond="ilu0", tol=1e-12, maxit=3500, P=P, **kw)
+        assert got["info"] == ref["info"] == 1, (method, got["info"])
+        assert abs(compute_norm(got["x"]) - k) <= 1e-5 * k and np.abs(got["x"] - k).max() <= 1e-9 * k, method
+        assert iters_close(got["iters"], ref["iters"]), (method, got["iters"], ref["iters"])
+        M.close()

@@ -217,3 +217,20 @@ def test_testmat_known_answer_cgs_tfqmr(oracle, testmat, method, precond):
     r = oracle.itersolve(A, np.ones(100), method=method, precond=precond, tol=1e-10, maxit=2000)
     assert r["info"] == 1, (method, precond, r["info"])
     assert np.abs(r["x"] - xref).max() < 1e-6
+
+
+LINSOLVERS = [("cg", {}), ("cgs", {}), ("bicgstab", {}), ("tfqmr", {}), ("gmres", {}), ("bicgstab2", {}), ("bicgstabl", dict(bicgstabl_l=4)),
+              ("idrs", {}), ("gcr", dict(gcr_restart=100))]
+
+
+@pytest.mark.parametrize("k,method,kw", [(k + 5, m, kw) for k, (m, kw) in enumerate(LINSOLVERS)])
+def test_reference_linearsolvers_case(oracle, k, method, kw):
+    """fem/tests/linearsolvers/TempDist.sif: every Krylov method + ILU0 at tol 1e-12 on the reference's own mesh; the exact answer is
+    the constant k and the reference checks `Reference Norm = k` (TempDist.sif:89-175)."""
+    from linearsolvers_case import tempdist_system
+    S, b, x0 = tempdist_system(float(k))
+    A = oracle.CRS.from_scipy(S)
+    r = oracle.solve_linear_system(A, b, x0=x0, method=method, precond="ilu0", tol=1e-12, maxit=3500, **kw)
+    assert r["info"] == 1
+    assert abs(r["norm"] - k) <= 1e-5 * k            # the test harness' norm tolerance
+    assert np.abs(r["x"] - k).max() <= 1e-9 * k
