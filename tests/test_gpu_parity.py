@@ -480,3 +480,21 @@ def test_reference_linearsolvers_case_gpu(oracle, b200):
         assert abs(compute_norm(got["x"]) - k) <= 1e-5 * k and np.abs(got["x"] - k).max() <= 1e-9 * k, method
         assert iters_close(got["iters"], ref["iters"]), (method, got["iters"], ref["iters"])
         M.close()
+
+
+def test_reference_winkel_poisson_norm_gpu(b200):
+    """fem/tests/WinkelBmPoissonCgIlu0 / IdrsIlu0 through the C ABI (mesh by the reference's ElmerGrid, device-side scaling):
+    `Reference Norm = 1.03281284`."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import winkel_case as W
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    A, b = W.system()
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 1); M.set_values(A.vals)
+    M.scale_system()
+    for method in ("cg", "idrs", "bicgstab", "gmres"):
+        got = M.solve(b, method=method, precond="ilu0", tol=1e-8, maxit=1000)
+        assert got["info"] == 1, method
+        assert abs(W.norm(got["x"]) - W.REFERENCE_NORM) <= 1e-6 * W.REFERENCE_NORM, (method, W.norm(got["x"]))
+    M.close()

@@ -111,3 +111,77 @@ def test_multi_gpu_parity(oracle, b200, WORLD, method, precond, kind):
     it = iters.pop()
     assert abs(it - ref["iters"]) <= max(1, int(np.ceil(0.02 * ref["iters"]))), (it, ref["iters"])
     assert np.linalg.norm(x - ref["x"]) / np.linalg.norm(ref["x"]) <= 10 * TOL
+
+
+def _winkel_worker(rank, world, port, out_q, npz):
+    os.environ["LOCAL_RANK"] = str(rank)
+    import torch
+    import torch.distributed as dist
+    import elmerfem_b200 as B
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        d = np.load(npz)
+        ids = [B.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        M = B.Matrix()
+        M.comm_init(world, rank, ids[0])
+        M.set_partition(int(d["gn"]), d["rows%d" % rank], d["cols%d" % rank], d["goffset"], 0, 1)
+        M.set_values(d["vals%d" % rank])
+        got = M.solve(d["b%d" % rank], method="cg", precond="ilu0", tol=1e-8, maxit=1000)
+        out_q.put((rank, got["x"].tolist(), got["info"], got["iters"]))
+        dist.barrier()
+        M.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("WORLD", [2, 4])
+def test_multi_gpu_winkel_metis(oracle, b200, WORLD, tmp_path):
+    """fem/tests/WinkelBmPoissonCgIlu0 on WORLD GPUs: the reference's METIS partition (ElmerGrid -partdual -metisrec N), irregular
+    neighbour lists, CG + block-Jacobi ILU0 => the reference's norm 1.03281284 and the oracle's iteration count at that partition count."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import winkel_case as W
+    from elmerfem_b200 import meshio
+    n = C.c_int(0)
+    if b200.lib().b200_device_count(C.byref(n)) != 0 or n.value < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    import torch.multiprocessing as mp
+    A, b = W.system()
+    x = np.zeros(A.n)
+    Dv, bn = oracle.scale_system(A, b, x)
+    P = meshio.Partitioning(os.path.join(W.mesh_dir(WORLD), "partitioning.%d" % WORLD), WORLD, ndof=1)
+    parts, Sc = P.owned_rows(A.to_scipy())
+    perm = P.dof_permutation()
+    bc = np.zeros(A.n); bc[perm] = b
+    arrays = dict(gn=P.gn, goffset=P.goffset)
+    for r, (rows, cols, vals) in enumerate(parts):
+        arrays["rows%d" % r] = rows; arrays["cols%d" % r] = cols; arrays["vals%d" % r] = vals
+        arrays["b%d" % r] = bc[P.goffset[r]:P.goffset[r + 1]]
+    npz = str(tmp_path / "winkel_parts.npz")
+    np.savez(npz, **arrays)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_winkel_worker, args=(r, WORLD, port, q, npz)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    xc = np.concatenate([np.array(r_[1]) for r_ in res])
+    assert {r_[2] for r_ in res} == {1}
+    xnat = xc[perm] * Dv
+    assert abs(W.norm(xnat) - W.REFERENCE_NORM) <= 1e-6 * W.REFERENCE_NORM, W.norm(xnat)
+    Ac = oracle.CRS.from_scipy(Sc)
+    block = np.searchsorted(P.goffset, np.arange(A.n), side="right") - 1
+    rowid = np.repeat(np.arange(A.n), np.diff(Ac.rows))
+    Abd = Ac.copy(); Abd.vals[block[rowid] != block[Ac.cols - 1]] = 0.0
+    ref = oracle.itersolve(Ac, bc, method="cg", precond="ilu0", ilu=oracle.ilu0(Abd), tol=1e-8, maxit=1000)
+    it = {r_[3] for r_ in res}
+    assert len(it) == 1 and abs(it.pop() - ref["iters"]) <= max(1, int(np.ceil(0.02 * ref["iters"])))

@@ -234,3 +234,48 @@ def test_reference_linearsolvers_case(oracle, k, method, kw):
     assert r["info"] == 1
     assert abs(r["norm"] - k) <= 1e-5 * k            # the test harness' norm tolerance
     assert np.abs(r["x"] - k).max() <= 1e-9 * k
+
+
+@pytest.mark.parametrize("method", ["cg", "idrs"])
+def test_reference_winkel_poisson_norm(oracle, method):
+    """fem/tests/WinkelBmPoissonCgIlu0 and ...IdrsIlu0 (serial): mesh from the reference's ElmerGrid, our hex8 assembly, the oracle's
+    CG / IDR(s) + ILU0 at tol 1e-8 with default scaling => the reference's `Reference Norm = 1.03281284`."""
+    import winkel_case as W
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    A, b = W.system()
+    r = oracle.solve_linear_system(A, b, method=method, precond="ilu0", tol=1e-8, maxit=1000)
+    assert r["info"] == 1
+    assert abs(r["norm"] - W.REFERENCE_NORM) <= 1e-7 * W.REFERENCE_NORM, r["norm"]
+
+
+@pytest.mark.parametrize("nparts", [2, 8])
+def test_reference_winkel_poisson_partitioned(oracle, b200, nparts):
+    """The same case partitioned as the reference's runtest.cmake does (ElmerGrid -partdual -metisrec N; the reference runs np = 2 and 8):
+    ownership from part.i.shared, continuous numbering, complete owned rows, halo plan checked against the rocalution restatement,
+    block-Jacobi ILU0 (ILU0 of every rank's owned x owned block, SParIterSolver.F90:2491-2497) => the same norm at every partition count."""
+    import winkel_case as W
+    from elmerfem_b200 import meshio
+    from test_halo_plan import check_against_oracle
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    A, b = W.system()
+    x = np.zeros(A.n)
+    oracle.scale_system(A, b, x)
+    P = meshio.Partitioning(os.path.join(W.mesh_dir(nparts), "partitioning.%d" % nparts), nparts, ndof=1)
+    parts, Sc = P.owned_rows(A.to_scipy())
+    check_against_oracle(b200, Sc, P.goffset)
+    perm = P.dof_permutation()
+    bc = np.zeros(A.n); bc[perm] = b
+    Ac = oracle.CRS.from_scipy(Sc)
+    block = np.searchsorted(P.goffset, np.arange(A.n), side="right") - 1
+    rowid = np.repeat(np.arange(A.n), np.diff(Ac.rows))
+    Abd = Ac.copy()
+    Abd.vals[block[rowid] != block[Ac.cols - 1]] = 0.0
+    r = oracle.itersolve(Ac, bc, method="cg", precond="ilu0", ilu=oracle.ilu0(Abd), tol=1e-8, maxit=1000)
+    assert r["info"] == 1
+    # back to the natural numbering and the unscaled unknowns (x = D x_scaled)
+    A0, b0 = W.system()
+    xs = np.zeros(A.n); Dv, bn = oracle.scale_system(A0, b0, xs)
+    xnat = r["x"][perm] * Dv
+    assert abs(W.norm(xnat) - W.REFERENCE_NORM) <= 1e-6 * W.REFERENCE_NORM, W.norm(xnat)
