@@ -498,3 +498,26 @@ def test_reference_winkel_poisson_norm_gpu(b200):
         assert got["info"] == 1, method
         assert abs(W.norm(got["x"]) - W.REFERENCE_NORM) <= 1e-6 * W.REFERENCE_NORM, (method, W.norm(got["x"]))
     M.close()
+
+
+def test_reference_winkel_navier_norm_gpu(oracle, b200):
+    """fem/tests/WinkelBmNavier* through the C ABI: ndeg = 3 (block-column SpMV, 3 accumulators), device-side scaling, ILU0 / Jacobi:
+    `Reference Norm = 2.25252433E-02`, SpMV and ILU0 bit-exact against the oracle on this unstructured-numbered operand."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import winkel_case as W
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    A, b = W.navier_system()
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 3); M.set_values(A.vals)
+    u = np.random.RandomState(41).standard_normal(A.n)
+    assert np.array_equal(M.matvec(u), oracle.matvec(A, u))
+    M.scale_system()
+    As = A.copy(); bs = b.copy(); xs = np.zeros(A.n); oracle.scale_system(As, bs, xs)
+    M.factorize()
+    assert np.array_equal(M.ilu_values(), oracle.ilu0(As))
+    for method, pc in (("cg", "ilu0"), ("bicgstabl", "ilu0"), ("bicgstab", "diagonal"), ("gmres", "ilu0")):
+        got = M.solve(b, method=method, precond=pc, tol=1e-10, maxit=5000, bicgstabl_l=4, gmres_restart=30)
+        assert got["info"] == 1, method
+        assert abs(W.norm(got["x"]) - W.NAVIER_REFERENCE_NORM) <= 1e-6 * W.NAVIER_REFERENCE_NORM, (method, W.norm(got["x"]))
+    M.close()

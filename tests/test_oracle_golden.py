@@ -279,3 +279,44 @@ def test_reference_winkel_poisson_partitioned(oracle, b200, nparts):
     xs = np.zeros(A.n); Dv, bn = oracle.scale_system(A0, b0, xs)
     xnat = r["x"][perm] * Dv
     assert abs(W.norm(xnat) - W.REFERENCE_NORM) <= 1e-6 * W.REFERENCE_NORM, W.norm(xnat)
+
+
+@pytest.mark.parametrize("method,precond", [("cg", "ilu0"), ("bicgstabl", "ilu0"), ("gcr", "diagonal"), ("idrs", "ilu1")])
+def test_reference_winkel_navier_norm(oracle, method, precond):
+    """fem/tests/WinkelBmNavier* (3-dof linear elasticity on the reference's winkel mesh, clamped wall, surface traction):
+    `Reference Norm = 2.25252433E-02`, solver independent."""
+    import winkel_case as W
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    A, b = W.navier_system()
+    r = oracle.solve_linear_system(A, b, method=method, precond=precond, tol=1e-10, maxit=5000, bicgstabl_l=4)
+    assert r["info"] == 1
+    assert abs(r["norm"] - W.NAVIER_REFERENCE_NORM) <= 1e-7 * W.NAVIER_REFERENCE_NORM, r["norm"]
+
+
+def test_reference_winkel_navier_partitioned(oracle, b200):
+    """The elasticity case on the reference's METIS k-way partition (runtest.cmake: -partdual -metiskway N), 3 dofs per node: dof ownership
+    copied from the nodes, halo plan against the rocalution restatement, block-Jacobi ILU0 => the same norm."""
+    import winkel_case as W
+    from elmerfem_b200 import meshio
+    from test_halo_plan import check_against_oracle
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    nparts = 4
+    A, b = W.navier_system()
+    x = np.zeros(A.n)
+    Dv, bn = oracle.scale_system(A, b, x)
+    P = meshio.Partitioning(os.path.join(W.navier_mesh_dir(nparts), "partitioning.%d" % nparts), nparts, ndof=3)
+    parts, Sc = P.owned_rows(A.to_scipy())
+    check_against_oracle(b200, Sc, P.goffset)
+    perm = P.dof_permutation()
+    bc = np.zeros(A.n); bc[perm] = b
+    Ac = oracle.CRS.from_scipy(Sc, ndeg=3)
+    block = np.searchsorted(P.goffset, np.arange(A.n), side="right") - 1
+    rowid = np.repeat(np.arange(A.n), np.diff(Ac.rows))
+    Abd = Ac.copy()
+    Abd.vals[block[rowid] != block[Ac.cols - 1]] = 0.0
+    r = oracle.itersolve(Ac, bc, method="bicgstabl", precond="ilu0", ilu=oracle.ilu0(Abd), tol=1e-10, maxit=5000, bicgstabl_l=4)
+    assert r["info"] == 1
+    xnat = r["x"][perm] * Dv
+    assert abs(W.norm(xnat) - W.NAVIER_REFERENCE_NORM) <= 1e-6 * W.NAVIER_REFERENCE_NORM, W.norm(xnat)
