@@ -467,6 +467,16 @@ int b200_set_ilu_order(void **handle, const int *order) {
     ilu_invalidate(h);
   });
 }
+int b200_set_bilu_blocks(void **handle, const int *blocks) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(blocks && *blocks >= 0, "BILU blocks must be >= 0");
+    const int b = *blocks <= 1 ? 0 : *blocks;
+    if (b == h.bilu_blocks) return;
+    h.bilu_blocks = b;
+    ilu_invalidate(h);
+  });
+}
 int b200_get_ilu_structure(void **handle, int *sizes, int *rows, int *cols, int *diag) {
   return guarded([&] {
     Handle &h = H(handle);

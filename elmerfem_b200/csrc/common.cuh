@@ -122,15 +122,17 @@ struct Handle {
   DBuf<double> d_vals, d_prec, d_ilu, d_dvals; bool have_vals = false, have_prec = false, ilu_valid = false, ilu_exists = false;
   // ILU(n > 0): the factor lives on its own pattern (CRSMatrix.F90:3488-3510); ILU0 aliases the matrix pattern
   int ilu_order = 0; bool ilu_pat_ready = false; long long ilu_nnz = 0;
+  int bilu_blocks = 0;                             // > 1: BILU, the factor of the block-diagonal part (CRS_BlockDiagonal, CRSMatrix.F90:2382-2420)
+  bool ilu_sep() const { return ilu_order > 0 || bilu_blocks > 1; }   // factor on its own pattern
   std::vector<int> hl_rows, hl_cols, hl_diag;    // 0-based host copies of ILURows/ILUCols/ILUDiag
   DBuf<int> dl_rows, dl_cols, dl_diag, dl_src;   // device copies; dl_src: position of the entry in the matrix values, -1 for fill
-  const std::vector<int> &lrows() const { return ilu_order ? hl_rows : h_rows; }
-  const std::vector<int> &lcols() const { return ilu_order ? hl_cols : h_cols; }
-  const std::vector<int> &ldiag() const { return ilu_order ? hl_diag : h_diag; }
-  const int *d_lrows() const { return ilu_order ? dl_rows.p : d_rows.p; }
-  const int *d_lcols() const { return ilu_order ? dl_cols.p : d_cols.p; }
-  const int *d_ldiag() const { return ilu_order ? dl_diag.p : d_diag.p; }
-  long long lnnz() const { return ilu_order ? ilu_nnz : nnz; }
+  const std::vector<int> &lrows() const { return ilu_sep() ? hl_rows : h_rows; }
+  const std::vector<int> &lcols() const { return ilu_sep() ? hl_cols : h_cols; }
+  const std::vector<int> &ldiag() const { return ilu_sep() ? hl_diag : h_diag; }
+  const int *d_lrows() const { return ilu_sep() ? dl_rows.p : d_rows.p; }
+  const int *d_lcols() const { return ilu_sep() ? dl_cols.p : d_cols.p; }
+  const int *d_ldiag() const { return ilu_sep() ? dl_diag.p : d_diag.p; }
+  long long lnnz() const { return ilu_sep() ? ilu_nnz : nnz; }
   // device-side Linear System Scaling (b200_scale_system): D, and D * bnorm of the running solve
   bool scaled = false; DBuf<double> d_scale, d_scale_rhs;
   // SpMV operand

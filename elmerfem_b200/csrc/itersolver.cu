@@ -156,9 +156,20 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
       if (got) ilun = (int)lround(o);
       else ilun = pcs.size() >= 4 ? pcs[3] - '0' : -1;                  // 541-546
       if (ilun < 0 || ilun > 9) ilun = 0;
-      if (ilun != h.ilu_order) { B200_CUDA(cudaSetDevice(h.device)); h.ilu_order = ilun; ilu_invalidate(h); }
+      if (ilun != h.ilu_order || h.bilu_blocks) { B200_CUDA(cudaSetDevice(h.device)); h.ilu_order = ilun; h.bilu_blocks = 0; ilu_invalidate(h); }
       pc = B200_PRECOND_ILU0;
-    } else if (pcs.rfind("bilu", 0) == 0 || pcs == "multigrid" || pcs.rfind("vanka", 0) == 0 || pcs == "slave" || pcs == "circuit")
+    } else if (pcs.rfind("bilu", 0) == 0) {
+      // IterSolve.F90:549-558, 745-765: ILU(n) of the block-diagonal part, Blocks = Solver % Variable % Dofs (here: Matrix_t % ndeg,
+      // or the shim's "B200 Variable Dofs").  Order 0 only: for n > 0 the reference's RE-factorisation leaves stale entries of the
+      // scattered row behind (only pattern positions of S are cleared, CRSMatrix.F90:3643-3649) and is not reproducible as a preconditioner.
+      int ilun = pcs.size() >= 5 ? pcs[4] - '0' : 0;
+      if (ilun < 0 || ilun > 9) ilun = 0;
+      if (ilun != 0) throw Declined{"BILU order > 0"};
+      int blocks = P.integer("B200 Variable Dofs", h.ndeg);
+      if (blocks <= 1) blocks = 0;
+      if (h.ilu_order != 0 || h.bilu_blocks != blocks) { B200_CUDA(cudaSetDevice(h.device)); h.ilu_order = 0; h.bilu_blocks = blocks; ilu_invalidate(h); }
+      pc = B200_PRECOND_ILU0;
+    } else if (pcs == "multigrid" || pcs.rfind("vanka", 0) == 0 || pcs == "slave" || pcs == "circuit")
       throw Declined{"preconditioner '" + pcs + "'"};
     else { fprintf(stderr, "[elmer_b200] IterSolve: Unknown preconditioner type, feature disabled.\n"); pc = B200_PRECOND_NONE; }
     if (P.real("Linear System ILU Factor", 0.0) > 2.220446049250313e-16) throw Declined{"'Linear System ILU Factor'"};

@@ -167,7 +167,7 @@ void ilu0_factor(Handle &h) {
     if (!h.grid_ilu) h.grid_ilu = persistent_blocks((const void *)k_ilu0_factor, 256, 0);
     int blocks = std::max(1, std::min(h.grid_ilu, (h.L.nslots + 7) / 8));
     launch_coresident((const void *)k_ilu0_factor, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
-                      (const int *)(h.ilu_order ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
+                      (const int *)(h.ilu_sep() ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
     int eb = std::min((h.n + 255) / 256, NUM_SMS * 8);
     k_ilu0_invert_diag<<<eb, 256, 0, st>>>(h.n, h.d_ldiag(), h.d_ilu.p);
     sell_refresh_values(h, h.L, h.d_ilu.p);

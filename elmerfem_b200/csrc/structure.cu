@@ -163,9 +163,18 @@ static void ilu1_round(int n, const std::vector<int> &rows, const std::vector<in
 }
 
 void ilu_pattern_build(Handle &h) {
-  if (h.ilu_order <= 0 || h.ilu_pat_ready) return;
+  if (!h.ilu_sep() || h.ilu_pat_ready) return;
   const int n = h.n;
   std::vector<int> r = h.h_rows, c = h.h_cols, d = h.h_diag, r2, c2, d2;
+  if (h.bilu_blocks > 1) {                                 // CRS_BlockDiagonal: keep the entries with MOD(i,Blocks) == MOD(j,Blocks)
+    const int B = h.bilu_blocks;
+    r2.assign((size_t)n + 1, 0); c2.clear(); d2.assign(n, 0);
+    for (int i = 0; i < n; ++i) {
+      for (int p = r[i]; p < r[i + 1]; ++p) if (i % B == c[p] % B) { if (c[p] == i) d2[i] = (int)c2.size(); c2.push_back(c[p]); }
+      r2[i + 1] = (int)c2.size();
+    }
+    r.swap(r2); c.swap(c2); d.swap(d2);
+  }
   for (int round = 0; round < h.ilu_order; ++round) { ilu1_round(n, r, c, d, r2, c2, d2); r.swap(r2); c.swap(c2); d.swap(d2); }
   std::vector<int> src(c.size(), -1);
 #pragma omp parallel for

@@ -132,6 +132,7 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   CHARACTER(LEN=4096) :: sif
   CHARACTER(:), ALLOCATABLE :: str
   LOGICAL :: Found, ScaleSystem, DeviceScaling, L
+  CHARACTER(LEN=32) :: tmp
   INTEGER :: rc, info(2), nnz, ival, base, ndeg
   REAL(KIND=dp) :: rval
   INTEGER(C_INTPTR_T) :: handle
@@ -161,6 +162,8 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   CALL AddInt( 'Linear System Residual Output' )
   CALL AddInt( 'Linear System GCR Restart' )
   CALL AddInt( 'Linear System GMRES Restart' )
+  WRITE( tmp, '(I0)' ) Solver % Variable % DOFs
+  CALL Append( 'B200 Variable Dofs = ' // TRIM(tmp) )                 ! Blocks of BILU (IterSolve.F90:746)
   CALL AddInt( 'BiCGstabl polynomial degree' )
   CALL AddInt( 'IDRS parameter' )
   CALL AddInt( 'Linear System Precondition Recompute' )

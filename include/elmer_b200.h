@@ -103,6 +103,10 @@ int b200_factorize(void **handle);                 /* ILU(order) of PrecValues (
  * factorises on the matrix pattern; n > 0 first adds n rounds of first-order fill (InitializeILU1, 3664-3795).
  * Changing the order drops the current factor. */
 int b200_set_ilu_order(void **handle, const int *order);
+/* BILU ("Linear System Preconditioning = BILU"): the incomplete factorisation acts on the block-diagonal part of the matrix,
+ * entries with MOD(i,blocks) == MOD(j,blocks) (CRS_BlockDiagonal, fem/src/CRSMatrix.F90:2382-2420; IterSolve.F90:745-765), blocks =
+ * Solver % Variable % Dofs.  blocks <= 1 switches it off.  Order 0 only through the keyword front-end (see b200_itersolver). */
+int b200_set_bilu_blocks(void **handle, const int *blocks);
 
 /* ---- solve ----------------------------------------------------------------------------- */
 /* b[n] in, x[n] in/out (initial guess in, solution out), ipar[50] in/out, dpar[10] in.

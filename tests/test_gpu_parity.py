@@ -521,3 +521,46 @@ def test_reference_winkel_navier_norm_gpu(oracle, b200):
         assert got["info"] == 1, method
         assert abs(W.norm(got["x"]) - W.NAVIER_REFERENCE_NORM) <= 1e-6 * W.NAVIER_REFERENCE_NORM, (method, W.norm(got["x"]))
     M.close()
+
+
+def test_bilu_bit_exact(oracle, b200):
+    """BILU ("Linear System Preconditioning = BILU", IterSolve.F90:549-558, 745-765): ILU0 of the block-diagonal part of the matrix
+    (CRS_BlockDiagonal, CRSMatrix.F90:2382-2420), Blocks = dofs per node.  Pattern, values and triangular solves bit-exact against the
+    oracle's ILU0 of the same block-diagonal matrix; Krylov iteration counts; keyword path."""
+    import scipy.sparse as sp
+    A, b = oracle.elasticity_beam(8, 3, 3, lx=2.5)
+    A = A.copy(); x = np.zeros(A.n); oracle.scale_system(A, b, x)
+    S = A.to_scipy().tocoo()
+    keep = (S.row % 3) == (S.col % 3)
+    Bm = oracle.CRS.from_scipy(sp.csr_matrix((S.data[keep], (S.row[keep], S.col[keep])), shape=S.shape))
+    F = oracle.CRS(Bm.rows, Bm.cols, Bm.diag, oracle.ilu0(Bm), 1)
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 3); M.set_values(A.vals)
+    M.set_bilu_blocks(3)
+    r, c, d = M.ilu_structure()
+    assert np.array_equal(r, F.rows) and np.array_equal(c, F.cols) and np.array_equal(d, F.diag)
+    M.factorize()
+    assert np.array_equal(M.ilu_values(), F.vals)
+    v = np.random.RandomState(51).standard_normal(A.n)
+    assert np.array_equal(M.lu_precondition(v), oracle.lu_precond(A, F, v))
+    for method in ("cg", "bicgstabl"):
+        ref = oracle.itersolve(A, b, method=method, precond="ilu0", ilu=F, tol=TOL, maxit=2000, bicgstabl_l=4)
+        got = M.solve(b, method=method, precond="ilu0", tol=TOL, maxit=2000, bicgstabl_l=4)
+        assert got["info"] == ref["info"] == 1 and iters_close(got["iters"], ref["iters"]), (method, got["iters"], ref["iters"])
+        assert rel_l2(got["x"], ref["x"]) <= 10 * TOL
+    M.close()
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 3); M.set_values(A.vals)
+    sif = """
+      Linear System Solver = Iterative
+      Linear System Iterative Method = CG
+      Linear System Preconditioning = BILU
+      Linear System Max Iterations = 2000
+      Linear System Convergence Tolerance = 1.0e-8
+    """
+    ref = oracle.itersolve(A, b, method="cg", precond="ilu0", ilu=F, tol=TOL, maxit=2000)
+    got = M.itersolver(b, None, sif, 0)
+    assert got is not None and got["info"] == 1 and iters_close(got["iters"], ref["iters"])
+    assert M.itersolver(b, None, sif.replace("BILU", "BILU1"), 0) is None          # order > 0: declined (see itersolver.cu)
+    got0 = M.itersolver(b, None, sif.replace("BILU", "ILU0"), 0)                    # back to plain ILU0 on the same handle
+    ref0 = oracle.itersolve(A, b, method="cg", precond="ilu0", tol=TOL, maxit=2000)
+    assert got0["info"] == 1 and iters_close(got0["iters"], ref0["iters"])
+    M.close()
