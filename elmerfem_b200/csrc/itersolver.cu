@@ -95,12 +95,14 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     else if (m == "cgs") method = B200_METHOD_CGS;
     else if (m == "tfqmr") method = B200_METHOD_TFQMR;
     else if (m == "bicgstab2") method = B200_METHOD_BICGSTAB2;
-    else if (m == "sgs" || m == "jacobi" || m == "richardson")
+    else if (m == "jacobi") method = B200_METHOD_JACOBI;
+    else if (m == "richardson") method = B200_METHOD_RICHARDSON;
+    else if (m == "sgs")
       throw Declined{"iterative method '" + m + "' is not on the accelerated path"};
     else method = B200_METHOD_BICGSTAB;                                  // CASE DEFAULT (313-314)
     if (P.logical("Linear System Complex") || P.logical("Linear System Pseudo Complex"))
       throw Declined{"complex / pseudo-complex systems"};
-    const bool internal = method >= B200_METHOD_BICGSTABL && method <= B200_METHOD_IDRS;
+    const bool internal = (method >= B200_METHOD_BICGSTABL && method <= B200_METHOD_IDRS) || method == B200_METHOD_JACOBI || method == B200_METHOD_RICHARDSON;
     // ---- work sizes and method parameters (327-392)
     ipar[3] = internal ? 1 : (method == B200_METHOD_CG ? 4 : 8);
     if (method == B200_METHOD_CGS) ipar[3] = 7;                         // HUTI_CGS_WORKSIZE

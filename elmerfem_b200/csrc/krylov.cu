@@ -841,6 +841,49 @@ static HostResult run_bicgstab2(Handle &h, const double *b, double *x, int pc, i
   return res;
 }
 
+// IterativeMethods.F90:336-391 Jacobi, 444-519 Richardson: x += r / a_ii, resp. x = b / m (first round), x += r / m with m = the row
+// sums (summed left to right by one thread per row, as the reference loop does).
+__global__ void k_row_sums(int n, const int *__restrict__ rows, const double *__restrict__ vals, double *__restrict__ m) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int j = rows[i]; j < rows[i + 1]; ++j) s = __dadd_rn(s, vals[j]);
+    m[i] = s;
+  }
+}
+__global__ void k_stationary_update(int n, const double *__restrict__ d, const double *__restrict__ r, const double *__restrict__ b, double *x, int first) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    x[i] = first ? __ddiv_rn(b[i], d[i]) : __dadd_rn(x[i], __ddiv_rn(r[i], d[i]));
+}
+static HostResult run_stationary(Handle &h, const double *b, double *x, int Rounds, double MinTol, double MaxTol, bool richardson) {
+  HostResult res;
+  B200_REQUIRE(h.nranks == 1, "Jacobi / Richardson iterations are implemented for single-rank handles only");
+  Solver S(h, 0, 2);
+  const int n = S.n;
+  double *R = S.vec[0], *M = S.vec[1];
+  S.matvec(x, R); S.lin(b, 1.0, R, -1.0);
+  double o[2];
+  { const double *xs[2] = {b, R}, *ys[2] = {b, R}; S.dots(2, xs, ys, o); }
+  const double bnorm = sqrt(o[0]);
+  double Residual = sqrt(o[1]) / bnorm;
+  bool Converged = Residual < MinTol, Diverged = (Residual > MaxTol) || (Residual != Residual);
+  int k = 0;
+  if (!(Converged || Diverged)) {
+    if (richardson) k_row_sums<<<S.blocks, 256, 0, S.st>>>(n, h.d_rows.p, h.d_vals.p, M);
+    const double *d = richardson ? M : h.d_dvals.p;
+    for (k = 1; k <= Rounds; ++k) {
+      k_stationary_update<<<S.blocks, 256, 0, S.st>>>(n, d, R, b, x, (richardson && k == 1) ? 1 : 0);
+      h.st_launch++;
+      S.matvec(x, R); S.lin(b, 1.0, R, -1.0);
+      Residual = S.norm(R) / bnorm;
+      Converged = Residual < MinTol; Diverged = (Residual > MaxTol) || (Residual != Residual);
+      if (Converged || Diverged) break;
+    }
+  }
+  res.iters = std::min(k, Rounds); res.residual = Residual;
+  res.info = Converged ? HUTI_CONVERGENCE : (Diverged ? HUTI_DIVERGENCE : HUTI_MAXITER);
+  return res;
+}
+
 // counter-based uniform [0,1) generator for the IDR(s) shadow space when the caller passes none
 __global__ void k_shadow_space(long long n, double *P, unsigned long long seed) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -982,7 +1025,7 @@ static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int Ma
 // parsing and the error mapping (fem/src/IterSolve.F90:470-471, 913, 964-1005).
 void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *dpar, int method, int pc, const double *d_P) {
   B200_REQUIRE(h.have_vals, "b200_solve before b200_set_values");
-  B200_REQUIRE(method >= 1 && method <= 9, "unknown iterative method");
+  B200_REQUIRE(method >= 1 && method <= 11, "unknown iterative method");
   B200_REQUIRE(pc >= 0 && pc <= 2, "unknown preconditioner");
   const int n = h.n;
   cudaStream_t st = h.stream;
@@ -1008,6 +1051,8 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
     case B200_M_CGS: hr = run_cgs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
     case B200_M_TFQMR: hr = run_tfqmr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
     case B200_M_BICGSTAB2: hr = run_bicgstab2(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
+    case B200_M_JACOBI: hr = run_stationary(h, d_b, d_x, IPAR(10), DPAR(1), DPAR(2), false); break;
+    case B200_M_RICHARDSON: hr = run_stationary(h, d_b, d_x, IPAR(10), DPAR(1), DPAR(2), true); break;
     default: B200_REQUIRE(false, "unknown iterative method code");
   }
   B200_CUDA(cudaEventRecord(h.ev_end, st));

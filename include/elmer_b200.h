@@ -58,6 +58,8 @@ extern "C" {
 #define B200_METHOD_CGS       7   /* huti_dcgssolv (right-oriented preconditioning)   */
 #define B200_METHOD_TFQMR     8   /* huti_dtfqmrsolv (preconditioner in the LEFT slot) */
 #define B200_METHOD_BICGSTAB2 9   /* huti_dbicgstab_2solv (preconditioner in the LEFT slot) */
+#define B200_METHOD_JACOBI    10  /* itermethod_jacobi     (IterativeMethods.F90:297-393), no preconditioner */
+#define B200_METHOD_RICHARDSON 11 /* itermethod_richardson (405-521), lumped-matrix scaling, no preconditioner */
 #define B200_METHOD_GMRES     6   /* huti_dgmressolv; restart in ipar(15); preconditioner in the LEFT slot as IterSolver does (IterSolve.F90:509-525) */
 
 /* Linear System Preconditioning (IterSolve.F90:529-547) */

@@ -581,6 +581,37 @@ void huti_dgmressolv(Ops &op, int ndim, double *X, const double *B, int *ipar, d
 #undef H_
 }
 
+// IterativeMethods.F90:336-391 Jacobi and 444-519 Richardson (preconditioned with the lumped matrix): stationary iterations, no
+// preconditioner callback.  `iters` = rounds performed.
+static void StationaryIteration(Ops &op, int n, double *x, const double *b, int Rounds, double MinTol, double MaxTol, double &Residual,
+                                bool &Converged, bool &Diverged, bool richardson, int *iters) {
+  const Matrix &A = *op.A;
+  std::vector<double> r(n), M(n);
+  Converged = Diverged = false; *iters = 0;
+  op.matvec(x, r.data());
+  for (int i = 0; i < n; ++i) r[i] = b[i] - r[i];
+  const double bnorm = op.norm(n, b);
+  double rnorm = op.norm(n, r.data());
+  Residual = rnorm / bnorm;
+  Converged = Residual < MinTol;
+  Diverged = (Residual > MaxTol) || (Residual != Residual);
+  if (Converged || Diverged) return;
+  if (richardson)
+    for (int i = 0; i < n; ++i) { double s = 0.0; for (int j = A.Rows[i] - 1; j < A.Rows[i + 1] - 1; ++j) s = s + A.Values[j]; M[i] = s; }
+  for (int k = 1; k <= Rounds; ++k) {
+    *iters = k;
+    if (richardson) { for (int i = 0; i < n; ++i) x[i] = (k == 1) ? b[i] / M[i] : x[i] + r[i] / M[i]; }
+    else for (int j = 0; j < n; ++j) x[j] = x[j] + r[j] / A.Values[A.Diag[j] - 1];
+    op.matvec(x, r.data());
+    for (int i = 0; i < n; ++i) r[i] = b[i] - r[i];
+    rnorm = op.norm(n, r.data());
+    Residual = rnorm / bnorm;
+    Converged = Residual < MinTol;
+    Diverged = (Residual > MaxTol) || (Residual != Residual);
+    if (Converged || Diverged) break;
+  }
+}
+
 // fhutiter/src/huti_cgs.F90:283-470 huti_dcgssolv.  work(n,7) = RTLD,P,Q,U,T1V,T2V,R.  Right-oriented preconditioning.
 void huti_dcgssolv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar, double *work) {
   const size_t N = (size_t)ndim;
@@ -1390,6 +1421,13 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
     bool Converged = false, Diverged = false; int iters = 0;
     RealIDRS(op, n, x, b, HUTI_MAXIT, HUTI_TOLERANCE, HUTI_MAXTOLERANCE, Converged, Diverged,
              HUTI_DBUGLVL, HUTI_IDRS_S, HUTI_SMOOTHING == 1, P, &iters, &res);
+    if (Converged) HUTI_INFO = HUTI_CONVERGENCE;
+    if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
+    if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;
+    HUTI_ITERS = iters; dpar[9] = res;
+  } else if (method == 10 || method == 11) {
+    bool Converged = false, Diverged = false; int iters = 0;
+    StationaryIteration(op, n, x, b, HUTI_MAXIT, HUTI_TOLERANCE, HUTI_MAXTOLERANCE, res, Converged, Diverged, method == 11, &iters);
     if (Converged) HUTI_INFO = HUTI_CONVERGENCE;
     if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
     if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;

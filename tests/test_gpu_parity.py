@@ -468,7 +468,7 @@ def test_reference_linearsolvers_case_gpu(oracle, b200):
     from linearsolvers_case import tempdist_system, compute_norm
     from test_oracle_golden import LINSOLVERS
     for k, (method, kw) in enumerate(LINSOLVERS):
-        k = float(k + 5)
+        k = float(k + 4)
         S, b, x0 = tempdist_system(k)
         A = oracle.CRS.from_scipy(S)
         M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 1); M.set_values(A.vals)
@@ -563,4 +563,41 @@ def test_bilu_bit_exact(oracle, b200):
     got0 = M.itersolver(b, None, sif.replace("BILU", "ILU0"), 0)                    # back to plain ILU0 on the same handle
     ref0 = oracle.itersolve(A, b, method="cg", precond="ilu0", tol=TOL, maxit=2000)
     assert got0["info"] == 1 and iters_close(got0["iters"], ref0["iters"])
+    M.close()
+
+
+def test_stationary_methods(oracle, b200):
+    """itermethod_jacobi / itermethod_richardson (IterativeMethods.F90:297-521).  Jacobi on the reference's own linearsolvers case
+    (TempDist.sif:71-76: `Reference Norm = 3`); Richardson (lumped-matrix scaling, meant for mass matrices) on a diagonally dominant system."""
+    import sys, os
+    import scipy.sparse as sp
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from linearsolvers_case import tempdist_system, compute_norm
+    S, b, x0 = tempdist_system(3.0)
+    A = oracle.CRS.from_scipy(S)
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, 1); M.set_values(A.vals)
+    M.scale_system()
+    ref = oracle.solve_linear_system(A, b, x0=x0, method="jacobi", precond="none", tol=1e-12, maxit=3500)
+    got = M.solve(b, x0=x0, method="jacobi", precond="none", tol=1e-12, maxit=3500)
+    assert got["info"] == ref["info"] == 1 and iters_close(got["iters"], ref["iters"]), (got["iters"], ref["iters"])
+    assert abs(compute_norm(got["x"]) - 3.0) <= 1e-5 * 3.0
+    M.close()
+    A2, _ = oracle.heat_cube(8, faces=["x0"], source=1.0)
+    Sm = (sp.identity(A2.n) * 3.0 + 0.1 * abs(A2.to_scipy())).tocsr()       # mass-matrix-like: positive entries, dominant diagonal
+    Am = oracle.CRS.from_scipy(Sm)
+    bm = np.random.RandomState(61).standard_normal(Am.n)
+    M = b200.Matrix(); M.set_structure(Am.rows, Am.cols, Am.diag, 1, 1); M.set_values(Am.vals)
+    for method in ("richardson", "jacobi"):
+        ref = oracle.itersolve(Am, bm, method=method, precond="none", tol=1e-10, maxit=500)
+        got = M.solve(bm, method=method, precond="none", tol=1e-10, maxit=500)
+        assert got["info"] == ref["info"] == 1 and got["iters"] == ref["iters"], (method, got["iters"], ref["iters"])
+        assert rel_l2(got["x"], ref["x"]) <= 1e-9
+    sif = """
+      Linear System Solver = Iterative
+      Linear System Iterative Method = Richardson
+      Linear System Max Iterations = 500
+      Linear System Convergence Tolerance = 1.0e-10
+    """
+    got = M.itersolver(bm, None, sif, 0)
+    assert got is not None and got["info"] == 1
     M.close()
