@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libelmer_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "elmer_b200.h")
 
-METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8, "bicgstab2": 9, "jacobi": 10, "richardson": 11}
+METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8, "bicgstab2": 9, "jacobi": 10, "richardson": 11, "sgs": 12}
 PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2}
 DECLINED = 100
 
@@ -106,7 +106,7 @@ def _check(rc, what):
 
 
 def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residual_output=0,
-                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10):
+                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10, sgs_omega=None):
     """HUTI ipar(50)/dpar(10) exactly as IterSolver fills them (fem/src/IterSolve.F90:245-503;
     slots fhutiter/src/huti_fdefs.h:101-155)."""
     ipar = np.zeros(50, dtype=np.int32)
@@ -129,6 +129,7 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
         ipar[17] = idrs_s
     ipar[27] = 1 if smoothing else 0
     dpar[0] = tol
+    dpar[2] = float(np.float32(1.8)) if sgs_omega is None else sgs_omega     # HUTI_SGSPARAM (IterSolve.F90:354-358)
     dpar[1] = maxtol
     return ipar, dpar
 

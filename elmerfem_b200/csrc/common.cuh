@@ -258,6 +258,7 @@ void tri_analyse(Handle &h);                           // levels + L/U level-sor
 void ilu0_factor(Handle &h);                           // d_ilu from d_prec/d_vals, refresh L/U values
 void lu_apply(Handle &h, double *u, const double *v);  // u = (LU)^-1 v   (device pointers)
 void diag_apply(Handle &h, double *u, const double *v);
+void sgs_sweeps(Handle &h, const double *b, double *x, double *t1, double *t2, double omega);   // one forward + one backward Gauss-Seidel sweep
 void tritask_analyse(Handle &h);                       // task-mode plans for both sweeps (host, once per structure)
 void tritask_refresh_values(Handle &h);                // copy the ILU values into the plans' streams
 void tritask_release(Handle &h);

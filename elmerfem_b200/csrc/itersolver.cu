@@ -97,12 +97,13 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     else if (m == "bicgstab2") method = B200_METHOD_BICGSTAB2;
     else if (m == "jacobi") method = B200_METHOD_JACOBI;
     else if (m == "richardson") method = B200_METHOD_RICHARDSON;
-    else if (m == "sgs")
+    else if (m == "sgs") method = B200_METHOD_SGS;
+    else if (false)
       throw Declined{"iterative method '" + m + "' is not on the accelerated path"};
     else method = B200_METHOD_BICGSTAB;                                  // CASE DEFAULT (313-314)
     if (P.logical("Linear System Complex") || P.logical("Linear System Pseudo Complex"))
       throw Declined{"complex / pseudo-complex systems"};
-    const bool internal = (method >= B200_METHOD_BICGSTABL && method <= B200_METHOD_IDRS) || method == B200_METHOD_JACOBI || method == B200_METHOD_RICHARDSON;
+    const bool internal = (method >= B200_METHOD_BICGSTABL && method <= B200_METHOD_IDRS) || method == B200_METHOD_JACOBI || method == B200_METHOD_RICHARDSON || method == B200_METHOD_SGS;
     // ---- work sizes and method parameters (327-392)
     ipar[3] = internal ? 1 : (method == B200_METHOD_CG ? 4 : 8);
     if (method == B200_METHOD_CGS) ipar[3] = 7;                         // HUTI_CGS_WORKSIZE
@@ -124,6 +125,10 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
       int l = P.integer("BiCGstabl polynomial degree", 2, &found);
       B200_REQUIRE(!found || l >= 2, "'BiCGstabl polynomial degree' < 2");
       ipar[15] = l;
+    }
+    if (method == B200_METHOD_SGS) {                                    // 354-359: the default is the single-precision literal 1.8
+      double om = P.real("SGS Overrelaxation Factor", 0.0, &found);
+      dpar[2] = found ? om : (double)1.8f;
     }
     if (method == B200_METHOD_IDRS) {
       int s = P.integer("IDRS parameter", 4, &found);

@@ -884,6 +884,34 @@ static HostResult run_stationary(Handle &h, const double *b, double *x, int Roun
   return res;
 }
 
+// IterativeMethods.F90:219-283 SGS: rounds of one forward + one backward Gauss-Seidel sweep, the true residual after each round.
+static HostResult run_sgs(Handle &h, const double *b, double *x, int Rounds, double MinTol, double MaxTol, double omega) {
+  HostResult res;
+  B200_REQUIRE(h.nranks == 1, "SGS is implemented for single-rank handles only");
+  Solver S(h, 0, 3);
+  const int n = S.n;
+  double *R = S.vec[0], *T1 = S.vec[1], *T2 = S.vec[2];
+  S.matvec(x, R); S.lin(b, 1.0, R, -1.0);
+  double o[2];
+  { const double *xs[2] = {b, R}, *ys[2] = {b, R}; S.dots(2, xs, ys, o); }
+  const double bnorm = sqrt(o[0]);
+  double Residual = sqrt(o[1]) / bnorm;
+  bool Converged = Residual < MinTol, Diverged = (Residual > MaxTol) || (Residual != Residual);
+  int k = 0;
+  if (!(Converged || Diverged)) {
+    for (k = 1; k <= Rounds; ++k) {
+      sgs_sweeps(h, b, x, T1, T2, omega);
+      S.matvec(x, R); S.lin(b, 1.0, R, -1.0);
+      Residual = S.norm(R) / bnorm;
+      Converged = Residual < MinTol; Diverged = (Residual > MaxTol) || (Residual != Residual);
+      if (Converged || Diverged) break;
+    }
+  }
+  res.iters = std::min(k, Rounds); res.residual = Residual;
+  res.info = Converged ? HUTI_CONVERGENCE : (Diverged ? HUTI_DIVERGENCE : HUTI_MAXITER);
+  return res;
+}
+
 // counter-based uniform [0,1) generator for the IDR(s) shadow space when the caller passes none
 __global__ void k_shadow_space(long long n, double *P, unsigned long long seed) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1025,7 +1053,7 @@ static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int Ma
 // parsing and the error mapping (fem/src/IterSolve.F90:470-471, 913, 964-1005).
 void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *dpar, int method, int pc, const double *d_P) {
   B200_REQUIRE(h.have_vals, "b200_solve before b200_set_values");
-  B200_REQUIRE(method >= 1 && method <= 11, "unknown iterative method");
+  B200_REQUIRE(method >= 1 && method <= 12, "unknown iterative method");
   B200_REQUIRE(pc >= 0 && pc <= 2, "unknown preconditioner");
   const int n = h.n;
   cudaStream_t st = h.stream;
@@ -1053,6 +1081,7 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
     case B200_M_BICGSTAB2: hr = run_bicgstab2(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
     case B200_M_JACOBI: hr = run_stationary(h, d_b, d_x, IPAR(10), DPAR(1), DPAR(2), false); break;
     case B200_M_RICHARDSON: hr = run_stationary(h, d_b, d_x, IPAR(10), DPAR(1), DPAR(2), true); break;
+    case B200_M_SGS: hr = run_sgs(h, d_b, d_x, IPAR(10), DPAR(1), DPAR(2), DPAR(3)); break;
     default: B200_REQUIRE(false, "unknown iterative method code");
   }
   B200_CUDA(cudaEventRecord(h.ev_end, st));

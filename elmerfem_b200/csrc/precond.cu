@@ -479,6 +479,88 @@ __global__ void __launch_bounds__(256, 1) k_sptrsv_wide(SellView T, const int *_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Symmetric Gauss-Seidel sweeps of itermethod_sgs (IterativeMethods.F90:219-283): forward i = 1..n, then backward i = n..1,
+//   s = sum_j A_ij x_j (current x, left to right) ;  x_i = x_i + Omega * (b_i - s) / a_ii.
+// The same wavefront as the triangular solves, on the matrix itself: rows in dependency-level order (the L / U plans of the
+// matrix pattern), a row's already-updated operands (j < i forward, j > i backward) are polled from the sentinel-filled
+// output vector, the others come from the input vector.  One lane walks one CRS row, so the sum runs in column order with
+// separate roundings exactly as the reference loop.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256, 2) k_sgs_sweep(int nslices, const int *__restrict__ perm, const int *__restrict__ slice_level,
+                                                       const int *__restrict__ lvl_slices, int *lvl_done, int lookahead, unsigned gate_sleep,
+                                                       const int *__restrict__ rows, const int *__restrict__ cols, const int *__restrict__ diag,
+                                                       const double *__restrict__ vals, const double *__restrict__ b, double omega,
+                                                       const double *__restrict__ xin, double *xout, Ctrl *ctrl) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slice = gwarp; slice < nslices; slice += nwarps) {
+    const int r = perm[slice * 32 + lane];
+    long long spins = 0;
+    const int wl = slice_level[slice] - lookahead;
+    if (lane == 0 && wl >= 0) {
+      const int need = lvl_slices[wl];
+      while (ld_relaxed_i(lvl_done + wl * 32) < need) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        if (gate_sleep) __nanosleep(gate_sleep);
+      }
+    }
+    __syncwarp();
+    if (r >= 0) {
+      double s = 0.0;
+      for (int p = rows[r]; p < rows[r + 1]; ++p) {
+        const int c = cols[p];
+        double xv;
+        if (BACKWARD ? (c > r) : (c < r)) {
+          xv = ld_relaxed(xout + c);
+          while (is_sentinel(xv)) {
+            if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+            xv = ld_relaxed(xout + c);
+          }
+        } else xv = xin[c];
+        s = nfma(s, xv, vals[p]);
+      }
+      double xn = __dadd_rn(xin[r], __ddiv_rn(__dmul_rn(omega, __dsub_rn(b[r], s)), vals[diag[r]]));
+      if (xn != xn) xn = __longlong_as_double((long long)CANON_NAN);
+      st_relaxed(xout + r, xn);
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(lvl_done + slice_level[slice] * 32, 1);
+  }
+}
+__global__ void k_sgs_prepare(int n, double *a, double *b2, int *counters, int ncounters) {
+  const double sent = __longlong_as_double((long long)SENTINEL);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
+  for (int i = i0; i < n; i += st) { a[i] = sent; b2[i] = sent; }
+  for (int i = i0; i < ncounters; i += st) counters[i * 32] = 0;
+}
+// x <- one forward and one backward sweep; t1, t2: work vectors of length n
+void sgs_sweeps(Handle &h, const double *b, double *x, double *t1, double *t2, double omega) {
+  B200_REQUIRE(h.have_vals, "SGS before b200_set_values");
+  if (h.n == 0) return;
+  if (h.ilu_sep()) { h.ilu_order = 0; h.bilu_blocks = 0; ilu_invalidate(h); }     // the sweeps need the plans of the matrix pattern itself
+  tri_analyse(h);
+  cudaStream_t st = h.stream;
+  static int grid_f = 0, grid_b = 0;
+  if (!grid_f) {
+    grid_f = persistent_blocks((const void *)k_sgs_sweep<false>, 256, 0);
+    grid_b = persistent_blocks((const void *)k_sgs_sweep<true>, 256, 0);
+  }
+  k_sgs_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, st>>>(h.n, t1, t2, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
+  const int la = h.tri_lookahead; const unsigned gs = h.tri_gate_sleep;
+  const int bf = std::max(1, std::min(grid_f, (h.L.nslices + 7) / 8)), bb = std::max(1, std::min(grid_b, (h.U.nslices + 7) / 8));
+  launch_coresident((const void *)k_sgs_sweep<false>, bf, 256, st, h.L.nslices, (const int *)h.L.perm.p, (const int *)h.L.gate.p, (const int *)h.d_lvlcnt_f.p,
+                    h.tri_counters.p, la, gs, (const int *)h.d_rows.p, (const int *)h.d_cols.p, (const int *)h.d_diag.p, (const double *)h.d_vals.p, b, omega,
+                    (const double *)x, t1, h.ctrl.p);
+  launch_coresident((const void *)k_sgs_sweep<true>, bb, 256, st, h.U.nslices, (const int *)h.U.perm.p, (const int *)h.U.gate.p, (const int *)h.d_lvlcnt_b.p,
+                    h.tri_counters.p + (size_t)(h.nlev_f + 1) * 32, la, gs, (const int *)h.d_rows.p, (const int *)h.d_cols.p, (const int *)h.d_diag.p,
+                    (const double *)h.d_vals.p, b, omega, (const double *)t1, t2, h.ctrl.p);
+  B200_CUDA(cudaMemcpyAsync(x, t2, (size_t)h.n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  B200_CUDA(cudaGetLastError());
+  h.st_launch += 3;
+}
+
 __global__ void k_tri_prepare(int na, double *a, int nb, double *b, int *counters, int ncounters) {
   const double sent = __longlong_as_double((long long)SENTINEL);
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;

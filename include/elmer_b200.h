@@ -60,6 +60,7 @@ extern "C" {
 #define B200_METHOD_BICGSTAB2 9   /* huti_dbicgstab_2solv (preconditioner in the LEFT slot) */
 #define B200_METHOD_JACOBI    10  /* itermethod_jacobi     (IterativeMethods.F90:297-393), no preconditioner */
 #define B200_METHOD_RICHARDSON 11 /* itermethod_richardson (405-521), lumped-matrix scaling, no preconditioner */
+#define B200_METHOD_SGS       12  /* itermethod_sgs (IterativeMethods.F90:179-285); Omega in dpar(3) (HUTI_SGSPARAM)   */
 #define B200_METHOD_GMRES     6   /* huti_dgmressolv; restart in ipar(15); preconditioner in the LEFT slot as IterSolver does (IterSolve.F90:509-525) */
 
 /* Linear System Preconditioning (IterSolve.F90:529-547) */

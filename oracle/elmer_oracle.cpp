@@ -612,6 +612,43 @@ static void StationaryIteration(Ops &op, int n, double *x, const double *b, int 
   }
 }
 
+// IterativeMethods.F90:219-283 SGS.
+static void SGS(Ops &op, int n, double *x, const double *b, int Rounds, double MinTol, double MaxTol, double &Residual, bool &Converged,
+                bool &Diverged, double Omega, int *iters) {
+  const Matrix &A = *op.A;
+  const int *Rows = A.Rows, *Cols = A.Cols; const double *Values = A.Values;
+  std::vector<double> r(n);
+  Converged = Diverged = false; *iters = 0;
+  op.matvec(x, r.data());
+  for (int i = 0; i < n; ++i) r[i] = b[i] - r[i];
+  const double bnorm = op.norm(n, b);
+  double rnorm = op.norm(n, r.data());
+  Residual = rnorm / bnorm;
+  Converged = Residual < MinTol;
+  Diverged = (Residual > MaxTol) || (Residual != Residual);
+  if (Converged || Diverged) return;
+  for (int k = 1; k <= Rounds; ++k) {
+    *iters = k;
+    for (int i = 1; i <= n; ++i) {
+      double s = 0.0;
+      for (int j = Rows[i - 1]; j <= Rows[i] - 1; ++j) s = s + x[Cols[j - 1] - 1] * Values[j - 1];
+      x[i - 1] = x[i - 1] + Omega * (b[i - 1] - s) / Values[A.Diag[i - 1] - 1];
+    }
+    for (int i = n; i >= 1; --i) {
+      double s = 0.0;
+      for (int j = Rows[i - 1]; j <= Rows[i] - 1; ++j) s = s + x[Cols[j - 1] - 1] * Values[j - 1];
+      x[i - 1] = x[i - 1] + Omega * (b[i - 1] - s) / Values[A.Diag[i - 1] - 1];
+    }
+    op.matvec(x, r.data());
+    for (int i = 0; i < n; ++i) r[i] = b[i] - r[i];
+    rnorm = op.norm(n, r.data());
+    Residual = rnorm / bnorm;
+    Converged = Residual < MinTol;
+    Diverged = (Residual > MaxTol) || (Residual != Residual);
+    if (Converged || Diverged) return;
+  }
+}
+
 // fhutiter/src/huti_cgs.F90:283-470 huti_dcgssolv.  work(n,7) = RTLD,P,Q,U,T1V,T2V,R.  Right-oriented preconditioning.
 void huti_dcgssolv(Ops &op, int ndim, double *X, const double *B, int *ipar, double *dpar, double *work) {
   const size_t N = (size_t)ndim;
@@ -1421,6 +1458,13 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
     bool Converged = false, Diverged = false; int iters = 0;
     RealIDRS(op, n, x, b, HUTI_MAXIT, HUTI_TOLERANCE, HUTI_MAXTOLERANCE, Converged, Diverged,
              HUTI_DBUGLVL, HUTI_IDRS_S, HUTI_SMOOTHING == 1, P, &iters, &res);
+    if (Converged) HUTI_INFO = HUTI_CONVERGENCE;
+    if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
+    if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;
+    HUTI_ITERS = iters; dpar[9] = res;
+  } else if (method == 12) {
+    bool Converged = false, Diverged = false; int iters = 0;
+    SGS(op, n, x, b, HUTI_MAXIT, HUTI_TOLERANCE, HUTI_MAXTOLERANCE, res, Converged, Diverged, DPAR(3), &iters);
     if (Converged) HUTI_INFO = HUTI_CONVERGENCE;
     if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
     if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8, "bicgstab2": 9, "jacobi": 10, "richardson": 11}
+METHODS = {"cg": 1, "bicgstab": 2, "bicgstabl": 3, "gcr": 4, "idrs": 5, "gmres": 6, "cgs": 7, "tfqmr": 8, "bicgstab2": 9, "jacobi": 10, "richardson": 11, "sgs": 12}
 PRECONDS = {"none": 0, "diagonal": 1, "ilu0": 2, "ilu": 2, "ilu1": 2, "ilu2": 2, "ilu3": 2}
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -130,7 +130,7 @@ def dnrm2(x):
 
 # ------------------------------------------------------------------ IterSolver
 def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residual_output=0,
-                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10):
+                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10, sgs_omega=None):
     """ipar/dpar exactly as IterSolver fills them (IterSolve.F90:245-503), HUTI slots per
     fhutiter/src/huti_fdefs.h:101-155."""
     ipar = np.zeros(50, dtype=np.int32)
@@ -154,6 +154,7 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
         ipar[18 - 1] = idrs_s
     ipar[28 - 1] = 1 if smoothing else 0
     dpar[1 - 1] = tol
+    dpar[3 - 1] = float(np.float32(1.8)) if sgs_omega is None else sgs_omega     # HUTI_SGSPARAM; the default is the REAL literal 1.8 (IterSolve.F90:358)
     dpar[2 - 1] = maxtol
     return ipar, dpar
 
