@@ -63,6 +63,8 @@ def lib():
         "b200_get_halo_plan": [vpp, ip, ip, ip, ip, ip, ip],
         "b200_get_stats": [vpp, dp], "b200_time_matvec": [vpp, ip, dp], "b200_time_lu_precondition": [vpp, ip, dp],
         "b200_partition_send_lists": [ip] * 10, "b200_partition_peer_layout": [ip, ip, ip, ip, C.POINTER(C.c_longlong)], "b200_partition_split": [ip] * 14,
+        "b200_node_graph": [ip, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_longlong), ip, ip],
+        "b200_optimize_bandwidth": [ip] * 9, "b200_initialize_structure": [ip] * 11,
         "b200_version": [ip, ip], "b200_vec_len": [vpp, C.POINTER(C.c_longlong)],
     }
     for name, args in sigs.items():
@@ -390,3 +392,60 @@ def partition_split(rows, cols_global, lo, hi, ghost_gid, index_base=1):
     g_r = np.zeros(n + 1, dtype=np.int32); g_c = np.zeros(max(int(sizes[1]), 1), dtype=np.int32)
     _check(lib().b200_partition_split(*head, _ip(sizes), _ip(oo_r), _ip(oo_c), _ip(oo_d), _ip(g_r), _ip(g_c)), "b200_partition_split")
     return dict(oo_rows=oo_r, oo_cols=oo_c[:sizes[0]], oo_diag=oo_d[:n], g_rows=g_r, g_cols=g_c[:sizes[1]])
+
+
+def node_graph(elem_ptr, elem_nodes, n_nodes, perm=None, k=None, index_base=1):
+    """Host-only: the list matrix MakeListMatrix builds for plain nodal elements (ElementUtils.F90:881-891) as CRS
+    rows/cols in index_base numbering.  perm = Elmer's Perm (1-based rows, 0 = inactive) or None (identity)."""
+    ep = np.ascontiguousarray(elem_ptr, dtype=np.int32); en = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+    pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    if k is None:
+        k = n_nodes if pm is None else int(pm.max(initial=0))
+    nnz = C.c_longlong(0)
+    head = (_i(ep.size - 1), _ip(ep), _ip(en), _i(index_base), _i(n_nodes), None if pm is None else _ip(pm), _i(k), C.byref(nnz))
+    _check(lib().b200_node_graph(*head, None, None), "b200_node_graph")
+    rows = np.zeros(k + 1, dtype=np.int32); cols = np.zeros(max(nnz.value, 1), dtype=np.int32)
+    _check(lib().b200_node_graph(*head, _ip(rows), _ip(cols)), "b200_node_graph")
+    return rows, cols[:nnz.value]
+
+
+def optimize_bandwidth(rows, cols, perm, optimize=True, use_optimized=False, index_base=1):
+    """Host-only: OptimizeBandwidth (BandwidthOptimize.F90:182-445).  Returns (new Perm, half bandwidth)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32); cols = np.ascontiguousarray(cols, dtype=np.int32)
+    pm = np.array(perm, dtype=np.int32)
+    hb = C.c_int(0)
+    _check(lib().b200_optimize_bandwidth(_i(rows.size - 1), _ip(rows), _ip(cols), _i(index_base), _i(pm.size), _ip(pm),
+                                         _i(1 if optimize else 0), _i(1 if use_optimized else 0), C.byref(hb)), "b200_optimize_bandwidth")
+    return pm, hb.value
+
+
+def initialize_structure(rows, cols, dofs, perm_initial=None, perm=None, index_base=1):
+    """Host-only: InitializeMatrix + CRS_SortMatrix (ElementUtils.F90:1631-1732): node graph -> (Rows, Cols, Diag)
+    with `dofs` interleaved unknowns per node, renumbered from perm_initial to perm when both are given."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32); cols = np.ascontiguousarray(cols, dtype=np.int32)
+    k = rows.size - 1
+    nnz = int(rows[-1] - rows[0])
+    R = np.zeros(k * dofs + 1, dtype=np.int32); Cc = np.zeros(max(nnz * dofs * dofs, 1), dtype=np.int32); D = np.zeros(max(k * dofs, 1), dtype=np.int32)
+    if perm is None:
+        ps, p0, p1 = None, None, None
+    else:
+        a = np.ascontiguousarray(perm_initial, dtype=np.int32); b = np.ascontiguousarray(perm, dtype=np.int32)
+        ps, p0, p1 = _i(a.size), _ip(a), _ip(b)
+    _check(lib().b200_initialize_structure(_i(k), _ip(rows), _ip(cols), _i(index_base), _i(dofs), ps, p0, p1, _ip(R), _ip(Cc), _ip(D)),
+           "b200_initialize_structure")
+    return R, Cc[:nnz * dofs * dofs], D[:k * dofs]
+
+
+def create_matrix_structure(elem_ptr, elem_nodes, n_nodes, dofs=1, optimize_bw=True, use_optimized=False, perm=None):
+    """The nodal path of CreateMatrix (ElementUtils.F90:1745-2170) from the three host-only steps above: initial Perm
+    (identity when the equation covers the mesh, 1918-1925), list matrix, OptimizeBandwidth, InitializeMatrix.
+    Returns dict(perm, half_bandwidth, rows, cols, diag) with Elmer's 1-based arrays."""
+    perm0 = np.arange(1, n_nodes + 1, dtype=np.int32) if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    k = int(perm0.max(initial=0))
+    lrows, lcols = node_graph(elem_ptr, elem_nodes, n_nodes, perm0, k)
+    perm1, hb = optimize_bandwidth(lrows, lcols, perm0, optimize_bw, use_optimized)
+    if optimize_bw:
+        R, Cc, D = initialize_structure(lrows, lcols, dofs, perm0, perm1)
+    else:
+        R, Cc, D = initialize_structure(lrows, lcols, dofs)
+    return dict(perm=perm1, half_bandwidth=hb, rows=R, cols=Cc, diag=D, list_rows=lrows, list_cols=lcols)

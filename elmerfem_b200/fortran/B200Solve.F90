@@ -105,6 +105,23 @@ MODULE B200Interface
       IMPORT; INTEGER(C_INTPTR_T) :: handle
       INTEGER(C_INT) :: gn, n_own, nnz, rows(*), cols(*), goffset(*), index_base, ndeg
     END FUNCTION
+    ! matrix-structure producer (host-only): what CreateMatrix does for nodal elements (ElementUtils.F90:1745-2170);
+    ! perm = Solver % Variable % Perm, arrays 1-based (index_base = 1)
+    INTEGER(C_INT) FUNCTION b200_node_graph(n_elems, elem_ptr, elem_nodes, index_base, n_nodes, perm, k, nnz, rows, cols) &
+        BIND(C, NAME="b200_node_graph")
+      IMPORT; INTEGER(C_INT) :: n_elems, elem_ptr(*), elem_nodes(*), index_base, n_nodes, perm(*), k
+      INTEGER(C_LONG_LONG) :: nnz
+      TYPE(C_PTR), VALUE :: rows, cols          ! C_NULL_PTR on the sizing call
+    END FUNCTION
+    INTEGER(C_INT) FUNCTION b200_optimize_bandwidth(k, rows, cols, index_base, perm_size, perm, optimize, &
+        use_optimized, half_bandwidth) BIND(C, NAME="b200_optimize_bandwidth")
+      IMPORT; INTEGER(C_INT) :: k, rows(*), cols(*), index_base, perm_size, perm(*), optimize, use_optimized, half_bandwidth
+    END FUNCTION
+    INTEGER(C_INT) FUNCTION b200_initialize_structure(k, rows, cols, index_base, dofs, perm_size, perm_initial, perm, &
+        out_rows, out_cols, out_diag) BIND(C, NAME="b200_initialize_structure")
+      IMPORT; INTEGER(C_INT) :: k, rows(*), cols(*), index_base, dofs, perm_size, perm_initial(*), perm(*)
+      INTEGER(C_INT) :: out_rows(*), out_cols(*), out_diag(*)
+    END FUNCTION
     FUNCTION b200_last_error() RESULT(msg) BIND(C, NAME="b200_last_error")
       IMPORT; TYPE(C_PTR) :: msg
     END FUNCTION

@@ -185,6 +185,32 @@ int b200_partition_split(const int *n_own, const int *rows, const int *cols, con
                          const int *nghost, const int *ghost_gid, int *sizes, int *oo_rows, int *oo_cols, int *oo_diag,
                          int *g_rows, int *g_cols);
 
+/* ---- matrix structure producer (host-only, no GPU needed) ------------------ */
+/* Node graph of a nodal discretisation, i.e. the list matrix MakeListMatrix builds for plain nodal elements
+ * (fem/src/ElementUtils.F90:881-891; rows ascending and duplicate-free as List_GetMatrixIndex keeps them,
+ * fem/src/ListMatrix.F90:334-386).  elem_ptr[n_elems+1] are 0-based offsets into elem_nodes, which holds node numbers in
+ * index_base numbering, bulk elements first, then boundary elements, as Mesh % Elements stores them.  perm[n_nodes]
+ * is Elmer's Perm (value = 1-based row of the node, <= 0: node not in the equation); NULL = every node, identity
+ * (what CreateMatrix uses when the equation covers the mesh, ElementUtils.F90:1918-1925).  k = number of rows.
+ * First call with rows = cols = NULL returns *nnz; then rows[k+1], cols[nnz] in index_base numbering. */
+int b200_node_graph(const int *n_elems, const int *elem_ptr, const int *elem_nodes, const int *index_base,
+                    const int *n_nodes, const int *perm, const int *k, long long *nnz, int *rows, int *cols);
+/* OptimizeBandwidth (fem/src/BandwidthOptimize.F90:182-445) on that graph: depth-first level search for the start
+ * node (Levelize, 375-434, including the start-node update at 266-269 exactly as written), Cuthill-McKee sweep with
+ * neighbours in ascending order (289-307), reversed numbering (312-323); the new numbering is accepted only if the
+ * half bandwidth does not grow unless *use_optimized (`Optimize Bandwidth Use Always`) (334-339).  perm[perm_size] is
+ * updated in place exactly as the reference updates Perm; *half_bandwidth = the function's result.  With
+ * *optimize == 0 only the initial half bandwidth is computed (`Optimize Bandwidth = False`). */
+int b200_optimize_bandwidth(const int *k, const int *rows, const int *cols, const int *index_base, const int *perm_size,
+                            int *perm, const int *optimize, const int *use_optimized, int *half_bandwidth);
+/* InitializeMatrix + CRS_SortMatrix (fem/src/ElementUtils.F90:1631-1732, fem/src/CRSMatrix.F90:188-246): expands the
+ * node graph (in the INITIAL numbering perm_initial describes) to the dofs-per-node CRS structure in the numbering
+ * of perm (both NULL: no reordering).  out_rows[dofs*k+1], out_cols[dofs*dofs*nnz], out_diag[dofs*k] in index_base
+ * numbering, ready for b200_set_structure (ndeg = dofs).  out_cols/out_diag may be NULL to get the row pointers only. */
+int b200_initialize_structure(const int *k, const int *rows, const int *cols, const int *index_base, const int *dofs,
+                              const int *perm_size, const int *perm_initial, const int *perm, int *out_rows,
+                              int *out_cols, int *out_diag);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* stats[0] last solve device ms (CUDA events on the solve stream), [1] matvec calls, [2] precond
  * applications, [3] last factorisation device ms, [4] kernels launched by the last solve,

@@ -54,6 +54,10 @@ def lib():
     L.orc_scale_system.restype = C.c_double
     L.orc_scale_system.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _dp]
     L.orc_backscale_system.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, C.c_double]
+    L.orc_make_list_matrix.restype = C.c_long
+    L.orc_make_list_matrix.argtypes = [C.c_int, _ip, _ip, _ip, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_optimize_bandwidth.argtypes = [C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, C.c_int]
+    L.orc_initialize_matrix.argtypes = [C.c_int, _ip, _ip, C.c_int, C.c_void_p, C.c_void_p, _ip, _ip, _ip]
     L.orc_set_threads.argtypes = [C.c_int]
     L.orc_max_threads.restype = C.c_int
     _LIB = L
@@ -225,3 +229,43 @@ def solve_linear_system(A, b, x0=None, scaling=True, **kw):
     r["x"] = x
     r["norm"] = float(np.sqrt(np.sum(x * x) / A.n))   # ComputeNorm, SolverUtils.F90:10290
     return r
+
+
+def make_list_matrix(elem_ptr, elem_nodes, reorder, k):
+    """MakeListMatrix, plain nodal branch (ElementUtils.F90:881-891): 1-based CRS of the list matrix."""
+    ep = np.ascontiguousarray(elem_ptr, dtype=np.int32); en = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+    ro = np.ascontiguousarray(reorder, dtype=np.int32)
+    nnz = lib().orc_make_list_matrix(ep.size - 1, ep, en, ro, k, None, None)
+    rows = np.zeros(k + 1, dtype=np.int32); cols = np.zeros(max(nnz, 1), dtype=np.int32)
+    lib().orc_make_list_matrix(ep.size - 1, ep, en, ro, k, rows.ctypes.data, cols.ctypes.data)
+    return rows, cols[:nnz]
+
+
+def optimize_bandwidth(rows, cols, perm, optimize=True, use_optimized=False):
+    """OptimizeBandwidth (BandwidthOptimize.F90:182-445) with InvInitialReorder built as CreateMatrix does
+    (ElementUtils.F90:1955-1958).  Returns (Perm, HalfBandWidth)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32); cols = np.ascontiguousarray(cols, dtype=np.int32)
+    pm = np.array(perm, dtype=np.int32)
+    k = rows.size - 1
+    inv = np.zeros(max(k, 1), dtype=np.int32)
+    for i in np.nonzero(pm > 0)[0]:
+        inv[pm[i] - 1] = i + 1
+    hb = lib().orc_optimize_bandwidth(k, rows, cols, pm.size, pm, inv, int(optimize), int(use_optimized))
+    return pm, hb
+
+
+def initialize_matrix(rows, cols, dofs, perm_initial=None, perm=None):
+    """InitializeMatrix + CRS_SortMatrix (ElementUtils.F90:1631-1732).  Returns 1-based (Rows, Cols, Diag)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32); cols = np.ascontiguousarray(cols, dtype=np.int32)
+    k = rows.size - 1
+    nnz = int(rows[-1] - 1)
+    R = np.zeros(k * dofs + 1, dtype=np.int32); Cc = np.zeros(max(nnz * dofs * dofs, 1), dtype=np.int32); D = np.zeros(max(k * dofs, 1), dtype=np.int32)
+    if perm is None:
+        lib().orc_initialize_matrix(k, rows, cols, dofs, None, None, R, Cc, D)
+    else:
+        p0 = np.ascontiguousarray(perm_initial, dtype=np.int32); p1 = np.ascontiguousarray(perm, dtype=np.int32)
+        inv = np.zeros(max(k, 1), dtype=np.int32)
+        for i in np.nonzero(p0 > 0)[0]:
+            inv[p0[i] - 1] = i + 1
+        lib().orc_initialize_matrix(k, rows, cols, dofs, p1.ctypes.data, inv.ctypes.data, R, Cc, D)
+    return R, Cc[:nnz * dofs * dofs], D[:k * dofs]
