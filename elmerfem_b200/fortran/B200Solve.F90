@@ -14,8 +14,9 @@
 !  SolveLinearSystem, a zero return value lets it run.  The shim therefore
 !    * returns 0 (DECLINES) for anything the device path does not implement -- Elmer then solves the system
 !      itself; nothing inside libelmer_b200 ever falls back to the CPU;
-!    * otherwise does what SolveLinearSystem does around IterSolver (SolverUtils.F90:14748-14751, 14869,
-!      14925-14927, 14965): ScaleLinearSystem, solve, BackScaleLinearSystem, ComputeChange.
+!    * otherwise does what SolveSystem / SolveLinearSystem do around IterSolver (SolverUtils.F90:15848-15865,
+!      14748-14751, 14869, 14925-14965): residual-mode change of variables, ScaleLinearSystem, solve,
+!      BackScaleLinearSystem, CalculateLoads, BackRotateNTSystem, ComputeChange.
 !
 !  This file cannot be compiled in the development image (no Fortran compiler); it is checked by
 !  tests/test_abi.py for agreement of every BIND(C) name with include/elmer_b200.h.
@@ -142,13 +143,17 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   TYPE(Solver_t) :: Solver
   TYPE(Matrix_t), POINTER :: A
   INTEGER :: n, DOFs
-  REAL(KIND=dp) :: b(n), x(n), Norm
+  REAL(KIND=dp), TARGET :: b(n), x(n)
+  REAL(KIND=dp) :: Norm
   INTEGER :: stat
 !------------------------------------------------------------------------------
   TYPE(ValueList_t), POINTER :: Params
   CHARACTER(LEN=4096) :: sif
   CHARACTER(:), ALLOCATABLE :: str
-  LOGICAL :: Found, ScaleSystem, DeviceScaling, L
+  LOGICAL :: Found, ScaleSystem, DeviceScaling, L, ResidualMode, BackRotation, CalcLoads
+  REAL(KIND=dp), ALLOCATABLE, TARGET :: Res(:)
+  REAL(KIND=dp), POINTER :: bb(:), pRes(:)
+  TYPE(Variable_t), POINTER :: NodalLoads
   CHARACTER(LEN=32) :: tmp
   INTEGER :: rc, info(2), nnz, ival, base, ndeg
   REAL(KIND=dp) :: rval
@@ -169,6 +174,22 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   IF ( .NOT. Found ) RETURN
   IF ( str /= 'iterative' ) RETURN
   IF ( ListGetLogical( Params, 'Linear System Skip Scaling', Found ) ) RETURN
+  ! branches of SolveSystem / SolveLinearSystem this function does not reproduce (SolverUtils.F90:15805-15892,
+  ! 14535-14700, 14740-14790): block and restricted systems, eigen / harmonic analysis, explicit time stepping on a
+  ! lumped matrix, Anderson acceleration, change computed in the scaled system, guess normalisation, constraint modes
+  IF ( ListGetLogical( Params, 'Linear System Block Mode', Found ) ) RETURN
+  IF ( Solver % NOFEigenValues > 0 ) THEN
+    IF ( ListGetLogical( Params, 'Eigen Analysis', Found ) ) RETURN
+    IF ( ListGetLogical( Params, 'Harmonic Analysis', Found ) ) RETURN
+  END IF
+  IF ( A % Lumped ) RETURN
+  IF ( ListGetLogical( Params, 'Nonlinear System Acceleration', Found ) ) RETURN
+  IF ( ListGetLogical( Params, 'Nonlinear System Compute Change in Scaled System', Found ) ) RETURN
+  IF ( ListGetLogical( Params, 'Linear System Normalize Guess', Found ) ) RETURN
+  IF ( ListGetLogical( Model % Control, 'Constraint Modes Analysis', Found ) ) RETURN
+  IF ( ListGetLogical( Params, 'Nonlinear System Constraint Modes', Found ) ) RETURN
+  IF ( ListGetLogical( Params, 'Steady State Constraint Modes', Found ) ) RETURN
+  IF ( ListGetLogical( Params, 'Run Control Constraint Modes', Found ) ) RETURN
 
   ! ---- keywords, verbatim, as text (parsed by b200_itersolver exactly as IterSolve.F90:250-583 does)
   sif = ''
@@ -205,12 +226,31 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   ScaleSystem = ListGetLogical( Params, 'Linear System Scaling', Found )
   IF ( .NOT. Found ) ScaleSystem = .TRUE.
   IF ( ALL( b(1:n) == 0.0_dp ) ) RETURN        ! zero rhs shortcut stays with Elmer (14717-14736)
+
+  ! ---- `Linear System Residual Mode`: SolveSystem calls this procedure BEFORE its change of variables
+  ! (SolverUtils.F90:15841-15865), and ComputeChange adds the stored previous solution back (10878-10883), so the
+  ! change of variables A dx = b - A x0, dx0 = 0 has to be done here when the solve is taken over.
+  ResidualMode = ListGetLogical( Params, 'Linear System Residual Mode', Found )
+  bb => b
+  IF ( ResidualMode ) THEN
+    ALLOCATE( Res(n) )
+    pRes => Res
+    IF ( ASSOCIATED( Solver % Variable % Perm ) ) CALL RotateNTSystemAll( x, Solver % Variable % Perm, DOFs )
+    CALL LinearSystemResidual( A, b, x, pRes )
+    bb => Res
+    x = 0.0_dp
+    IF ( ALL( Res == 0.0_dp ) ) THEN             ! zero rhs shortcut stays with Elmer, as above
+      x(1:n) = Solver % Variable % NonlinValues(1:n)     ! stored by SolveSystem at 15836
+      RETURN
+    END IF
+  END IF
   ! 'B200 Device Scaling = True': the device copy is scaled by b200_scale_system (bit-identical values), b and x are
   ! scaled / back-scaled inside b200_itersolver, and the host matrix is never touched (no ScaleLinearSystem /
   ! BackScaleLinearSystem passes over A % Values).  Not with a separate preconditioning matrix.
   DeviceScaling = ScaleSystem .AND. ListGetLogical( Params, 'B200 Device Scaling', Found ) .AND. &
                   .NOT. ASSOCIATED( A % PrecValues )
-  IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL ScaleLinearSystem( Solver, A, b, x )
+  IF ( ScaleSystem .AND. .NOT. DeviceScaling ) &
+      CALL ScaleLinearSystem( Solver, A, bb, x, RhsScaling=.TRUE., ConstraintScaling=.TRUE. )      ! 14748-14751
 
   ! ---- device mirror: structure once per matrix, values every call (once per nonlinear iteration)
   handle = A % SpMV
@@ -237,11 +277,12 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   END IF
 
   ! ---- IterSolver on the device
-  rc = b200_itersolver( handle, b, x, TRIM(sif)//C_NULL_CHAR, A % SolveCount, info )
+  rc = b200_itersolver( handle, bb, x, TRIM(sif)//C_NULL_CHAR, A % SolveCount, info )
 
   IF ( rc == B200_DECLINED ) THEN
-    ! undo the scaling and let Elmer's own path run
-    IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL BackScaleLinearSystem( Solver, A, b, x )
+    ! undo the scaling (and the change of variables) and let Elmer's own path run
+    IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL BackScaleLinearSystem( Solver, A, bb, x, ConstraintScaling=.TRUE. )
+    IF ( ResidualMode ) x(1:n) = Solver % Variable % NonlinValues(1:n)      ! stored by SolveSystem at 15836
     RETURN
   END IF
   IF ( rc /= 0 ) CALL Fatal( Caller, 'b200_itersolver failed' )
@@ -262,9 +303,24 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   WRITE( Message, '(A,I0,A,I0)' ) 'B200 linear solve: HUTI_INFO=', info(1), ' iterations=', info(2)
   CALL Info( Caller, Message, Level=5 )
 
-  ! ---- what SolveLinearSystem does after IterSolver (14925-14927, 14965)
-  IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL BackScaleLinearSystem( Solver, A, b, x )
-  CALL ComputeChange( Solver, .FALSE., n, x )
+  ! ---- what SolveLinearSystem does after IterSolver, in its order (14925-14965): back-scaling, nodal loads,
+  ! back-rotation of normal-tangential dofs, ComputeChange (which also applies relaxation and, in residual mode,
+  ! adds the previous solution)
+  IF ( ScaleSystem .AND. .NOT. DeviceScaling ) CALL BackScaleLinearSystem( Solver, A, bb, x, ConstraintScaling=.TRUE. )
+  NodalLoads => VariableGet( Solver % Mesh % Variables, GetVarName( Solver % Variable ) // ' Loads' )
+  IF ( ASSOCIATED( NodalLoads ) ) THEN
+    CalcLoads = ListGetLogical( Params, 'Calculate Loads', Found )
+    IF ( .NOT. Found ) CalcLoads = .TRUE.
+    IF ( CalcLoads ) CALL CalculateLoads( Solver, A, x, DOFs, .TRUE., NodalLoads )
+  END IF
+  BackRotation = ListGetLogical( Params, 'Back Rotate N-T Solution', Found )
+  IF ( .NOT. Found ) BackRotation = .TRUE.
+  BackRotation = BackRotation .AND. ASSOCIATED( Solver % Variable % Perm )
+  IF ( BackRotation ) THEN
+    CALL BackRotateNTSystem( x, Solver % Variable % Perm, DOFs )
+    IF ( ASSOCIATED( NodalLoads ) ) CALL BackRotateNTSystem( NodalLoads % Values, NodalLoads % Perm, DOFs )
+  END IF
+  CALL ComputeChange( Solver, .FALSE., n, x, Matrix=A, RHS=bb )
   Norm = Solver % Variable % Norm
   stat = 1
 
