@@ -108,7 +108,8 @@ def _check(rc, what):
 
 
 def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residual_output=0,
-                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10, sgs_omega=None):
+                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10, sgs_omega=None,
+                   robust=False, robust_tol=None, robust_limit=None, robust_margin=None, robust_max_bad=None, robust_start=None):
     """HUTI ipar(50)/dpar(10) exactly as IterSolver fills them (fem/src/IterSolve.F90:245-503;
     slots fhutiter/src/huti_fdefs.h:101-155)."""
     ipar = np.zeros(50, dtype=np.int32)
@@ -133,6 +134,13 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
     dpar[0] = tol
     dpar[2] = float(np.float32(1.8)) if sgs_omega is None else sgs_omega     # HUTI_SGSPARAM (IterSolve.F90:354-358)
     dpar[1] = maxtol
+    if robust:                        # `Linear System Robust` (IterSolve.F90:482-496), defaults as there
+        ipar[25] = 1
+        dpar[2] = tol ** float(np.float32(2.0) / np.float32(3.0)) if robust_tol is None else robust_tol   # HUTI_TOLERANCE**(2.0/3.0)
+        dpar[4] = np.sqrt(tol) if robust_limit is None else robust_limit
+        dpar[3] = 1.1 if robust_margin is None else robust_margin
+        ipar[26] = maxit // 2 if robust_max_bad is None else robust_max_bad
+        ipar[28] = 1 if robust_start is None else robust_start
     return ipar, dpar
 
 

@@ -146,7 +146,19 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     ipar[13] = 1;                                                        // HUTI_USERSUPPLIEDX (473)
     dpar[0] = P.real("Linear System Convergence Tolerance", 0.0);
     dpar[1] = P.real("Linear System Divergence Limit", 1.0e20, &found);
-    if (P.logical("Linear System Robust")) throw Declined{"'Linear System Robust'"};
+    if (P.logical("Linear System Robust")) {                             // 482-496, defaults as there; after the SGS factor, which
+      ipar[25] = 1;                                                      // shares dpar(3) with the robust tolerance
+      dpar[2] = P.real("Linear System Robust Tolerance", 0.0, &found);
+      if (!found) dpar[2] = pow(dpar[0], (double)(2.0f / 3.0f));         // HUTI_TOLERANCE**(2.0/3.0): default-real exponent
+      dpar[4] = P.real("Linear System Robust Limit", 0.0, &found);
+      if (!found) dpar[4] = sqrt(dpar[0]);
+      dpar[3] = P.real("Linear System Robust Margin", 0.0, &found);
+      if (!found) dpar[3] = 1.1;
+      ipar[26] = P.integer("Linear System Robust Max Iterations", 0, &found);
+      if (!found) ipar[26] = maxit / 2;
+      ipar[28] = P.integer("Linear System Robust Start Iteration", 0, &found);
+      if (!found) ipar[28] = 1;
+    }
     ipar[27] = P.logical("IDRS Smoothing") ? 1 : 0;
     // ---- preconditioner (506-577)
     // GMRES is left-preconditioned by IterSolver itself (509-525) and so is run_gmres; for CG/BiCGStab the keyword is declined

@@ -374,16 +374,23 @@ static void symv_u(int n, const double *A, int lda, const double *x, double *y) 
 static double sdot(int n, const double *x, const double *y) { double s = 0; for (int i = 0; i < n; ++i) s += x[i] * y[i]; return s; }
 
 struct HostResult { int info = 0, iters = 0; double residual = 0; };
+// `Linear System Robust` (IterSolve.F90:482-496): keep the best iterate seen and stop on it when the iteration has
+// wandered off; in the reference only BiCGStab(l) and IDR(s) look at it (IterativeMethods.F90:649-659, 1535-1544)
+struct RobustPar { bool on = false; double Tol = 0, Step = 0, MaxTol = 0; int MaxBadIter = 0, Start = 1; };
 
 // IterativeMethods.F90:694-1168
-static HostResult run_bicgstabl(Handle &h, const double *b, double *x, int pc, int MaxRounds, double Tol, double MaxTol, int l) {
+static HostResult run_bicgstabl(Handle &h, const double *b, double *x, int pc, int MaxRounds, double Tol, double MaxTol, int l,
+                                const RobustPar &Rb) {
   HostResult res;
   B200_REQUIRE(l >= 2, "BiCGStab(l): polynomial degree < 2");
   const int nw = 3 + 2 * (l + 1);
-  Solver S(h, pc, nw + 1);
+  Solver S(h, pc, nw + 1 + (Rb.on ? 1 : 0));
   const int n = S.n;
   auto work = [&](int c) { return S.vec[c - 1]; };
   double *t = S.vec[nw];
+  double *Bestx = Rb.on ? S.vec[nw + 1] : nullptr;              // 649-659
+  double BestNorm = sqrt(DBL_MAX);
+  int BadIterCount = 0;
   const int rr = 1, r = rr + 1, u = r + (l + 1), xp = u + (l + 1), bp = xp + 1;
   const int ldr = l + 1;
   std::vector<double> rw((size_t)ldr * nw, 0.0);
@@ -516,11 +523,20 @@ static HostResult run_bicgstabl(Handle &h, const double *b, double *x, int pc, i
       // round when rcmp is false): not executed, numbers unchanged.
     }
     errorind = rnrm / bnrm;
+    if (Rb.on && Round >= Rb.Start) {                          // 1110-1126
+      if (errorind < Rb.Step * BestNorm) { BestNorm = errorind; copy_vec(h, n, x, Bestx); BadIterCount = 0; }
+      else BadIterCount = BadIterCount + 1;
+      if (BestNorm < Rb.Tol && (errorind > Rb.MaxTol || BadIterCount > Rb.MaxBadIter)) break;
+    }
     Converged = errorind < Tol;
     Diverged = (errorind > MaxTol) || (errorind != errorind);
     if (Converged || Diverged) break;
   }
 L100:
+  if (Rb.on) {                                                 // 1133-1139
+    if (BestNorm < Rb.Tol) Converged = true;
+    if (BestNorm < errorind) copy_vec(h, n, Bestx, x);
+  }
   res.iters = std::min(MaxRounds, Round);
   res.residual = errorind;
   // 1156-1166: x = M^-1 x + xp
@@ -923,10 +939,13 @@ __global__ void k_shadow_space(long long n, double *P, unsigned long long seed) 
 
 // IterativeMethods.F90:1579-1913
 static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int MaxRounds, double Tol, double MaxTol, int s,
-                           bool Smoothing, const double *d_P, long long goffset_seed) {
+                           bool Smoothing, const double *d_P, long long goffset_seed, const RobustPar &Rb) {
   HostResult res;
   B200_REQUIRE(s >= 1, "IDR(s): s < 1");
-  Solver S(h, pc, 3 * s + 5);
+  Solver S(h, pc, 3 * s + 5 + (Rb.on ? 1 : 0));
+  double *Bestx = Rb.on ? S.vec[3 * s + 5] : nullptr;          // 1535-1544
+  double BestNorm = sqrt(DBL_MAX);
+  int BadIterCount = 0;
   const int n = S.n;
   auto P = [&](int j) { return S.vec[j - 1]; };
   auto G = [&](int j) { return S.vec[s + j - 1]; };
@@ -1036,11 +1055,20 @@ static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int Ma
     iter++;
     normr = Smoothing ? S.norm(r_s) : S.norm(r);
     errorind = normr / normb;
+    if (Rb.on) {                                               // 1862-1884
+      if (errorind < Rb.Step * BestNorm) { BestNorm = errorind; copy_vec(h, n, Smoothing ? x_s : x, Bestx); BadIterCount = 0; }
+      else BadIterCount = BadIterCount + 1;
+      if (BestNorm < Rb.Tol && (errorind > Rb.MaxTol || BadIterCount > Rb.MaxBadIter)) break;
+    }
     Converged = errorind < Tol;
     Diverged = (errorind > MaxTol) || (errorind != errorind);
     if (iter == MaxRounds) break;
   }
   if (Smoothing) copy_vec(h, n, x_s, x);
+  if (Rb.on) {                                                 // 1892-1898
+    if (BestNorm < Rb.Tol) Converged = true;
+    if (BestNorm < errorind) copy_vec(h, n, Bestx, x);
+  }
   res.iters = iter; res.residual = errorind;
   if (Converged) res.info = HUTI_CONVERGENCE;
   if (Diverged) res.info = HUTI_DIVERGENCE;
@@ -1069,12 +1097,14 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
   if (method == B200_M_BICGSTAB || method == B200_M_BICGSTABL || method == B200_M_BICGSTAB2) fill_if_all_zero(h, n, d_x, 1.0e-8);   // IterSolve.F90:470-471
   HostResult hr;
   if (n == 0) { IPAR(30) = HUTI_CONVERGENCE; IPAR(31) = 0; return; }
+  RobustPar rb;                                               // huti_fdefs.h:132-135, 153-155
+  rb.on = IPAR(26) == 1; rb.MaxBadIter = IPAR(27); rb.Start = IPAR(29); rb.Tol = DPAR(3); rb.Step = DPAR(4); rb.MaxTol = DPAR(5);
   switch (method) {
     case B200_M_CG: run_cg(h, d_b, d_x, pc, IPAR(10)); break;
     case B200_M_BICGSTAB: run_bicgstab(h, d_b, d_x, pc, IPAR(10)); break;
-    case B200_M_BICGSTABL: hr = run_bicgstabl(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(16)); break;
+    case B200_M_BICGSTABL: hr = run_bicgstabl(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(16), rb); break;
     case B200_M_GCR: hr = run_gcr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(17), IPAR(11)); break;
-    case B200_M_IDRS: hr = run_idrs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(18), IPAR(28) == 1, d_P, h.rank); break;
+    case B200_M_IDRS: hr = run_idrs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(18), IPAR(28) == 1, d_P, h.rank, rb); break;
     case B200_M_GMRES: hr = run_gmres(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(15), stopc); break;
     case B200_M_CGS: hr = run_cgs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;
     case B200_M_TFQMR: hr = run_tfqmr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), stopc); break;

@@ -116,7 +116,10 @@ int b200_set_bilu_blocks(void **handle, const int *blocks);
  * P: n x ipar(18) column-major shadow space for IDR(s) (the shim fills it with RANDOM_NUMBER as
  * IterativeMethods.F90:1640 does) or NULL for a built-in counter-based generator.
  * The ILU0 factor is (re)computed here only if none exists for the current values and
- * precond = ILU0 -- call b200_factorize / b200_set_values to apply IterSolver's recompute policy. */
+ * precond = ILU0 -- call b200_factorize / b200_set_values to apply IterSolver's recompute policy.
+ * `Linear System Robust` (IterSolve.F90:482-496): ipar(26) = 1 with ipar(27) max bad iterations, ipar(29) start
+ * iteration, dpar(3) robust tolerance, dpar(4) margin, dpar(5) limit (huti_fdefs.h:132-135, 153-155) is honoured
+ * by BiCGStab(l) and IDR(s), the two methods that look at it in the reference. */
 int b200_solve(void **handle, const double *b, double *x, int *ipar, double *dpar,
                const int *method, const int *precond, const double *P);
 /* Same with b, x, P resident in device memory (used to time the solve without PCIe traffic). */
@@ -126,7 +129,7 @@ int b200_solve_device(void **handle, const double *d_b, double *d_x, int *ipar, 
 /* IterSolver(A,x,b,Solver): `sif` is the text of the Solver section's linear-system keywords, one
  * "Keyword = value" per line (case-insensitive, as in a .sif).  solve_count in/out = A%SolveCount.
  * info_out[0] = HUTI_INFO, info_out[1] = iterations.  Unsupported keywords that would change the
- * algorithm (complex, ILU order > 0, BILU, ILUT, left preconditioning, user stopping criteria ...)
+ * algorithm (complex, BILU order > 0, ILUT, left preconditioning for CG/BiCGStab, backward-error stopping criteria ...)
  * make it return B200_DECLINED without touching x so that the caller runs Elmer's own path. */
 #define B200_DECLINED 100
 int b200_itersolver(void **handle, const double *b, double *x, const char *sif, int *solve_count,

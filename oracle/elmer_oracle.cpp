@@ -957,13 +957,31 @@ void small_dsymv_u(int n, const double *A, int lda, const double *x, double *y) 
   }
 }
 
-// IterativeMethods.F90:694-1168 RealBiCGStabl (no constraint matrix, Robust off).
+// `Linear System Robust` (IterSolve.F90:482-496; IterativeMethods.F90:607-610, 649-659, 1498-1501, 1535-1544)
+struct RobustPar { bool on = false; double Tol = 0, Step = 0, MaxTol = 0; int MaxBadIter = 0, Start = 1; };
+// huti_fdefs.h:132-135, 153-155: HUTI_ROBUST ipar(26), _MAXBADIT ipar(27), _START ipar(29), _TOLERANCE dpar(3), _STEPSIZE dpar(4),
+// _MAXTOLERANCE dpar(5)
+RobustPar robust_from(const int *ipar, const double *dpar) {
+  RobustPar r;
+  r.on = IPAR(26) == 1; r.MaxBadIter = IPAR(27); r.Start = IPAR(29);
+  r.Tol = DPAR(3); r.Step = DPAR(4); r.MaxTol = DPAR(5);
+  return r;
+}
+
+// IterativeMethods.F90:694-1168 RealBiCGStabl (no constraint matrix).
 // Returns through Converged/Diverged/Halted; *rounds_out = MIN(MaxRounds, Round) as printed at 1147.
 void RealBiCGStabl(Ops &op, int n, double *x, const double *b, int MaxRounds, double Tol, double MaxTol,
                    bool &Converged, bool &Diverged, bool &Halted, int OutputInterval, int l,
-                   int *rounds_out, double *res_out) {
+                   int *rounds_out, double *res_out, const RobustPar &Rb = RobustPar()) {
   const double zero = 0.0, one = 1.0, delta = 1.0e-2;
   size_t N = (size_t)n;
+  // 649-659
+  const bool Robust = Rb.on;
+  double BestNorm = std::sqrt(DBL_MAX);
+  int BadIterCount = 0, BestIter = 0;
+  std::vector<double> Bestx;
+  if (Robust) Bestx.assign(N, 0.0);
+  (void)BestIter;
   *rounds_out = 0; *res_out = 0;
   if (l < 2) { fprintf(stderr, "RealBiCGStabl: Polynomial degree < 2\n"); Halted = true; return; }
   // 719: IF ( ALL(x == 0.0d0) ) x = b
@@ -1128,11 +1146,28 @@ void RealBiCGStabl(Ops &op, int n, double *x, const double *b, int MaxRounds, do
     errorind = rnrm / bnrm;
     if (OutputInterval != 0 && OutputInterval != INT_MAX && Round % OutputInterval == 0)
       printf("%8d%11.4E%11.4E\n", Round, rnrm, errorind);
+    if (Robust) {                                  // 1110-1126
+      if (Round >= Rb.Start) {
+        if (errorind < Rb.Step * BestNorm) {
+          BestIter = Round;
+          BestNorm = errorind;
+          for (int i = 0; i < n; ++i) Bestx[i] = x[i];
+          BadIterCount = 0;
+        } else {
+          BadIterCount = BadIterCount + 1;
+        }
+        if (BestNorm < Rb.Tol && (errorind > Rb.MaxTol || BadIterCount > Rb.MaxBadIter)) break;
+      }
+    }
     Converged = (errorind < Tol);
     Diverged = (errorind > MaxTol) || (errorind != errorind);
     if (Converged || Diverged) break;
   }
 L100:
+  if (Robust) {                                    // 1133-1139
+    if (BestNorm < Rb.Tol) Converged = true;
+    if (BestNorm < errorind) for (int i = 0; i < n; ++i) x[i] = Bestx[i];
+  }
   *rounds_out = std::min(MaxRounds, Round);
   *res_out = errorind;
   // 1156-1166: x = M^-1 x + xp
@@ -1210,12 +1245,19 @@ void GCR(Ops &op, int n, double *x, const double *b, int Rounds, double MinToler
   *iters_out = std::min(k, Rounds);
 }
 
-// IterativeMethods.F90:1579-1913 RealIDRS (no constraint matrix, Robust off, user stopc off).
+// IterativeMethods.F90:1579-1913 RealIDRS (no constraint matrix, user stopc off).
 // P (n x s, column major) replaces CALL RANDOM_NUMBER(P) at 1640: the caller supplies it.
 void RealIDRS(Ops &op, int n, double *x, const double *b, int MaxRounds, double Tol, double MaxTol,
               bool &Converged, bool &Diverged, int OutputInterval, int s, bool Smoothing,
-              const double *Pin, int *iters_out, double *res_out) {
+              const double *Pin, int *iters_out, double *res_out, const RobustPar &Rb = RobustPar()) {
   size_t N = (size_t)n;
+  // 1535-1544
+  const bool Robust = Rb.on;
+  double BestNorm = std::sqrt(DBL_MAX);
+  int BadIterCount = 0, BestIter = 0;
+  std::vector<double> Bestx;
+  if (Robust) Bestx.assign(N, 0.0);
+  (void)BestIter;
   std::vector<double> Pm(N * s), G(N * s, 0.0), U(N * s, 0.0), r(N), v(N), t(N);
   std::vector<double> M((size_t)s * s, 0.0), f(s), mu(s), alpha(s), beta(s), gamma(s);
   std::vector<double> r_s, x_s;
@@ -1334,11 +1376,27 @@ void RealIDRS(Ops &op, int n, double *x, const double *b, int MaxRounds, double 
     errorind = normr / normb;
     if (OutputInterval != 0 && OutputInterval != INT_MAX && iter % OutputInterval == 0)
       printf("%8d%11.4E\n", iter, errorind);
+    if (Robust) {                                  // 1862-1884
+      if (errorind < Rb.Step * BestNorm) {
+        BestIter = iter;
+        BestNorm = errorind;
+        const double *src = Smoothing ? x_s.data() : x;
+        for (int q = 0; q < n; ++q) Bestx[q] = src[q];
+        BadIterCount = 0;
+      } else {
+        BadIterCount = BadIterCount + 1;
+      }
+      if (BestNorm < Rb.Tol && (errorind > Rb.MaxTol || BadIterCount > Rb.MaxBadIter)) break;
+    }
     Converged = (errorind < Tol);
     Diverged = (errorind > MaxTol) || (errorind != errorind);
     if (iter == MaxRounds) break;
   }
   if (Smoothing) for (int q = 0; q < n; ++q) x[q] = x_s[q];
+  if (Robust) {                                    // 1892-1898
+    if (BestNorm < Rb.Tol) Converged = true;
+    if (BestNorm < errorind) for (int q = 0; q < n; ++q) x[q] = Bestx[q];
+  }
   *iters_out = iter;
   *res_out = errorind;
 }
@@ -1440,7 +1498,7 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
   } else if (method == 3) {
     bool Converged = false, Diverged = false, Halted = false; int rounds = 0;
     RealBiCGStabl(op, n, x, b, HUTI_MAXIT, HUTI_TOLERANCE, HUTI_MAXTOLERANCE, Converged, Diverged, Halted,
-                  HUTI_DBUGLVL, HUTI_BICGSTABL_L, &rounds, &res);
+                  HUTI_DBUGLVL, HUTI_BICGSTABL_L, &rounds, &res, robust_from(ipar, dpar));
     if (Converged) HUTI_INFO = HUTI_CONVERGENCE;
     else if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
     else if (Halted) HUTI_INFO = HUTI_HALTED;
@@ -1457,7 +1515,7 @@ int orc_itersolve(int n, const int *rows, const int *cols, const int *diag, cons
   } else if (method == 5) {
     bool Converged = false, Diverged = false; int iters = 0;
     RealIDRS(op, n, x, b, HUTI_MAXIT, HUTI_TOLERANCE, HUTI_MAXTOLERANCE, Converged, Diverged,
-             HUTI_DBUGLVL, HUTI_IDRS_S, HUTI_SMOOTHING == 1, P, &iters, &res);
+             HUTI_DBUGLVL, HUTI_IDRS_S, HUTI_SMOOTHING == 1, P, &iters, &res, robust_from(ipar, dpar));
     if (Converged) HUTI_INFO = HUTI_CONVERGENCE;
     if (Diverged) HUTI_INFO = HUTI_DIVERGENCE;
     if (!Converged && !Diverged) HUTI_INFO = HUTI_MAXITER;

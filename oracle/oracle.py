@@ -134,7 +134,8 @@ def dnrm2(x):
 
 # ------------------------------------------------------------------ IterSolver
 def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residual_output=0,
-                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10, sgs_omega=None):
+                   bicgstabl_l=2, gcr_restart=None, idrs_s=4, smoothing=False, stopc=1, gmres_restart=10, sgs_omega=None,
+                   robust=False, robust_tol=None, robust_limit=None, robust_margin=None, robust_max_bad=None, robust_start=None):
     """ipar/dpar exactly as IterSolver fills them (IterSolve.F90:245-503), HUTI slots per
     fhutiter/src/huti_fdefs.h:101-155."""
     ipar = np.zeros(50, dtype=np.int32)
@@ -160,6 +161,13 @@ def fill_ipar_dpar(n, method, tol=1e-8, maxit=1000, minit=0, maxtol=1e20, residu
     dpar[1 - 1] = tol
     dpar[3 - 1] = float(np.float32(1.8)) if sgs_omega is None else sgs_omega     # HUTI_SGSPARAM; the default is the REAL literal 1.8 (IterSolve.F90:358)
     dpar[2 - 1] = maxtol
+    if robust:                        # IterSolve.F90:482-496 (after the SGS factor: dpar(3) is shared)
+        ipar[26 - 1] = 1
+        dpar[3 - 1] = tol ** float(np.float32(2.0) / np.float32(3.0)) if robust_tol is None else robust_tol   # **(2.0/3.0), default real
+        dpar[5 - 1] = np.sqrt(tol) if robust_limit is None else robust_limit
+        dpar[4 - 1] = 1.1 if robust_margin is None else robust_margin
+        ipar[27 - 1] = maxit // 2 if robust_max_bad is None else robust_max_bad
+        ipar[29 - 1] = 1 if robust_start is None else robust_start
     return ipar, dpar
 
 
