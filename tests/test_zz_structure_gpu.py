@@ -39,17 +39,22 @@ def test_elmer_ordered_beam_parity(oracle, b200):
 
 
 # ---- `Linear System Robust` on the device (IterativeMethods.F90:1110-1139, 1862-1898): same stop, same iterate ----------
-ROBUST_CASES = [("bicgstabl", dict(bicgstabl_l=2), "none"), ("bicgstabl", dict(bicgstabl_l=2), "ilu0"),
-                ("idrs", dict(idrs_s=4), "none")]
+# The cases are ones whose stopping step does not move when the ORACLE's dot products are summed in another order
+# (oracle.set_dot_order 0/1/2 all stop at the same step).  That matters: IDR(4) without a preconditioner at a robust
+# tolerance of 1e-4 stops after 115, 70 or 70 steps on the CPU depending on the summation order alone (the device
+# took 95), because "is this residual within 10 % of the best one" is decided on a residual history that has
+# drifted by then.
+ROBUST_CASES = [("bicgstabl", dict(bicgstabl_l=2), "none", 1e-4, 1e-2), ("bicgstabl", dict(bicgstabl_l=2), "ilu0", 1e-4, 1e-2),
+                ("idrs", dict(idrs_s=4), "none", 1e-2, 1e-1), ("idrs", dict(idrs_s=2), "ilu0", 1e-3, 1e-1)]
 
 
-@pytest.mark.parametrize("method,kw,pc", ROBUST_CASES)
-def test_robust_mode_parity(oracle, b200, method, kw, pc):
+@pytest.mark.parametrize("method,kw,pc,rtol,rlimit", ROBUST_CASES)
+def test_robust_mode_parity(oracle, b200, method, kw, pc, rtol, rlimit):
     A, b = oracle.cavity_flow(6)
     A = A.copy()
     oracle.scale_system(A, b, np.zeros(A.n))
-    P = oracle.shadow_space(A.n, 4) if method == "idrs" else None
-    opts = dict(tol=1e-10, maxit=400, robust=True, robust_tol=1e-4, robust_limit=1e-2, robust_max_bad=0, **kw)
+    P = oracle.shadow_space(A.n, kw["idrs_s"]) if method == "idrs" else None
+    opts = dict(tol=1e-10, maxit=400, robust=True, robust_tol=rtol, robust_limit=rlimit, robust_max_bad=0, **kw)
     ref = oracle.itersolve(A, b, method=method, precond=pc, P=P, **opts)
     plain = oracle.itersolve(A, b, method=method, precond=pc, P=P, tol=1e-10, maxit=400, **kw)
     assert ref["iters"] < plain["iters"]                    # the safeguard does fire in this case
@@ -63,7 +68,7 @@ def test_robust_mode_parity(oracle, b200, method, kw, pc):
         assert close(got["iters"], ref["iters"]), (got["iters"], ref["iters"])
         assert got["iters"] < plain["iters"]
         true = lambda x: float(np.linalg.norm(oracle.matvec(A, x) - b) / np.linalg.norm(b))
-        assert true(got["x"]) < 1e-4 and true(got["x"]) <= got["residual"] * (1 + 1e-6)    # the best iterate came back
+        assert true(got["x"]) < rtol and true(got["x"]) <= got["residual"] * (1 + 1e-6)    # the best iterate came back
         if got["iters"] == ref["iters"]:                     # same stop => same iterate (an UNconverged one: rounding
             assert np.linalg.norm(got["x"] - ref["x"]) <= 1e-6 * np.linalg.norm(ref["x"])   # differences are not damped)
         # keyword path: no longer declined
