@@ -320,3 +320,18 @@ def test_reference_winkel_navier_partitioned(oracle, b200):
     assert r["info"] == 1
     xnat = r["x"][perm] * Dv
     assert abs(W.norm(xnat) - W.NAVIER_REFERENCE_NORM) <= 1e-6 * W.NAVIER_REFERENCE_NORM, W.norm(xnat)
+
+
+@pytest.mark.parametrize("method,precond", [("bicgstab", "ilu1"), ("bicgstab", "ilu0"), ("cg", "diagonal"), ("idrs", "ilu1")])
+def test_reference_coordinate_scaling_norm(oracle, b200, method, precond):
+    """fem/tests/CoordinateScaling/case.sif (HeatSolver on ElmerGrid's 20 x 20 quad mesh, `Coordinate Scaling = 0.001`, BiCGStab + ILU1 at
+    1e-8): `Reference Norm = Real 3.93779036434094704E-002` -- the one norm the reference prints with all 17 digits; the oracle's answer
+    agrees to 1e-13 with the SIF's own solver and with others (the norm does not depend on the method).  The structure and numbering come
+    from the library's CreateMatrix producer; the bandwidth optimiser's numbering is rejected on this mesh (half bandwidth 23 stays)."""
+    import coordinatescaling_case as cs
+    A, b, info = cs.system()
+    assert info["half_bandwidth"] == 23 and np.array_equal(info["perm"], np.arange(1, info["nn"] + 1))
+    r = oracle.solve_linear_system(A, b, method=method, precond=precond, tol=1e-8 if method == "bicgstab" else 1e-12, maxit=500)
+    assert r["info"] == 1
+    tol = 1e-13 if (method, precond) == ("bicgstab", "ilu1") else 1e-8
+    assert abs(r["norm"] - cs.REFERENCE_NORM) <= tol * cs.REFERENCE_NORM, r["norm"]

@@ -82,3 +82,33 @@ def test_robust_mode_parity(oracle, b200, method, kw, pc, rtol, rlimit):
             assert np.array_equal(out["x"], got["x"])        # same device path, same bits
     finally:
         M.close()
+
+
+def test_reference_coordinate_scaling_norm_gpu(oracle, b200):
+    """fem/tests/CoordinateScaling through the C ABI: structure from the library's CreateMatrix producer, device-side Linear System
+    Scaling, BiCGStab + ILU1 via the keyword path exactly as case.sif states it => `Reference Norm = 3.93779036434094704E-002`."""
+    import coordinatescaling_case as cs
+    A, b, _ = cs.system()
+    M = b200.Matrix()
+    try:
+        M.set_structure(A.rows, A.cols, A.diag, 1, 1)
+        M.set_values(A.vals)
+        M.scale_system()
+        sif = """
+          Linear System Solver = Iterative
+          Linear System Iterative Method = BiCGStab
+          Linear System Max Iterations = 500
+          Linear System Convergence Tolerance = 1.0e-8
+          Linear System Preconditioning = ILU1
+          Linear System ILUT Tolerance = 1.0e-3
+          Linear System Abort Not Converged = False
+          Linear System Residual Output = 10
+          Linear System Precondition Recompute = 1
+        """
+        got = M.itersolver(b, None, sif)
+        ref = oracle.solve_linear_system(A, b, method="bicgstab", precond="ilu1", tol=1e-8, maxit=500)
+        assert got is not None and got["info"] == 1
+        assert abs(got["iters"] - ref["iters"]) <= 1
+        assert abs(cs.compute_norm(got["x"]) - cs.REFERENCE_NORM) <= 1e-7 * cs.REFERENCE_NORM, cs.compute_norm(got["x"])
+    finally:
+        M.close()
