@@ -69,3 +69,36 @@ def test_ilun_random_matrices(oracle, n, density, seed, order):
     u = oracle.lu_precond(A, F if order else F.vals, v)
     back = (np.tril(LU, -1) * P + np.eye(n)) @ ((np.triu(LU) * P) @ u)
     assert np.abs(back - v).max() <= 1e-9 * max(1.0, np.abs(v).max())
+
+
+@settings(max_examples=40, deadline=None)
+@given(nn=st.integers(2, 150), ne=st.integers(1, 200), seed=st.integers(0, 10 ** 6), frac=st.floats(0.3, 1.0), dofs=st.integers(1, 3),
+       use_optimized=st.booleans())
+def test_create_matrix_random_meshes(oracle, b200, nn, ne, seed, frac, dofs, use_optimized):
+    """CreateMatrix's nodal path (node graph -> OptimizeBandwidth -> InitializeMatrix) of the library against the list-matrix restatement,
+    on random "meshes": elements of 1..8 nodes, equations that cover only part of the nodes, isolated nodes, several components."""
+    rs = np.random.RandomState(seed)
+    elems = [rs.choice(nn, size=rs.randint(1, min(8, nn) + 1), replace=False) + 1 for _ in range(ne)]
+    ptr = np.zeros(ne + 1, dtype=np.int32); ptr[1:] = np.cumsum([len(e) for e in elems])
+    nodes = np.concatenate(elems).astype(np.int32)
+    appears = np.zeros(nn, dtype=bool); appears[nodes - 1] = True
+    active = (rs.rand(nn) < frac) & appears                    # nodes outside every element carry no dof of the equation
+    active[nodes[0] - 1] = True
+    k = int(active.sum())
+    perm0 = np.zeros(nn, dtype=np.int32)
+    perm0[rs.permutation(np.nonzero(active)[0])] = np.arange(1, k + 1)
+    lr_o, lc_o = oracle.make_list_matrix(ptr, nodes, perm0, k)
+    lr_p, lc_p = b200.node_graph(ptr, nodes, nn, perm0, k)
+    assert np.array_equal(lr_p, lr_o) and np.array_equal(lc_p, lc_o)
+    assert np.all(np.diff(lr_o) > 0)
+    p_o, hb_o = oracle.optimize_bandwidth(lr_o, lc_o, perm0, True, use_optimized)
+    p_p, hb_p = b200.optimize_bandwidth(lr_p, lc_p, perm0, True, use_optimized)
+    assert hb_p == hb_o and np.array_equal(p_p, p_o)
+    assert np.array_equal(np.sort(p_p[active]), np.arange(1, k + 1)) and np.all(p_p[~active] == 0)
+    got = b200.initialize_structure(lr_p, lc_p, dofs, perm0, p_p)
+    ref = oracle.initialize_matrix(lr_o, lc_o, dofs, perm0, p_o)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+    R, Cc, D = got
+    assert np.array_equal(Cc[D - 1], np.arange(1, k * dofs + 1))          # Diag points at the diagonal
+    assert all(np.all(np.diff(Cc[R[i] - 1:R[i + 1] - 1]) > 0) for i in range(k * dofs))
