@@ -65,6 +65,7 @@ def lib():
         "b200_partition_send_lists": [ip] * 10, "b200_partition_peer_layout": [ip, ip, ip, ip, C.POINTER(C.c_longlong)], "b200_partition_split": [ip] * 14,
         "b200_node_graph": [ip, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_longlong), ip, ip],
         "b200_optimize_bandwidth": [ip] * 9, "b200_initialize_structure": [ip] * 11,
+        "b200_itersolver_plan": [C.c_char_p, ip, ip, ip, ip, ip, ip, ip, dp],
         "b200_version": [ip, ip], "b200_vec_len": [vpp, C.POINTER(C.c_longlong)],
     }
     for name, args in sigs.items():
@@ -457,3 +458,20 @@ def create_matrix_structure(elem_ptr, elem_nodes, n_nodes, dofs=1, optimize_bw=T
     else:
         R, Cc, D = initialize_structure(lrows, lcols, dofs)
     return dict(perm=perm1, half_bandwidth=hb, rows=R, cols=Cc, diag=D, list_rows=lrows, list_cols=lcols)
+
+
+def itersolver_plan(sif, n, ndeg=1):
+    """Host-only: IterSolver's keyword decisions (IterSolve.F90:250-577) as b200_itersolver takes them.  Returns a dict, or
+    None with the reason in last_error() when the keyword combination is DECLINED."""
+    method = C.c_int(0); pc = C.c_int(0); order = C.c_int(0); blocks = C.c_int(0)
+    ipar = np.zeros(50, dtype=np.int32); dpar = np.zeros(10, dtype=np.float64)
+    rc = lib().b200_itersolver_plan(sif.encode(), _i(n), _i(ndeg), C.byref(method), C.byref(pc), C.byref(order), C.byref(blocks),
+                                    _ip(ipar), _dp(dpar))
+    if rc == DECLINED:
+        return None
+    _check(rc, "b200_itersolver_plan")
+    return dict(method=method.value, precond=pc.value, ilu_order=order.value, bilu_blocks=blocks.value, ipar=ipar, dpar=dpar)
+
+
+def last_error():
+    return lib().b200_last_error().decode()

@@ -68,6 +68,13 @@ MODULE B200Interface
       CHARACTER(KIND=C_CHAR) :: sif(*)
       INTEGER(C_INT) :: solve_count, info_out(2)
     END FUNCTION
+    ! host-only: what b200_itersolver would decide for these keywords (rc = B200_DECLINED: Elmer's own path would run)
+    INTEGER(C_INT) FUNCTION b200_itersolver_plan(sif, n, ndeg, method, precond, ilu_order, bilu_blocks, ipar, dpar) &
+        BIND(C, NAME="b200_itersolver_plan")
+      IMPORT; CHARACTER(KIND=C_CHAR) :: sif(*)
+      INTEGER(C_INT) :: n, ndeg, method, precond, ilu_order, bilu_blocks, ipar(50)
+      REAL(C_DOUBLE) :: dpar(10)
+    END FUNCTION
     ! the five HUTI callbacks, host vectors
     INTEGER(C_INT) FUNCTION b200_matvec(handle, u, v) BIND(C, NAME="b200_matvec")
       IMPORT; INTEGER(C_INTPTR_T) :: handle

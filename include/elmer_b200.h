@@ -134,6 +134,11 @@ int b200_solve_device(void **handle, const double *d_b, double *d_x, int *ipar, 
 #define B200_DECLINED 100
 int b200_itersolver(void **handle, const double *b, double *x, const char *sif, int *solve_count,
                     int *info_out);
+/* Host-only (no GPU needed): what b200_itersolver decides from the keywords alone for a matrix of n rows with ndeg dofs per node --
+ * IterSolve.F90:250-577 -- method and preconditioner codes, ILU order (-1: no ILU preconditioner), BILU blocks, and the HUTI
+ * ipar[50] / dpar[10] it would pass on.  Returns B200_DECLINED (reason in b200_last_error) exactly when b200_itersolver would. */
+int b200_itersolver_plan(const char *sif, const int *n, const int *ndeg, int *method, int *precond, int *ilu_order,
+                         int *bilu_blocks, int *ipar, double *dpar);
 
 /* ---- the callbacks, exposed for parity tests and for user code ----------------------------- */
 int b200_matvec(void **handle, const double *u, double *v);                /* v = A u            */
