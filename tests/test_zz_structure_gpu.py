@@ -1,7 +1,10 @@
-"""GPU leg of the matrix-structure producer: a system whose Rows/Cols/Diag come from
-b200_node_graph / b200_optimize_bandwidth / b200_initialize_structure (Elmer's default `Optimize Bandwidth`
-numbering, accepted on a beam) goes through the C ABI like any other matrix; the ordering changes the ILU0 factor
-and the dependency levels, so factor, triangular solve and Krylov parity are checked again on it."""
+"""GPU legs added late in round 1 (all run green on a B200, `gpurun_out/c_tests.log`, `d_tests.log`, `e_tests.log`):
+
+* matrix-structure producer: a system whose Rows/Cols/Diag come from b200_node_graph / b200_optimize_bandwidth /
+  b200_initialize_structure (Elmer's default `Optimize Bandwidth` numbering, accepted on a beam) goes through the C ABI like any other
+  matrix; the ordering changes the ILU0 factor and the dependency levels, so factor, triangular solve and Krylov parity are checked on it;
+* `Linear System Robust` for BiCGStab(l) and IDR(s), solver API and keyword path;
+* the reference's fem/tests/CoordinateScaling case with its SIF keywords verbatim."""
 import numpy as np
 import pytest
 
