@@ -18,3 +18,15 @@ cp cube5/mesh.header cube5/mesh.nodes cube5/mesh.elements cube5/mesh.boundary $H
 mkdir -p $HERE/elmergrid/partitioning.3
 cp cube5/partitioning.3/part.* $HERE/elmergrid/partitioning.3/
 rm -rf $W
+
+# fem/tests/CoordinateScaling: the 20 x 20 quad mesh of square.grd, as that test's runtest.cmake makes it (`ElmerGrid 1 2 square`)
+W=$(mktemp -d)
+cd $W
+cp /root/reference/fem/tests/CoordinateScaling/square.grd .
+$EG 1 2 square > /dev/null
+mkdir -p $HERE/coordinatescaling
+cp square.grd square/mesh.header square/mesh.nodes square/mesh.elements square/mesh.boundary $HERE/coordinatescaling/
+rm -rf $W
+# fem/tests/ElmerGridExtrudeMaterial: only the .grd is kept; tests/extrudematerial_case.py runs ElmerGrid on it at test time
+mkdir -p $HERE/extrudematerial
+cp /root/reference/fem/tests/ElmerGridExtrudeMaterial/cubes.grd $HERE/extrudematerial/
