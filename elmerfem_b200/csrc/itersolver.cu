@@ -104,9 +104,7 @@ static void plan_from_sif(const Sif &P, int n, int ndeg, SolvePlan &pl) {
   else if (m == "jacobi") method = B200_METHOD_JACOBI;
   else if (m == "richardson") method = B200_METHOD_RICHARDSON;
   else if (m == "sgs") method = B200_METHOD_SGS;
-  else if (false)
-    throw Declined{"iterative method '" + m + "' is not on the accelerated path"};
-  else method = B200_METHOD_BICGSTAB;                                  // CASE DEFAULT (313-314)
+  else method = B200_METHOD_BICGSTAB;                                  // CASE DEFAULT (313-314): unknown names run BiCGStab
   if (P.logical("Linear System Complex") || P.logical("Linear System Pseudo Complex"))
     throw Declined{"complex / pseudo-complex systems"};
   const bool internal = (method >= B200_METHOD_BICGSTABL && method <= B200_METHOD_IDRS) || method == B200_METHOD_JACOBI || method == B200_METHOD_RICHARDSON || method == B200_METHOD_SGS;

@@ -134,3 +134,8 @@ def test_errors_are_errors_not_declines():
         _plan("Linear System Iterative Method = CG\n")                                  # Max Iterations missing
     with pytest.raises(B.B200Error):
         _plan("Linear System Max Iterations = 10\nLinear System Iterative Method = bicgstabl\nBiCGstabl polynomial degree = 1\n")
+
+
+def test_unknown_method_name_runs_bicgstab_as_in_itersolve():
+    p = _plan("Linear System Max Iterations = 10\nLinear System Iterative Method = FancyNewMethod\n")   # CASE DEFAULT, IterSolve.F90:313-314
+    assert p["method"] == 2 and p["ipar"][3] == 8
