@@ -272,3 +272,38 @@ def test_create_matrix_structure_beam_solution_is_the_permuted_one(oracle):
     assert got["info"] == 1 and ref["info"] == 1
     x_back = got["x"][perm - 1]                       # mesh node m is row perm[m]
     assert np.linalg.norm(x_back - ref["x"]) <= 1e-7 * np.linalg.norm(ref["x"])
+
+
+def test_empty_and_degenerate_inputs():
+    """No elements / no active nodes / a single node: sizes come back consistent and nothing is touched out of bounds."""
+    ptr = np.zeros(1, dtype=np.int32)                                  # zero elements
+    rows, cols = b200.node_graph(ptr, np.zeros(1, dtype=np.int32), 5, np.zeros(5, dtype=np.int32), 0)
+    assert rows.tolist() == [1] and cols.size == 0
+    p, hb = b200.optimize_bandwidth(rows, np.ones(1, dtype=np.int32), np.zeros(5, dtype=np.int32))
+    assert hb == 1 and p.tolist() == [0] * 5
+    R, Cc, D = b200.initialize_structure(rows, np.ones(1, dtype=np.int32), 2)
+    assert R.tolist() == [1] and Cc.size == 0
+    # one node, one 1-node element (a 101 point element)
+    ptr, nodes = _flat([[1]])
+    rows, cols = b200.node_graph(ptr, nodes, 1)
+    assert rows.tolist() == [1, 2] and cols.tolist() == [1]
+    p, hb = b200.optimize_bandwidth(rows, cols, np.array([1], dtype=np.int32))
+    assert p.tolist() == [1] and hb == 1
+    r_o, c_o = orc.make_list_matrix(ptr, nodes, np.array([1], dtype=np.int32), 1)
+    p_o, hb_o = orc.optimize_bandwidth(r_o, c_o, np.array([1], dtype=np.int32))
+    assert p_o.tolist() == [1] and hb_o == 1
+    R, Cc, D = b200.initialize_structure(rows, cols, 3)
+    assert R.tolist() == [1, 4, 7, 10] and Cc.tolist() == [1, 2, 3] * 3 and D.tolist() == [1, 5, 9]
+
+
+def test_structure_entry_points_reject_inconsistent_input():
+    rows = np.array([1, 3, 4], dtype=np.int32); cols = np.array([1, 2, 7], dtype=np.int32)      # column 7 of a 2-row graph
+    with pytest.raises(b200.B200Error):
+        b200.optimize_bandwidth(rows, cols, np.array([1, 2], dtype=np.int32))
+    good = np.array([1, 2, 2], dtype=np.int32)
+    with pytest.raises(b200.B200Error):
+        b200.optimize_bandwidth(rows, good, np.array([1, 5], dtype=np.int32))                    # Perm entry beyond k
+    with pytest.raises(b200.B200Error):
+        b200.initialize_structure(rows, good, 0)                                                 # dofs < 1
+    with pytest.raises(b200.B200Error):
+        b200.initialize_structure(rows, good, 1, np.array([1, 2], dtype=np.int32), np.array([1, 0], dtype=np.int32))   # numbering misses a row
