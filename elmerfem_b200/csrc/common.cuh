@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include "skewgeom.h"
 
 namespace b200 {
 
@@ -109,6 +110,9 @@ struct TriTask {
   DBuf<unsigned> fill_dst; DBuf<int> fill_src;   // stream double index <- position in the ILU value array
 };
 
+// skewed-lane triangular solve (skew.cu, opt-in B200_TRI_MODE=2): geometry + the two per-step entry streams + work vectors
+struct SkewPlan { SkewGeom g; DBuf<double> SL, SU, y, x; bool ready = false, tried = false; };
+
 struct Handle {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -146,6 +150,7 @@ struct Handle {
   DBuf<int> d_lvlcnt_f, d_lvlcnt_b;              // slices per level (forward / backward)
   DBuf<int> d_urhs; DBuf<double> d_yl, d_xu;     // backward rhs map (U slot -> L slot); slot-ordered solve vectors
   // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
+  SkewPlan sk; int sk_blocks_per_sm = 0;
   TriTask TL, TU; bool tt_ready = false; int tri_mode = 0, tri_mode_cfg = 0, tt_rows = 0, tt_wpb = 0; unsigned tt_wait_ns = 100; int tt_pf = 16; DBuf<double> d_ytask, d_xtask;
   double tt_ms_level = 0, tt_ms_task = 0;
   // workspace
@@ -263,6 +268,10 @@ void tritask_analyse(Handle &h);                       // task-mode plans for bo
 void tritask_refresh_values(Handle &h);                // copy the ILU values into the plans' streams
 void tritask_release(Handle &h);
 bool tritask_usable(Handle &h);
+void skew_analyse(Handle &h);                          // skewed-lane plan (host detection of the grid stencil; no-op when it does not apply)
+void skew_refresh_values(Handle &h);
+void skew_release(Handle &h);
+void lu_apply_skew(Handle &h, double *u, const double *v);
 void lu_apply_task(Handle &h, double *u, const double *v);
 void halo_release(Handle &h);
 size_t vec_len(const Handle &h);                       // n + ghost entries: length every SpMV operand must have

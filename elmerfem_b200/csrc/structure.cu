@@ -202,6 +202,7 @@ void ilu_invalidate(Handle &h) {
   h.ilu_valid = h.ilu_exists = false; h.tri_ready = false; h.ilu_pat_ready = false;
   h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0;
   tritask_release(h);
+  skew_release(h);
   h.tri_mode = h.tri_mode_cfg;
 }
 

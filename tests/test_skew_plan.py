@@ -1,0 +1,56 @@
+"""The opt-in skewed-lane triangular solve (csrc/skew.cu, B200_TRI_MODE=2) on the CPU: tests/skew_harness.cpp executes the kernel's schedule
+through the kernel's own geometry / detection / stream-layout header (csrc/skewgeom.h) on real ILU0 factors; the result must be
+bit-identical to the oracle's CRS_LUSolve, and matrices without the grid stencil must be refused (the level kernel then stays).
+The CUDA kernel itself has not run on hardware yet (written at the end of round 1 without GPU budget)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("skew") / "skew_harness.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "skew_harness.cpp")])
+    L = C.CDLL(so)
+    L.skew_emulate.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _ip]
+    return L
+
+
+def _run(harness, A, ilu, v):
+    x = np.zeros(A.n); geom = np.zeros(5, dtype=np.int32)
+    rc = harness.skew_emulate(A.n, A.rows - 1, A.cols - 1, A.diag - 1, np.ascontiguousarray(ilu), np.ascontiguousarray(v), x, geom)
+    return rc, x, geom
+
+
+@pytest.mark.parametrize("dims", [(6, 6, 6), (9, 4, 5), (3, 40, 4), (12, 12, 1), (35, 3, 3)])
+def test_bit_identical_to_crs_lusolve(oracle, harness, dims):
+    A, b = oracle.heat_cube(0, faces=["x0"], dims=dims)
+    A = A.copy()
+    oracle.scale_system(A, b, np.zeros(A.n))
+    ilu = oracle.ilu0(A)
+    v = np.random.RandomState(3).standard_normal(A.n)
+    rc, x, geom = _run(harness, A, ilu, v)
+    assert rc == 0
+    assert tuple(geom[:3]) == (dims[0] + 1, dims[1] + 1, dims[2] + 1)
+    assert geom[3] <= 32 and geom[3] * geom[4] >= geom[1]
+    assert np.array_equal(x, oracle.lu_precond(A, ilu, v))
+
+
+def test_other_structures_are_refused(oracle, harness):
+    A, b = oracle.elasticity_beam(3, 3, 3)                      # 3 dofs per node: not the scalar stencil
+    rc, _, _ = _run(harness, A, oracle.ilu0(A), np.ones(A.n))
+    assert rc == 1
+    import scipy.sparse as sp
+    H, _ = oracle.heat_cube(5, faces=["x0"])
+    p = np.random.RandomState(0).permutation(H.n)
+    S = H.to_scipy()[p][:, p]                                    # same graph, scrambled numbering
+    Hs = oracle.CRS.from_scipy(sp.csr_matrix(S))
+    rc, _, _ = _run(harness, Hs, oracle.ilu0(Hs), np.ones(Hs.n))
+    assert rc == 1
