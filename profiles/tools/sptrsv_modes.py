@@ -1,4 +1,7 @@
-"""Task-mode vs level-mode triangular solves: bitwise comparison + timing (scratch)."""
+"""Triangular-solve kernels side by side: bitwise comparison against the first variant + timing.
+    python profiles/tools/sptrsv_modes.py 200 heat 0 1                       level kernel vs task kernel
+    python profiles/tools/sptrsv_modes.py 200 heat 0 2 2,B200_SKEW_BLOCKS_PER_SM=2   level kernel vs the experimental skewed-lane kernel
+A variant is `<B200_TRI_MODE>[,ENV=value,...]`.  Run mode 2 under `timeout`: it has not been on hardware yet (round 1)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
