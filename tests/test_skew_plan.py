@@ -20,6 +20,7 @@ def harness(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "skew_harness.cpp")])
     L = C.CDLL(so)
     L.skew_emulate.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _ip]
+    L.skew_emulate_concurrent.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_uint]
     return L
 
 
@@ -54,3 +55,21 @@ def test_other_structures_are_refused(oracle, harness):
     Hs = oracle.CRS.from_scipy(sp.csr_matrix(S))
     rc, _, _ = _run(harness, Hs, oracle.ilu0(Hs), np.ones(Hs.n))
     assert rc == 1
+
+
+@pytest.mark.parametrize("dims,nw", [((6, 6, 6), 1), ((6, 6, 6), 2), ((5, 70, 4), 2), ((5, 70, 4), 3), ((5, 70, 4), 7), ((9, 40, 5), 5),
+                                     ((9, 40, 5), 64), ((4, 4, 12), 4)])
+def test_no_deadlock_for_any_warp_count_or_interleaving(oracle, harness, dims, nw):
+    """The kernel's task assignment (warp w takes tasks w, w+NW, ... in increasing order) with the sentinel protocol: emulated warps are
+    interleaved pseudo-randomly and may only advance when their L2 operands exist.  Fewer warps than strips per plane, one warp, more
+    warps than tasks: every run must finish (no deadlock) with the bit-identical result."""
+    A, b = oracle.heat_cube(0, faces=["x0"], dims=dims)
+    A = A.copy()
+    oracle.scale_system(A, b, np.zeros(A.n))
+    ilu = oracle.ilu0(A)
+    v = np.random.RandomState(5).standard_normal(A.n)
+    ref = oracle.lu_precond(A, ilu, v)
+    for seed in (1, 2, 3):
+        rc = harness.skew_emulate_concurrent(A.n, A.rows - 1, A.cols - 1, A.diag - 1, np.ascontiguousarray(ilu), np.ascontiguousarray(v),
+                                             np.ascontiguousarray(ref), nw, seed)
+        assert rc == 0, (rc, seed)
