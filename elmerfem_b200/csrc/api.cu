@@ -57,6 +57,11 @@ static void ensure_runtime(Handle &h) {
   h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
   h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", 0);   // 0 level kernel (default), 1 task kernel, -1 time both and pick
   h.sk_blocks_per_sm = env_int("B200_SKEW_BLOCKS_PER_SM", 0);
+  h.sk_cfg = env_int("B200_SKEW_CFG", 0);
+  h.sk_wpb = env_int("B200_SKEW_WPB", 0);
+  h.wv_blocks_per_sm = env_int("B200_WAVE_BLOCKS_PER_SM", 0);
+  h.wv_cfg = env_int("B200_WAVE_CFG", 0);
+  h.wv_e = env_int("B200_WAVE_E", 3);
   h.tt_rows = env_int("B200_TT_ROWS", 0);
   h.tt_wpb = env_int("B200_TT_WPB", 0);
   h.tt_wait_ns = (unsigned)env_int("B200_TT_WAIT_NS", 100);
@@ -249,7 +254,7 @@ int b200_destroy(void **handle) {
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
     h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
     h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
-    tritask_release(*h); skew_release(*h); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
+    tritask_release(*h); skew_release(*h); wave_release(*h); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
     for (auto &w : h->work) w.release();
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();

@@ -10,6 +10,7 @@
 #include <vector>
 #include <stdexcept>
 #include "skewgeom.h"
+#include "wavegeom.h"
 
 namespace b200 {
 
@@ -111,7 +112,13 @@ struct TriTask {
 };
 
 // skewed-lane triangular solve (skew.cu, opt-in B200_TRI_MODE=2): geometry + the two per-step entry streams + work vectors
-struct SkewPlan { SkewGeom g; DBuf<double> SL, SU, y, x; bool ready = false, tried = false; };
+struct SkewPlan { SkewGeom g; DBuf<double> SL, SU, yin, y, x; DBuf<long long> trace; bool ready = false, tried = false, trace_on = false; };
+
+// wave-tile triangular solve (wave.cu, B200_TRI_MODE=3): geometry, tile tables, the two per-step entry streams, work vectors
+struct WavePlan {
+  WaveGeom g; DBuf<int> tile_of, tile_sig, tile_grp; DBuf<double> SL, SU, yin, y, x; DBuf<long long> trace;
+  bool ready = false, tried = false, trace_on = false;
+};
 
 struct Handle {
   int device = 0;
@@ -150,7 +157,8 @@ struct Handle {
   DBuf<int> d_lvlcnt_f, d_lvlcnt_b;              // slices per level (forward / backward)
   DBuf<int> d_urhs; DBuf<double> d_yl, d_xu;     // backward rhs map (U slot -> L slot); slot-ordered solve vectors
   // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
-  SkewPlan sk; int sk_blocks_per_sm = 0;
+  SkewPlan sk; int sk_blocks_per_sm = 0, sk_cfg = 0, sk_wpb = 0;
+  WavePlan wv; int wv_blocks_per_sm = 0, wv_cfg = 0, wv_e = 3;
   TriTask TL, TU; bool tt_ready = false; int tri_mode = 0, tri_mode_cfg = 0, tt_rows = 0, tt_wpb = 0; unsigned tt_wait_ns = 100; int tt_pf = 16; DBuf<double> d_ytask, d_xtask;
   double tt_ms_level = 0, tt_ms_task = 0;
   // workspace
@@ -272,7 +280,15 @@ void skew_analyse(Handle &h);                          // skewed-lane plan (host
 void skew_refresh_values(Handle &h);
 void skew_release(Handle &h);
 void lu_apply_skew(Handle &h, double *u, const double *v);
+void skew_trace_enable(Handle &h, bool on);
+void skew_trace_fetch(Handle &h, std::vector<long long> &out);
 void lu_apply_task(Handle &h, double *u, const double *v);
+void wave_analyse(Handle &h);                          // wave-tile plan (host detection of the grid stencil; no-op when it does not apply)
+void wave_refresh_values(Handle &h);
+void wave_release(Handle &h);
+void lu_apply_wave(Handle &h, double *u, const double *v);
+void wave_trace_enable(Handle &h, bool on);
+void wave_trace_fetch(Handle &h, std::vector<long long> &out);
 void halo_release(Handle &h);
 size_t vec_len(const Handle &h);                       // n + ghost entries: length every SpMV operand must have
 void matvec_full(Handle &h, const double *x, double *y);   // y = A x incl. halo exchange when partitioned

@@ -155,6 +155,7 @@ void ilu0_factor(Handle &h) {
   B200_REQUIRE(h.have_vals, "ILU0 requested before b200_set_values");
   tri_analyse(h);
   if (h.tri_mode == 2) skew_analyse(h);
+  else if (h.tri_mode == 3) wave_analyse(h);
   else if (h.tri_mode != 0) tritask_analyse(h);
   cudaStream_t st = h.stream;
   h.d_ilu.ensure(h.lnnz());
@@ -174,6 +175,7 @@ void ilu0_factor(Handle &h) {
     if (h.U.nslots) k_gather_diag_slots<<<(h.U.nslots + 255) / 256, 256, 0, st>>>(h.U.nslots, h.U.perm.p, h.d_ldiag(), h.d_ilu.p, h.d_dinv_slot.p);
     if (h.tt_ready) tritask_refresh_values(h);
     if (h.sk.ready) skew_refresh_values(h);
+    if (h.wv.ready) wave_refresh_values(h);
     B200_CUDA(cudaGetLastError());
   }
   B200_CUDA(cudaEventRecord(h.evf1, st));
@@ -591,6 +593,7 @@ void lu_apply(Handle &h, double *u, const double *v) {
   B200_REQUIRE(h.ilu_valid, "LU preconditioner applied without a valid ILU0 factor");
   if (h.n == 0) return;
   if (h.tri_mode == 2 && h.sk.ready) { lu_apply_skew(h, u, v); return; }   // experimental, opt-in; not ready -> level kernel
+  if (h.tri_mode == 3 && h.wv.ready) { lu_apply_wave(h, u, v); return; }   // grid stencils; not detected -> level kernel
   if (h.tri_mode == 1) { lu_apply_task(h, u, v); return; }
   k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
   static const bool wide_ok = !(getenv("B200_TRI_WIDE") && atoi(getenv("B200_TRI_WIDE")) == 0);

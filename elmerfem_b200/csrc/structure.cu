@@ -203,6 +203,7 @@ void ilu_invalidate(Handle &h) {
   h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0;
   tritask_release(h);
   skew_release(h);
+  wave_release(h);
   h.tri_mode = h.tri_mode_cfg;
 }
 

@@ -78,8 +78,49 @@ struct Matrix {
 // g_dot_order != 0 is NOT the reference: it replays the same dot product in the summation orders other BLAS
 // builds use (Elmer may be linked against OpenBLAS/MKL instead of mathlibs, CMakeLists.txt:270-...), to
 // measure how far iteration counts move with the summation order alone.
-//   1: eight interleaved partial sums (SIMD-style kernel), 2: pairwise over blocks of 256
+//   1: eight interleaved partial sums (SIMD-style kernel), 2: pairwise over blocks of 256, 3: the device's order (below)
 static int g_dot_order = 0;
+// g_dot_order == 3: the summation order of the DEVICE reductions (elmerfem_b200/csrc/common.cuh grid_reduce, blas1.cu
+// k_dot_batch, the SpMV epilogues of spmv.cu and the fused vector kernels of krylov.cu), so that whole solves can be compared
+// bit for bit: B = min(ceil(n/256), g_dev_blocks) blocks of 256 threads; thread t adds the products of elements t, t + 256 B, ...
+// to one accumulator (separate multiply and add roundings); the 32 lanes of a warp are summed by the xor-shuffle tree
+// (offsets 16, 8, 4, 2, 1); the 8 warp sums of a block by the same tree; the block partials are added by 256 threads with stride
+// 256, then the same two trees.  The SELL SpMV kernels own rows (slice = warp, warp + 8 B, ...; row = 32 slice + lane), which is the
+// same element -> thread map.  Single-rank handles only (an all-reduce adds its own order).
+static int g_dev_blocks = 148 * 8;
+static inline double tree32(double *v) {            // v[32] is overwritten
+  for (int o = 16; o > 0; o >>= 1) for (int i = 0; i < o; ++i) v[i] = v[i] + v[i + o];
+  return v[0];
+}
+static double block256(const double *acc) {          // 256 thread accumulators -> block partial
+  double w[32];
+  for (int k = 0; k < 32; ++k) w[k] = 0.0;
+  for (int warp = 0; warp < 8; ++warp) {
+    double v[32];
+    for (int l = 0; l < 32; ++l) v[l] = acc[warp * 32 + l];
+    w[warp] = tree32(v);
+  }
+  return tree32(w);
+}
+static double dot_device(long n, const double *x, const double *y) {
+  if (n <= 0) return 0.0;
+  long B = (n + 255) / 256;
+  if (B > g_dev_blocks) B = g_dev_blocks;
+  const long T = B * 256;
+  std::vector<double> acc((size_t)T, 0.0);
+#pragma omp parallel for schedule(static)
+  for (long t = 0; t < T; ++t) {
+    double a = 0.0;
+    for (long i = t; i < n; i += T) { double p = x[i] * y[i]; a = a + p; }
+    acc[t] = a;
+  }
+  std::vector<double> part((size_t)B);
+#pragma omp parallel for schedule(static)
+  for (long b = 0; b < B; ++b) part[b] = block256(&acc[(size_t)b * 256]);
+  double fin[256];
+  for (int t = 0; t < 256; ++t) { double a = 0.0; for (long i = t; i < B; i += 256) a = a + part[i]; fin[t] = a; }
+  return block256(fin);
+}
 static double dot_pairwise(const double *x, const double *y, long lo, long hi) {
   if (hi - lo <= 256) { double s = 0.0; for (long i = lo; i < hi; ++i) s += x[i] * y[i]; return s; }
   long mid = lo + (hi - lo) / 2;
@@ -96,6 +137,7 @@ double ref_ddot(int n, const double *dx, const double *dy) {
     return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
   if (g_dot_order == 2) return dot_pairwise(dx, dy, 0, n);
+  if (g_dot_order == 3) return dot_device(n, dx, dy);
   int m = n % 5;
   if (m != 0) {
     for (int i = 0; i < m; ++i) dtemp = dtemp + dx[i] * dy[i];
@@ -1409,6 +1451,7 @@ void RealIDRS(Ops &op, int n, double *x, const double *b, int MaxRounds, double 
 extern "C" {
 
 void orc_set_dot_order(int mode) { g_dot_order = mode; }
+void orc_set_device_blocks(int blocks) { g_dev_blocks = blocks; }
 void orc_set_threads(int nthreads) {
 #ifdef _OPENMP
   omp_set_num_threads(nthreads > 0 ? nthreads : 1);

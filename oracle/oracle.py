@@ -70,8 +70,15 @@ def set_threads(n):
 
 def set_dot_order(mode):
     """0 = the reference's ddot/dnrm2 (default); 1, 2 = the same dot products summed in the orders other BLAS
-    builds use (sensitivity study only, see elmer_oracle.cpp)."""
+    builds use (sensitivity study only, see elmer_oracle.cpp); 3 = the summation order of the device reductions
+    (grid-stride thread partials, xor-shuffle trees, block partials: elmerfem_b200/csrc/common.cuh grid_reduce), under
+    which a single-rank device solve must agree with the oracle bit for bit."""
     lib().orc_set_dot_order(int(mode))
+
+
+def set_device_blocks(blocks=148 * 8):
+    """Grid size of the device reductions emulated by dot order 3 (B200_BLAS_BLOCKS / B200_SPMV_BLOCKS, default 148 * 8)."""
+    lib().orc_set_device_blocks(int(blocks))
 
 
 def max_threads():

@@ -1,7 +1,6 @@
-"""The opt-in skewed-lane triangular solve (csrc/skew.cu, B200_TRI_MODE=2) on the CPU: tests/skew_harness.cpp executes the kernel's schedule
-through the kernel's own geometry / detection / stream-layout header (csrc/skewgeom.h) on real ILU0 factors; the result must be
-bit-identical to the oracle's CRS_LUSolve, and matrices without the grid stencil must be refused (the level kernel then stays).
-The CUDA kernel itself has not run on hardware yet (written at the end of round 1 without GPU budget)."""
+"""The skewed-lane triangular solve (csrc/skew.cu) on the CPU: tests/skew_harness.cpp executes the kernel's schedule through the kernel's
+own geometry / detection / layout / operand-routing header (csrc/skewgeom.h) on real ILU0 factors; the result must be bit-identical to
+the oracle's CRS_LUSolve, and matrices without the grid stencil must be refused (the level kernel then stays)."""
 import ctypes as C
 import os
 import subprocess
@@ -19,14 +18,14 @@ def harness(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("skew") / "skew_harness.so")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "skew_harness.cpp")])
     L = C.CDLL(so)
-    L.skew_emulate.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _ip]
-    L.skew_emulate_concurrent.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_uint]
+    L.skew_emulate.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _ip, C.c_int]
+    L.skew_emulate_concurrent.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_uint, C.c_int]
     return L
 
 
-def _run(harness, A, ilu, v):
+def _run(harness, A, ilu, v, E=3):
     x = np.zeros(A.n); geom = np.zeros(5, dtype=np.int32)
-    rc = harness.skew_emulate(A.n, A.rows - 1, A.cols - 1, A.diag - 1, np.ascontiguousarray(ilu), np.ascontiguousarray(v), x, geom)
+    rc = harness.skew_emulate(A.n, A.rows - 1, A.cols - 1, A.diag - 1, np.ascontiguousarray(ilu), np.ascontiguousarray(v), x, geom, E)
     return rc, x, geom
 
 
@@ -37,11 +36,12 @@ def test_bit_identical_to_crs_lusolve(oracle, harness, dims):
     oracle.scale_system(A, b, np.zeros(A.n))
     ilu = oracle.ilu0(A)
     v = np.random.RandomState(3).standard_normal(A.n)
-    rc, x, geom = _run(harness, A, ilu, v)
-    assert rc == 0
-    assert tuple(geom[:3]) == (dims[0] + 1, dims[1] + 1, dims[2] + 1)
-    assert geom[3] <= 32 and geom[3] * geom[4] >= geom[1]
-    assert np.array_equal(x, oracle.lu_precond(A, ilu, v))
+    for E in (3, 1, 7):                                          # request lead of the kernel configurations
+        rc, x, geom = _run(harness, A, ilu, v, E)
+        assert rc == 0
+        assert tuple(geom[:3]) == (dims[0] + 1, dims[1] + 1, dims[2] + 1)
+        assert geom[3] <= 29 and geom[3] * geom[4] >= geom[1]
+        assert np.array_equal(x, oracle.lu_precond(A, ilu, v))
 
 
 def test_other_structures_are_refused(oracle, harness):
@@ -71,5 +71,5 @@ def test_no_deadlock_for_any_warp_count_or_interleaving(oracle, harness, dims, n
     ref = oracle.lu_precond(A, ilu, v)
     for seed in (1, 2, 3):
         rc = harness.skew_emulate_concurrent(A.n, A.rows - 1, A.cols - 1, A.diag - 1, np.ascontiguousarray(ilu), np.ascontiguousarray(v),
-                                             np.ascontiguousarray(ref), nw, seed)
+                                             np.ascontiguousarray(ref), nw, seed, 3)
         assert rc == 0, (rc, seed)
