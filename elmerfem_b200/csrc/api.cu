@@ -55,7 +55,7 @@ static void ensure_runtime(Handle &h) {
   h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 16));
   h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", 100);
   h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
-  h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", 0);   // 0 level kernel (default), 1 task kernel, -1 time both and pick
+  h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", -2);  // 0 level kernel, 1 task kernel, 2 skewed lanes, 3 wave tiles, -1 time level/task and pick, -2 (default) wave tiles where the grid stencil is detected and they win
   h.sk_blocks_per_sm = env_int("B200_SKEW_BLOCKS_PER_SM", 0);
   h.sk_cfg = env_int("B200_SKEW_CFG", 0);
   h.sk_wpb = env_int("B200_SKEW_WPB", 0);

@@ -150,12 +150,13 @@ static void launch_coresident(const void *kernel, int blocks, int threads, cudaS
 }
 
 static void tri_autotune(Handle &h);
+static void tri_autotune_wave(Handle &h);
 
 void ilu0_factor(Handle &h) {
   B200_REQUIRE(h.have_vals, "ILU0 requested before b200_set_values");
   tri_analyse(h);
   if (h.tri_mode == 2) skew_analyse(h);
-  else if (h.tri_mode == 3) wave_analyse(h);
+  else if (h.tri_mode == 3 || h.tri_mode == -2) wave_analyse(h);
   else if (h.tri_mode != 0) tritask_analyse(h);
   cudaStream_t st = h.stream;
   h.d_ilu.ensure(h.lnnz());
@@ -186,7 +187,8 @@ void ilu0_factor(Handle &h) {
   B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "ILU0 factorisation: dependency wait timed out");
   h.ilu_valid = true; h.ilu_exists = true;
   h.st_factor_launch = h.n > 0 ? (h.tt_ready ? 7 : 5) : 0;   // factor, invert diag, 2 x SELL refresh, diag gather, 2 x stream refresh
-  if (h.tri_mode < 0) tri_autotune(h);
+  if (h.tri_mode == -1) tri_autotune(h);
+  else if (h.tri_mode == -2) tri_autotune_wave(h);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -629,6 +631,36 @@ static void tri_autotune(Handle &h) {
   h.tt_ms_level = ms[0] / 2; h.tt_ms_task = ms[1] / 2;
   h.tri_mode = ms[1] < ms[0] ? 1 : 0;
   h.st_launch -= 18; h.st_pcond -= 6;
+  a.release(); b.release();
+}
+
+// Default (B200_TRI_MODE unset): when the factor is that of a structured-grid stencil, the level kernel and the wave-tile kernel
+// (bit-identical results) are timed once on the real factor and the faster one is kept; the loser's plan is released.
+static void tri_autotune_wave(Handle &h) {
+  if (h.n == 0 || !h.wv.ready) { h.tri_mode = 0; return; }
+  cudaStream_t st = h.stream;
+  DBuf<double> a, b; a.ensure(h.n); b.ensure(h.n);
+  B200_CUDA(cudaMemsetAsync(h.ctrl.p, 0, sizeof(Ctrl), st));
+  B200_CUDA(cudaMemsetAsync(a.p, 0, (size_t)h.n * sizeof(double), st));
+  float ms[2] = {0, 0};
+  const int modes[2] = {0, 3};
+  for (int m = 0; m < 2; ++m) {
+    h.tri_mode = modes[m];
+    lu_apply(h, b.p, a.p);
+    B200_CUDA(cudaEventRecord(h.evf0, st));
+    for (int r = 0; r < 3; ++r) lu_apply(h, b.p, a.p);
+    B200_CUDA(cudaEventRecord(h.evf1, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaEventElapsedTime(&ms[m], h.evf0, h.evf1));
+  }
+  B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "triangular solve: dependency wait timed out while tuning");
+  h.tt_ms_level = ms[0] / 3; h.tt_ms_task = ms[1] / 3;
+  h.tri_mode = ms[1] < ms[0] ? 3 : 0;
+  if (h.tri_mode == 0) wave_release(h);
+  if (getenv("B200_WAVE_DEBUG")) fprintf(stderr, "[wave] autotune: level kernel %.3f ms, wave tiles %.3f ms per application -> mode %d\n", ms[0] / 3, ms[1] / 3, h.tri_mode);
+  h.st_launch -= 28; h.st_pcond -= 8;
   a.release(); b.release();
 }
 

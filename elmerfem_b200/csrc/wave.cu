@@ -7,8 +7,11 @@
 // of a tile come from L2, fetched E steps ahead by loader threads (sentinel protocol: the result vector is pre-filled with a NaN payload
 // no arithmetic produces, a loader that still finds it polls).  Shearing the line coordinate (beta = b + c) makes the tile DAG acyclic
 // with dependencies only towards smaller (sigma, C), so neighbouring tiles run concurrently, one L2 hop apart, and the critical path
-// holds (number of tile rows + columns) hops instead of one per level.  Matrix entries and right-hand sides of a tile step are one
-// contiguous block each, moved by TMA bulk copies into an NSLOT-deep shared-memory ring (mbarrier completion).
+// holds (number of tile rows + columns) hops instead of one per level.  Matrix entries and right-hand sides of a tile step are
+// contiguous rows of NTHR values; every compute thread streams ITS column of them into an NSLOT-deep shared-memory ring with cp.async
+// (coalesced 256-byte warp requests, thread-private slots: no synchronisation beyond cp.async.wait_group, and steps in which the
+// thread has no row are not fetched at all).  [A TMA bulk-copy ring was measured first: one thread pays ~300 cycles per step for the
+// expect_tx + copy issue and ~260 for the mbarrier wait, more than the whole step otherwise costs.]
 // Arithmetic: the reference's operations in the reference's order (entries in ascending column order, separate multiply / subtract
 // roundings, inverse diagonal last); pad entries (neighbours outside the grid) are (+0) x (+0).  Bit-identical to the level kernel and
 // to the CPU loop.
@@ -52,20 +55,25 @@ __global__ void k_wave_sentinel(long long nv, double *__restrict__ x) {
 }
 
 __device__ __forceinline__ unsigned wv_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void wv_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void wv_mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void wv_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool wv_mbar_try_wait(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
+__device__ __forceinline__ void wv_prefetch_l2(const void *p, unsigned bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
+#ifdef WV_NO_BAR
+__device__ __forceinline__ void wv_bar(int nthreads) { asm volatile("" ::: "memory"); }
+#else
 __device__ __forceinline__ void wv_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
-__device__ __forceinline__ void wv_st_relaxed(double *p, double v) { asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+#endif
+// the sweep's own store: no compiler barrier (nothing in this thread reads the result vector)
+#ifndef WV_ST
+#define WV_ST 0
+#endif
+__device__ __forceinline__ void wv_st_relaxed(double *p, double v) {
+#if WV_ST == 0
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v));
+#elif WV_ST == 1
+  asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v));
+#elif WV_ST == 2
+  asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v));
+#endif
+}
 __device__ __forceinline__ double wv_ld_relaxed(const double *p) {
   double v; asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v;
 }
@@ -75,101 +83,140 @@ __device__ __forceinline__ long long wv_gtime() { long long t; asm volatile("mov
 //   forward  (UPPER = false): out_i = rhs_i - sum_{j<i} L_ij out_j                   (4642-4649)
 //   backward (UPPER = true) : out_i = Dinv_i * (rhs_i - sum_{j>i} U_ij out_j)       (4653-4660)
 // S: matrix stream, RHS: right-hand side at pos(sweep coordinates); Q: result at pos(mirrored sweep coordinates), pre-filled with the
-// sentinel.  E: steps a halo row is requested ahead.  Block = TB * TC compute threads + HW loader warps.
-template <bool UPPER, int TB, int TC, int NSLOT, int E>
-__global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32)) k_wave(WaveGeom g, const int *__restrict__ tile_of, const int *__restrict__ tile_sig,
-                                                                                       const int *__restrict__ tile_grp, const double *__restrict__ S,
-                                                                                       const double *__restrict__ RHS, double *Q, Ctrl *ctrl, long long *trace) {
+// sentinel.  E: steps a halo row is requested ahead; PF: steps the L2 prefetch runs ahead.
+// Block = TB * TC compute threads + HW loader warps (these take part in the step barrier) + one free-running prefetch warp.
+//
+// Matrix entries: every thread reads ITS column of the stream straight into registers (coalesced 256-byte warp loads, L1 bypassed),
+// three steps before the value is used, from L2 -- where the prefetch warp has put the block PF steps earlier with one
+// cp.async.bulk.prefetch.L2 per WV_PFG steps.  Steps in which the thread has no row are not loaded.  [Measured alternatives: a TMA
+// bulk-copy ring costs one thread ~300 cycles per step for expect_tx + copy issue and ~260 for the mbarrier wait; a cp.async ring
+// costs the LSU 16 LDGSTS + 15 LDS per thread and step, +240 cycles per step.]
+constexpr int WV_PFG = 4;      // steps per prefetch instruction
+template <bool UPPER, int TB, int TC, int E, int PF>
+__global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) + 32) k_wave(WaveGeom g, const int *__restrict__ tile_of, const int *__restrict__ tile_sig,
+                                                                                            const int *__restrict__ tile_grp, const double *__restrict__ S,
+                                                                                            const double *__restrict__ RHS, double *Q, Ctrl *ctrl, long long *trace) {
   if (ctrl->done) return;
   constexpr int NTHR = TB * TC, NH = TB + 2 + 2 * TC, NE = UPPER ? 14 : 13;
-  constexpr int SLOT_D = (NE + 1) * NTHR;                         // doubles per ring slot: matrix rows, then the right-hand sides
   constexpr int YW = TB + 2, YH = TC + 1, YSLOT = YW * YH;
-  constexpr int NALL = NTHR + 32 * ((NH + 31) / 32);
+  constexpr int NALL = NTHR + 32 * ((NH + 31) / 32);                // threads of the step barrier
+  constexpr int NA = UPPER ? 7 : 5, NB = 2, NC = UPPER ? 6 : 7;     // values per step of the three chains (see below)
   extern __shared__ __align__(128) unsigned char wv_smem[];
-  double *ring = reinterpret_cast<double *>(wv_smem);
-  double *Yr = ring + (size_t)NSLOT * SLOT_D;
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(Yr + WV_RING * YSLOT);
+  double *Yr = reinterpret_cast<double *>(wv_smem);
+  volatile int *done_steps = reinterpret_cast<volatile int *>(Yr + WV_RING * YSLOT);   // steps of the current tile behind the barrier
   const int tid = threadIdx.x;
-  if (tid == 0) {
-#pragma unroll
-    for (int q = 0; q < NSLOT; ++q) wv_mbar_init(wv_smem_u32(bars + q), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
   const int NT = g.NT, NR = g.NR;
-  unsigned gs = 0;                                                  // tile steps consumed so far by this CTA (ring position / parity)
   long long spins = 0;
   for (int k = blockIdx.x; k < g.ntiles; k += gridDim.x) {
     const int sig = tile_sig[k], C = tile_grp[k];
     const long long step0 = (long long)k * NT;
-    for (int q = tid; q < WV_RING * YSLOT; q += NALL) Yr[q] = 0.0;
+    __syncthreads();                                                // every warp (the free-running prefetch warp too) has left the previous tile
+    for (int q = tid; q < WV_RING * YSLOT; q += NALL + 32) Yr[q] = 0.0;
+    if (tid == 0) *done_steps = 0;
     long long tr0 = 0, tr_polls = 0;
     if (trace && tid == NTHR) tr0 = wv_gtime();
-    auto issue = [&](int tau, unsigned slot) {                     // step tau of this tile -> ring slot (one thread)
-      const unsigned bar = wv_smem_u32(bars + slot);
-      wv_mbar_expect_tx(bar, SLOT_D * 8);
-      wv_bulk_g2s(wv_smem_u32(ring + (size_t)slot * SLOT_D), S + (step0 + tau) * (NE * NTHR), NE * NTHR * 8, bar);
-      wv_bulk_g2s(wv_smem_u32(ring + (size_t)slot * SLOT_D + NE * NTHR), RHS + (step0 + tau) * NTHR, NTHR * 8, bar);
-    };
-    __syncthreads();                                                // ring zeroed, previous tile's slots all consumed
-    if (tid == NTHR) {
-#pragma unroll
-      for (int q = 0; q < NSLOT; ++q) if (q < NT) issue(q, (gs + q) % NSLOT);
-    }
+    __syncthreads();                                                // ring zeroed
     if (tid < NTHR) {
       // ---------------- compute thread: line (jb, w) ----------------
+      // Three independent chains per step, so that only the five terms that need the results of step tau - 1 follow the barrier:
+      //   A: row of step tau      terms 8..12 (B: a+1 | A: a-1, a, a+1 | own a-1) on `hi`, publish               (backward: the whole row)
+      //   B: row of step tau + 1  terms 6, 7  (B: a-1, a)                          mid -> hi
+      //   C: row of step tau + 2  terms 0..5  (D, C: a-1, a, a+1)                  rhs -> mid
+      // in the reference's left-to-right order (4642-4649).  The backward row starts with its newest operand (4653-4660): nothing of it
+      // can be summed early, only the products are formed ahead.
+      // Registers: VA / VB / VC hold the entries chain A / B / C needs, four steps deep (loop unrolled by four: constant indices);
+      // at step tau the loads of steps tau + 3 (A), tau + 4 (B), tau + 5 (C) are issued, i.e. each value three steps before its use.
       const int jb = tid % TB, w = tid / TB;
       const WaveLine ln = wv_line(g, sig, C, jb, w);
       double *qp = Q + (ln.valid ? wv_pos_mirror(g, tile_of, 0, ln.b, ln.c) : 0);     // row a at qp - a * NTHR
       const double *yA = Yr + (w + 1) * YW + (jb + 1), *yB = Yr + w * YW + (jb + 2), *yC = Yr + w * YW + (jb + 1), *yD = Yr + w * YW + jb;
       double *yO = Yr + (w + 1) * YW + (jb + 2);
-      double Am = 0.0, A0 = 0.0, Bm = 0.0, B0 = 0.0, Cm = 0.0, C0 = 0.0, Cp = 0.0, Dm = 0.0, D0 = 0.0, Dp = 0.0, h = 0.0;
-      double v[NE], rv, acc8 = 0.0, P[8];
-      auto fetch = [&](unsigned step) {                            // values of the step into registers, and what does not wait for step - 1
-        const unsigned slot = step % NSLOT, bar = wv_smem_u32(bars + slot), parity = (step / NSLOT) & 1u;
-        while (!wv_mbar_try_wait(bar, parity)) { if (++spins > WV_SPIN_LIMIT) { ctrl->spin_timeout = 1; break; } }
-        const double *sp = ring + (size_t)slot * SLOT_D + tid;
+      const double *gS = S + step0 * (NE * NTHR) + tid, *gR = RHS + step0 * NTHR + tid;
+      const int tau0 = ln.tau0;
+      const bool valid = ln.valid;
+      double Am = 0.0, A0 = 0.0, B0 = 0.0, Cm = 0.0, C0 = 0.0, Dm = 0.0, D0 = 0.0, h = 0.0;
+      double hi = 0.0, mid = 0.0;                                   // forward: partial rows of steps tau and tau + 1
+      double P1[8], P2[6];                                          // backward: products of steps tau (terms 0..7) and tau + 1 (terms 0..5)
+      double VA[4][NA], VB[4][NB], VC[4][NC];
 #pragma unroll
-        for (int e = 0; e < NE; ++e) v[e] = sp[e * NTHR];
-        rv = sp[NE * NTHR];
-        if (!UPPER) {
-          acc8 = nfms(rv, v[0], Dm); acc8 = nfms(acc8, v[1], D0); acc8 = nfms(acc8, v[2], Dp);
-          acc8 = nfms(acc8, v[3], Cm); acc8 = nfms(acc8, v[4], C0); acc8 = nfms(acc8, v[5], Cp);
-          acc8 = nfms(acc8, v[6], Bm); acc8 = nfms(acc8, v[7], B0);
-        } else {
-          P[0] = __dmul_rn(v[0], Dm); P[1] = __dmul_rn(v[1], D0); P[2] = __dmul_rn(v[2], Dp);
-          P[3] = __dmul_rn(v[3], Cm); P[4] = __dmul_rn(v[4], C0); P[5] = __dmul_rn(v[5], Cp);
-          P[6] = __dmul_rn(v[6], Bm); P[7] = __dmul_rn(v[7], B0);
-        }
-      };
-      fetch(gs);
-      for (int tau = 0; tau < NT; ++tau) {
-        const double An = yA[((tau - 1) & (WV_RING - 1)) * YSLOT], Bn = yB[((tau - 1) & (WV_RING - 1)) * YSLOT];
-        const int a = tau - ln.tau0;
-        const bool active = ln.valid && (unsigned)a < (unsigned)NR;
-        double acc;
-        if (!UPPER) {
-          acc = nfms(acc8, v[8], Bn); acc = nfms(acc, v[9], Am); acc = nfms(acc, v[10], A0); acc = nfms(acc, v[11], An); acc = nfms(acc, v[12], h);
-        } else {
-          acc = nfms(rv, v[12], h); acc = nfms(acc, v[11], An); acc = nfms(acc, v[10], A0); acc = nfms(acc, v[9], Am); acc = nfms(acc, v[8], Bn);
+      for (int e = 0; e < 8; ++e) P1[e] = 0.0;
 #pragma unroll
-          for (int e = 7; e >= 0; --e) acc = __dsub_rn(acc, P[e]);
-          acc = __dmul_rn(v[13], acc);
-        }
-        if (acc != acc) acc = __longlong_as_double((long long)CANON_NAN);
-        if (!active) acc = 0.0;
-        yO[(tau & (WV_RING - 1)) * YSLOT] = acc;
-        if (active) wv_st_relaxed(qp - (long long)a * NTHR, acc);
-        h = acc;
-        Am = A0; A0 = An; Bm = B0; B0 = Bn;
-        // everything of step tau + 1 that does not depend on step tau
-        const double Cn = yC[((tau - 2) & (WV_RING - 1)) * YSLOT], Dn = yD[((tau - 4) & (WV_RING - 1)) * YSLOT];
-        Cm = C0; C0 = Cp; Cp = Cn; Dm = D0; D0 = Dp; Dp = Dn;
-        if (tau + 1 < NT) fetch(gs + tau + 1);
-        wv_bar(NALL);
+      for (int e = 0; e < 6; ++e) P2[e] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int e = 0; e < NA; ++e) VA[q][e] = 0.0;
+#pragma unroll
+        for (int e = 0; e < NB; ++e) VB[q][e] = 0.0;
+#pragma unroll
+        for (int e = 0; e < NC; ++e) VC[q][e] = 0.0;
       }
-    } else {
+      // (no row of a compute thread lies in steps 0 .. WV_PRE - 1, so nothing has to be loaded before the loop)
+      for (int t0 = 0; t0 < NT; t0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int tau = t0 + u;
+          if (tau < NT) {
+            const int un = (u + 3) & 3;
+            {                                                       // chain A of step tau + 3: terms 8..12 (+ inverse diagonal, right-hand side)
+              const int st = tau + 3;
+              if (valid && (unsigned)(st - tau0) < (unsigned)NR) {
+                const double *src = gS + (long long)st * (NE * NTHR);
+#pragma unroll
+                for (int e = 0; e < 5; ++e) VA[un][e] = ld_stream(src + (8 + e) * NTHR);
+                if (UPPER) { VA[un][5] = ld_stream(src + 13 * NTHR); VA[un][6] = ld_stream(gR + (long long)st * NTHR); }
+              }
+            }
+            {                                                       // chain B of step tau + 4: terms 6, 7
+              const int st = tau + 4;
+              if (valid && (unsigned)(st - tau0) < (unsigned)NR) {
+                const double *src = gS + (long long)st * (NE * NTHR);
+                VB[un][0] = ld_stream(src + 6 * NTHR); VB[un][1] = ld_stream(src + 7 * NTHR);
+              }
+            }
+            {                                                       // chain C of step tau + 5: terms 0..5 (+ right-hand side)
+              const int st = tau + 5;
+              if (valid && (unsigned)(st - tau0) < (unsigned)NR) {
+                const double *src = gS + (long long)st * (NE * NTHR);
+#pragma unroll
+                for (int e = 0; e < 6; ++e) VC[un][e] = ld_stream(src + e * NTHR);
+                if (!UPPER) VC[un][6] = ld_stream(gR + (long long)st * NTHR);
+              }
+            }
+            const int r1 = ((tau - 1) & (WV_RING - 1)) * YSLOT, r3 = ((tau - 3) & (WV_RING - 1)) * YSLOT;
+            const double An = yA[r1], Bn = yB[r1], Cn = yC[r1], Dn = yD[r3];
+            const int a = tau - tau0;
+            const bool active = valid && (unsigned)a < (unsigned)NR;
+            double acc;
+            if (!UPPER) {
+              acc = nfms(hi, VA[u][0], Bn); acc = nfms(acc, VA[u][1], Am); acc = nfms(acc, VA[u][2], A0);
+              acc = nfms(acc, VA[u][3], An); acc = nfms(acc, VA[u][4], h);
+              hi = nfms(mid, VB[u][0], B0); hi = nfms(hi, VB[u][1], Bn);
+              mid = nfms(VC[u][6], VC[u][0], Dm); mid = nfms(mid, VC[u][1], D0); mid = nfms(mid, VC[u][2], Dn);
+              mid = nfms(mid, VC[u][3], Cm); mid = nfms(mid, VC[u][4], C0); mid = nfms(mid, VC[u][5], Cn);
+            } else {
+              acc = nfms(VA[u][6], VA[u][4], h); acc = nfms(acc, VA[u][3], An); acc = nfms(acc, VA[u][2], A0);
+              acc = nfms(acc, VA[u][1], Am); acc = nfms(acc, VA[u][0], Bn);
+#pragma unroll
+              for (int e = 7; e >= 0; --e) acc = __dsub_rn(acc, P1[e]);
+              acc = __dmul_rn(VA[u][5], acc);
+#pragma unroll
+              for (int e = 0; e < 6; ++e) P1[e] = P2[e];
+              P1[6] = __dmul_rn(VB[u][0], B0); P1[7] = __dmul_rn(VB[u][1], Bn);
+              P2[0] = __dmul_rn(VC[u][0], Dm); P2[1] = __dmul_rn(VC[u][1], D0); P2[2] = __dmul_rn(VC[u][2], Dn);
+              P2[3] = __dmul_rn(VC[u][3], Cm); P2[4] = __dmul_rn(VC[u][4], C0); P2[5] = __dmul_rn(VC[u][5], Cn);
+            }
+            if (acc != acc) acc = __longlong_as_double((long long)CANON_NAN);
+            if (!active) acc = 0.0;
+            yO[(tau & (WV_RING - 1)) * YSLOT] = acc;
+            if (active) wv_st_relaxed(qp - (long long)a * NTHR, acc);
+            h = acc;
+            Am = A0; A0 = An; B0 = Bn; Cm = C0; C0 = Cn; Dm = D0; D0 = Dn;
+            wv_bar(NALL);
+          }
+        }
+      }
+    } else if (tid < NALL) {
       // ---------------- loader thread: halo line hh ----------------
       const int hh = tid - NTHR;
       int jb = 0, w = 0;
@@ -181,6 +228,7 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32)) 
       double *yO = Yr + (w + 1) * YW + (jb + 2);
       const int tau0 = ln.tau0;
       double H[E + 1];
+      long long cy_bar = 0;
 #pragma unroll
       for (int q = 0; q < E + 1; ++q) H[q] = 0.0;
       auto request = [&](int tau) -> double {                     // the row the line publishes at step tau
@@ -207,18 +255,26 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32)) 
               } while (is_sentinel(head));
             }
             if (hh < NH) yO[(tau & (WV_RING - 1)) * YSLOT] = head;
+            const long long c1 = trace ? clock64() : 0;
             wv_bar(NALL);
-            // the slot of step tau was read during step tau - 1: free since the previous barrier
-            if (tid == NTHR && tau + NSLOT < NT) issue(tau + NSLOT, (gs + tau) % NSLOT);
+            if (trace) cy_bar += clock64() - c1;
+            if (tid == NTHR) *done_steps = tau + 1;
           }
         }
       }
       if (trace) {
-        if (tid == NTHR) { long long *r = trace + ((UPPER ? g.ntiles : 0) + (long long)k) * 4; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); r[0] = tr0; r[1] = wv_gtime(); r[3] = smid; }
-        if (tr_polls) atomicAdd((unsigned long long *)(trace + ((UPPER ? g.ntiles : 0) + (long long)k) * 4 + 2), (unsigned long long)tr_polls);
+        if (tid == NTHR) { long long *r = trace + ((UPPER ? g.ntiles : 0) + (long long)k) * 8; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); r[0] = tr0; r[1] = wv_gtime(); r[3] = smid; r[5] = cy_bar; }
+        if (tr_polls) atomicAdd((unsigned long long *)(trace + ((UPPER ? g.ntiles : 0) + (long long)k) * 8 + 2), (unsigned long long)tr_polls);
+      }
+    } else if (PF > 0 && tid == NALL) {
+      // ---------------- prefetch warp (one lane): stream blocks of WV_PFG steps into L2, at most PF steps ahead of the barrier ----------------
+      for (int st = 0; st < NT; st += WV_PFG) {
+        while (*done_steps + PF < st) { if (++spins > WV_SPIN_LIMIT) break; }
+        const int ns = (NT - st < WV_PFG) ? NT - st : WV_PFG;
+        wv_prefetch_l2(S + (step0 + st) * (NE * NTHR), (unsigned)(ns * NE * NTHR * 8));
+        wv_prefetch_l2(RHS + (step0 + st) * NTHR, (unsigned)(ns * NTHR * 8));
       }
     }
-    gs += NT;
   }
 }
 
@@ -242,8 +298,8 @@ void wave_analyse(Handle &h) {
     if (getenv("B200_WAVE_DEBUG")) fprintf(stderr, "[wave] not usable (%s): level kernel stays\n", why);
     return;
   }
-  const int cfg = h.wv_cfg;
-  const int TB = (cfg == 1) ? 16 : ((cfg == 2) ? 32 : ((cfg == 3) ? 8 : 16)), TC = (cfg == 1) ? 4 : ((cfg == 2) ? 4 : 8);
+  const int cfg = h.wv_cfg;                                         // tile shape; the ring depth / request lead go with it (wave_launch)
+  const int TB = (cfg == 5) ? 32 : ((cfg == 3) ? 8 : 16), TC = (cfg == 1 || cfg == 5) ? 4 : 8;
   WaveTiles T;
   wv_plan(w.g, sg.NR, sg.NL, sg.NP, TB, TC, T);
   const WaveGeom &g = w.g;
@@ -272,37 +328,35 @@ void wave_refresh_values(Handle &h) {
   B200_CUDA(cudaGetLastError());
 }
 
-template <bool UPPER, int TB, int TC, int NSLOT, int E>
+template <bool UPPER, int TB, int TC, int E, int PF>
 static void wave_launch_cfg(Handle &h, const double *S, const double *rhs, double *out) {
-  const void *kern = (const void *)k_wave<UPPER, TB, TC, NSLOT, E>;
-  constexpr int NTHR = TB * TC, NH = TB + 2 + 2 * TC, NE = UPPER ? 14 : 13, NALL = NTHR + 32 * ((NH + 31) / 32);
-  const size_t smem = (size_t)NSLOT * (NE + 1) * NTHR * 8 + (size_t)WV_RING * (TB + 2) * (TC + 1) * 8 + NSLOT * 8;
+  const void *kern = (const void *)k_wave<UPPER, TB, TC, E, PF>;
+  constexpr int NTHR = TB * TC, NH = TB + 2 + 2 * TC, NBLK = NTHR + 32 * ((NH + 31) / 32) + 32;
+  const size_t smem = (size_t)WV_RING * (TB + 2) * (TC + 1) * 8 + 16;
   int dev = 0, sms = 0, per_sm = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NALL, smem));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NBLK, smem));
   B200_REQUIRE(per_sm >= 1, "wave-tile triangular solve: kernel does not fit on an SM");
-  const int want = h.wv_blocks_per_sm > 0 ? std::min(per_sm, h.wv_blocks_per_sm) : per_sm;
+  const int want = h.wv_blocks_per_sm > 0 ? std::min(per_sm, h.wv_blocks_per_sm) : std::min(per_sm, 2);
   const int blocks = std::max(1, std::min(sms * want, h.wv.g.ntiles));
   WaveGeom g = h.wv.g; Ctrl *ctrl = h.ctrl.p; long long *trace = h.wv.trace_on ? h.wv.trace.p : nullptr;
   const int *tile_of = h.wv.tile_of.p, *tsig = h.wv.tile_sig.p, *tgrp = h.wv.tile_grp.p;
   void *argv[] = {(void *)&g, (void *)&tile_of, (void *)&tsig, (void *)&tgrp, (void *)&S, (void *)&rhs, (void *)&out, (void *)&ctrl, (void *)&trace};
-  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(NALL), argv, smem, h.stream));
+  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(NBLK), argv, smem, h.stream));
 }
 
 template <bool UPPER>
 static void wave_launch(Handle &h, const double *S, const double *rhs, double *out) {
-  const WaveGeom &g = h.wv.g;
-  if (g.TB == 16 && g.TC == 8) {
-    if (h.wv_e == 7) wave_launch_cfg<UPPER, 16, 8, 6, 7>(h, S, rhs, out);
-    else if (h.wv_e == 1) wave_launch_cfg<UPPER, 16, 8, 6, 1>(h, S, rhs, out);
-    else wave_launch_cfg<UPPER, 16, 8, 6, 3>(h, S, rhs, out);
+  switch (h.wv_cfg) {                                                // <tile TB x TC, request lead, prefetch lead>
+    case 1: wave_launch_cfg<UPPER, 16, 4, 7, 16>(h, S, rhs, out); break;
+    case 2: wave_launch_cfg<UPPER, 16, 8, 7, 0>(h, S, rhs, out); break;
+    case 3: wave_launch_cfg<UPPER, 8, 8, 7, 16>(h, S, rhs, out); break;
+    case 4: wave_launch_cfg<UPPER, 16, 8, 7, 32>(h, S, rhs, out); break;
+    case 5: wave_launch_cfg<UPPER, 32, 4, 7, 16>(h, S, rhs, out); break;
+    case 6: wave_launch_cfg<UPPER, 16, 8, 3, 16>(h, S, rhs, out); break;
+    default: wave_launch_cfg<UPPER, 16, 8, 7, 16>(h, S, rhs, out); break;
   }
-  else if (g.TB == 16 && g.TC == 4) wave_launch_cfg<UPPER, 16, 4, 8, 3>(h, S, rhs, out);
-  else if (g.TB == 32 && g.TC == 4) wave_launch_cfg<UPPER, 32, 4, 6, 3>(h, S, rhs, out);
-  else if (g.TB == 8 && g.TC == 8) wave_launch_cfg<UPPER, 8, 8, 8, 3>(h, S, rhs, out);
-  else throw Error("wave-tile triangular solve: no kernel for this tile shape");
 }
 
 void lu_apply_wave(Handle &h, double *u, const double *v) {
@@ -317,17 +371,17 @@ void lu_apply_wave(Handle &h, double *u, const double *v) {
   h.st_launch += 4; h.st_pcond++;
 }
 
-// per-tile trace (profiles/tools/wave_lab.cu): 4 long long per (sweep, tile): start, end, polls, smid
+// per-tile trace (profiles/tools/wave_lab.cu): 8 long long per (sweep, tile): start, end, polls, smid, cycles thread 0 waited for TMA / at the step barrier
 void wave_trace_enable(Handle &h, bool on) {
   if (on) {
-    const size_t m = (size_t)h.wv.g.ntiles * 2 * 4;
+    const size_t m = (size_t)h.wv.g.ntiles * 2 * 8;
     h.wv.trace.ensure(m);
     B200_CUDA(cudaMemsetAsync(h.wv.trace.p, 0, m * sizeof(long long), h.stream));
   }
   h.wv.trace_on = on;
 }
 void wave_trace_fetch(Handle &h, std::vector<long long> &out) {
-  out.assign((size_t)h.wv.g.ntiles * 2 * 4, 0);
+  out.assign((size_t)h.wv.g.ntiles * 2 * 8, 0);
   B200_CUDA(cudaStreamSynchronize(h.stream));
   B200_CUDA(cudaMemcpy(out.data(), h.wv.trace.p, out.size() * sizeof(long long), cudaMemcpyDeviceToHost));
 }

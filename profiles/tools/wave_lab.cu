@@ -94,13 +94,13 @@ int main(int argc, char **argv) {
   if (trace_file) {
     std::vector<long long> tr; wave_trace_fetch(h, tr);
     FILE *f = fopen(trace_file, "w");
-    fprintf(f, "# sweep tile start_ns end_ns polls smid\n");
+    fprintf(f, "# sweep tile start_ns end_ns polls smid loader0: cyc_mbar_wait cyc_bar cyc_issue -\n");
     const long long nt = g.ntiles;
     long long t0 = -1;
-    for (size_t k = 0; k < tr.size() / 4; ++k) if (tr[k * 4 + 0] && (t0 < 0 || tr[k * 4 + 0] < t0)) t0 = tr[k * 4 + 0];
+    for (size_t k = 0; k < tr.size() / 8; ++k) if (tr[k * 8 + 0] && (t0 < 0 || tr[k * 8 + 0] < t0)) t0 = tr[k * 8 + 0];
     for (int sw = 0; sw < 2; ++sw) for (long long k = 0; k < nt; ++k) {
-      const long long *r = &tr[(sw * nt + k) * 4];
-      fprintf(f, "%d %lld %lld %lld %lld %lld\n", sw, k, r[0] - t0, r[1] - t0, r[2], r[3]);
+      const long long *r = &tr[(sw * nt + k) * 8];
+      fprintf(f, "%d %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", sw, k, r[0] - t0, r[1] - t0, r[2], r[3], r[4], r[5], r[6], r[7]);
     }
     fclose(f);
     wave_trace_enable(h, false);
