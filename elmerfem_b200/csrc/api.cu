@@ -62,6 +62,7 @@ static void ensure_runtime(Handle &h) {
   h.wv_blocks_per_sm = env_int("B200_WAVE_BLOCKS_PER_SM", 0);
   h.wv_cfg = env_int("B200_WAVE_CFG", 0);
   h.wv_e = env_int("B200_WAVE_E", 3);
+  h.bl_host = env_int("B200_BICGSTABL_HOST", 0) != 0;
   h.tt_rows = env_int("B200_TT_ROWS", 0);
   h.tt_wpb = env_int("B200_TT_WPB", 0);
   h.tt_wait_ns = (unsigned)env_int("B200_TT_WAIT_NS", 100);

@@ -2,7 +2,8 @@
 // batched dot products in one pass with one deterministic grid reduction (replaces ddot/dnrm2,
 // mathlibs/src/blas/ddot.f, dnrm2.f as bound at fem/src/IterSolve.F90:910-912), batched
 // y = a x + b y updates (the !$OMP PARALLEL DO vector loops of fem/src/IterativeMethods.F90).
-// All streaming: 128-bit loads/stores where the vectors are 16-byte aligned, grid = multiple of 148.
+// All streaming: one coalesced 8-byte access per thread and vector (256 B per warp request; measured at 0.9-1.0 of the HBM peak,
+// so no 128-bit vectorisation), grid = multiple of 148.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -73,6 +74,19 @@ void axpby_batch(Handle &h, int n, int nops, const LinOp *ops) {
 void axpby(Handle &h, int n, double a, const double *x, double b, double *y) {
   LinOp o{x, y, a, b};
   axpby_batch(h, n, 1, &o);
+}
+
+// y = x / d with a true division (IDR(s) shadow space, IterativeMethods.F90:1659; GMRES basis vectors, huti_gmres.F90:189): x * (1/d)
+// differs from x / d in the last bit
+__global__ void __launch_bounds__(256) k_div_scalar(int n, const double *__restrict__ x, double *__restrict__ y, double d) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = __ddiv_rn(x[i], d);
+}
+void div_scalar(Handle &h, int n, const double *x, double *y, double d) {
+  if (n == 0) return;
+  int blocks = std::max(1, std::min((n + 255) / 256, h.blas_blocks));
+  k_div_scalar<<<blocks, 256, 0, h.stream>>>(n, x, y, d);
+  B200_CUDA(cudaGetLastError());
+  h.st_launch++;
 }
 
 __global__ void k_copy(int n, const double *__restrict__ x, double *__restrict__ y) {

@@ -159,6 +159,7 @@ struct Handle {
   // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
   SkewPlan sk; int sk_blocks_per_sm = 0, sk_cfg = 0, sk_wpb = 0;
   WavePlan wv; int wv_blocks_per_sm = 0, wv_cfg = 0, wv_e = 3;
+  bool bl_host = false;                           // B200_BICGSTABL_HOST=1: host-driven BiCGStab(l) (the round-1 driver) instead of the device-resident one
   TriTask TL, TU; bool tt_ready = false; int tri_mode = 0, tri_mode_cfg = 0, tt_rows = 0, tt_wpb = 0; unsigned tt_wait_ns = 100; int tt_pf = 16; DBuf<double> d_ytask, d_xtask;
   double tt_ms_level = 0, tt_ms_task = 0;
   // workspace

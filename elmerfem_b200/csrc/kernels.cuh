@@ -29,6 +29,7 @@ void axpby(Handle &h, int n, double a, const double *x, double b, double *y);
 struct LinOp { const double *x; double *y; double a, b; };
 void axpby_batch(Handle &h, int n, int nops, const LinOp *ops);
 void copy_vec(Handle &h, int n, const double *x, double *y);
+void div_scalar(Handle &h, int n, const double *x, double *y, double d);   // y = x / d (true division)
 void fill_vec(Handle &h, long long n, double *x, double v);
 // *flag = 1 if all x == 0 (device int)
 void fill_if_all_zero(Handle &h, int n, double *x, double v);

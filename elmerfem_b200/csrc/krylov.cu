@@ -267,7 +267,8 @@ struct Poller {
 };
 
 // ---------------------------------------------------------------------------------------------
-static void run_cg(Handle &h, const double *b, double *x, int pc, int maxit) {
+static void run_cg(Handle &h, const double *b, double *x, int pc, int maxit, int stopc) {
+  const bool true_resid = (stopc == 0 || stopc == 1);
   Solver S(h, pc, 4);
   double *Z = S.vec[0], *P = S.vec[1], *Q = S.vec[2], *R = S.vec[3];
   const int n = S.n; cudaStream_t st = S.st; Ctrl *ctrl = S.ctrl; double *sc = S.sc;
@@ -294,7 +295,7 @@ static void run_cg(Handle &h, const double *b, double *x, int pc, int maxit) {
       dot1(h, n, R, Z, sc + S_RHONEXT); reduce_scalars(h, sc + S_RHONEXT, 1);
     } else h.st_pcond++;
     // true residual ||A X - B|| (421-432); skipped by the pseudo-residual criteria
-    { SpmvArgs a; a.x = x; a.b = b; a.out = sc + S_RES2; a.ctrl = ctrl; spmv_any(h, a, EPI_RESID); reduce_scalars(h, sc + S_RES2, 1); }
+    if (true_resid) { SpmvArgs a; a.x = x; a.b = b; a.out = sc + S_RES2; a.ctrl = ctrl; spmv_any(h, a, EPI_RESID); reduce_scalars(h, sc + S_RES2, 1); }
     k_cg_check<<<1, 1, 0, st>>>(ctrl, sc);
     h.st_launch += 3;
     B200_CUDA(cudaGetLastError());
@@ -303,7 +304,8 @@ static void run_cg(Handle &h, const double *b, double *x, int pc, int maxit) {
   read_ctrl(h);
 }
 
-static void run_bicgstab(Handle &h, const double *b, double *x, int pc, int maxit) {
+static void run_bicgstab(Handle &h, const double *b, double *x, int pc, int maxit, int stopc) {
+  const bool true_resid = (stopc == 0 || stopc == 1);
   Solver S(h, pc, 8);
   double *RTLD = S.vec[0], *P = S.vec[1], *T1V = S.vec[2], *V = S.vec[3], *Sv = S.vec[4], *T2V = S.vec[5], *T = S.vec[6], *R = S.vec[7];
   const int n = S.n; cudaStream_t st = S.st; Ctrl *ctrl = S.ctrl; double *sc = S.sc;
@@ -328,7 +330,7 @@ static void run_bicgstab(Handle &h, const double *b, double *x, int pc, int maxi
     { SpmvArgs a; a.x = t2; a.y = T; a.w = Sv; a.out = sc + S_TS; a.ctrl = ctrl; spmv_any(h, a, EPI_DOT2); reduce_scalars(h, sc + S_TS, 2); }
     k_bicg_xr<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, x, t1, t2, R, Sv, T, RTLD, h.red_partials.p, h.red_counters.p);
     reduce_scalars(h, sc + S_RHONEXT, 2);
-    { SpmvArgs a; a.x = x; a.b = b; a.out = sc + S_RES2; a.ctrl = ctrl; spmv_any(h, a, EPI_RESID); reduce_scalars(h, sc + S_RES2, 1); }
+    if (true_resid) { SpmvArgs a; a.x = x; a.b = b; a.out = sc + S_RES2; a.ctrl = ctrl; spmv_any(h, a, EPI_RESID); reduce_scalars(h, sc + S_RES2, 1); }
     k_bicg_check<<<1, 1, 0, st>>>(ctrl, sc);
     h.st_launch += 5;
     B200_CUDA(cudaGetLastError());
@@ -550,6 +552,293 @@ L100:
   return res;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BiCGStab(l), device resident (the default; `Linear System Robust` keeps the host-driven driver above).
+// Every scalar of RealBiCGStabl lives in device memory; the (l+1) x (l+1) Gram algebra of the convex-polynomial part (940-1037: dgetrf /
+// dgetrs / dsymv / ddot on the small work array) runs in ONE thread, restated operation by operation; the dots of the BiCG part ride in
+// the epilogues of the SpMVs that produce their operand (sigma = rr.u_k with u_k = A M^-1 u_(k-1); the next rho1 = rr.r_k with
+// r_k = A M^-1 r_(k-1)) and ||r_0||^2 in the kernel that updates r_0, so a round is a fixed sequence of launches with no host
+// synchronisation: the stopping tests raise Ctrl::done, after which already-queued kernels return at once; the host polls the pinned
+// control block one round behind.  The reliable-update branch (1050-1079: recompute r = b' - A M^-1 x, flying restart) is queued every
+// round and skipped on the device (Ctrl::done = 2 for the length of the section) when `rcmp` is false.
+// Reductions over ranks per round: 2 per k (sigma; ||r_0||^2 stacked with the next rho1) + the Gram matrix = 2 l + 1, each a true
+// dependency of the next vector update.
+enum { BL_RHO0 = 0, BL_RHO1S, BL_ALPHA, BL_BETA, BL_OMEGA, BL_SIGMA, BL_RNRM2, BL_RHO1, BL_RNRM, BL_RNRM0, BL_BNRM, BL_MXX, BL_MXR, BL_XPDT, BL_RCMP, BL_ROUND,
+       BL_GRAM = 16, BL_GAM = 40 };
+constexpr int BL_MAXL = 5;       // (l+1)(l+2)/2 <= NRED Gram dots in one pass
+
+__global__ void k_bl_init(double *sc, double bnrm, double rnrm0) {
+  sc[BL_RHO0] = 1.0; sc[BL_ALPHA] = 0.0; sc[BL_OMEGA] = 1.0; sc[BL_SIGMA] = 1.0;
+  sc[BL_RNRM] = rnrm0; sc[BL_RNRM0] = rnrm0; sc[BL_BNRM] = bnrm; sc[BL_MXX] = rnrm0; sc[BL_MXR] = rnrm0; sc[BL_XPDT] = 0.0; sc[BL_RCMP] = 0.0; sc[BL_ROUND] = 1.0;
+}
+// 820-834: [rho0 = -omega rho0 at the top of a round]; beta = alpha (rho1 / rho0); rho0 = rho1
+__global__ void k_bl_rho(Ctrl *c, double *sc, int first) {
+  if (c->done) return;
+  double rho0 = sc[BL_RHO0];
+  if (first) rho0 = -sc[BL_OMEGA] * rho0;
+  const double rho1 = sc[BL_RHO1];
+  c->iters = (int)sc[BL_ROUND];
+  if (rho0 == 0.0) { c->info = HUTI_HALTED; c->done = 1; return; }
+  if (rho1 != rho1) { c->info = HUTI_DIVERGENCE; c->done = 1; return; }
+  sc[BL_BETA] = sc[BL_ALPHA] * (rho1 / rho0);
+  sc[BL_RHO0] = rho1; sc[BL_RHO1S] = rho1;
+}
+struct BlVecs { double *r[BL_MAXL + 1]; double *u[BL_MAXL + 1]; };
+// u_j = r_j - beta u_j, j < k   (836-842)
+__global__ void __launch_bounds__(256) k_bl_uupd(int n, const Ctrl *c, const double *sc, BlVecs v, int k) {
+  if (c->done) return;
+  const double beta = sc[BL_BETA];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int j = 0; j < k; ++j) v.u[j][i] = __dsub_rn(v.r[j][i], __dmul_rn(beta, v.u[j][i]));
+}
+// 852-862: alpha = rho1 / sigma
+__global__ void k_bl_alpha(Ctrl *c, double *sc) {
+  if (c->done) return;
+  const double sigma = sc[BL_SIGMA];
+  if (sigma == 0.0) { c->info = HUTI_HALTED; c->done = 1; return; }
+  if (sigma != sigma) { c->info = HUTI_DIVERGENCE; c->done = 1; return; }
+  sc[BL_ALPHA] = sc[BL_RHO1S] / sigma;
+}
+// x += alpha u_0 ; r_j -= alpha u_(j+1), j < k ; ||r_0||^2   (865-875, 886)
+__global__ void __launch_bounds__(256) k_bl_xr(int n, const Ctrl *c, double *sc, double *__restrict__ x, BlVecs v, int k, double *partials, unsigned int *counter) {
+  if (c->done) return;
+  const double alpha = sc[BL_ALPHA];
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    x[i] = __dadd_rn(x[i], __dmul_rn(alpha, v.u[0][i]));
+    for (int j = 0; j < k; ++j) {
+      const double rj = __dsub_rn(v.r[j][i], __dmul_rn(alpha, v.u[j + 1][i]));
+      v.r[j][i] = rj;
+      if (j == 0) acc[0] += rj * rj;
+    }
+  }
+  grid_reduce<1>(acc, partials, counter, [sc](double(&t)[1]) { sc[BL_RNRM2] = t[0]; });
+}
+// 886-909: rnrm = ||r_0||, running maxima, convergence inside the BiCG part (EarlyExit)
+__global__ void k_bl_check(Ctrl *c, double *sc, double Tol) {
+  if (c->done) return;
+  const double rnrm = sqrt(sc[BL_RNRM2]);
+  sc[BL_RNRM] = rnrm;
+  if (rnrm != rnrm) { c->info = HUTI_DIVERGENCE; c->done = 1; return; }
+  sc[BL_MXX] = fmax(sc[BL_MXX], rnrm); sc[BL_MXR] = fmax(sc[BL_MXR], rnrm);
+  const double errorind = rnrm / sc[BL_BNRM];
+  c->residual = errorind;
+  if (errorind < Tol) { c->info = HUTI_CONVERGENCE; c->done = 1; return; }
+  if (errorind != errorind) { c->info = HUTI_DIVERGENCE; c->done = 1; return; }
+}
+// 917-1011, 1036-1068: the convex polynomial part on the Gram matrix and the reliable-update decisions, one thread
+template <int L>
+__global__ void k_bl_poly(Ctrl *c, double *sc) {
+  if (c->done) return;
+  constexpr int ldr = L + 1, nw = 3 + 2 * (L + 1);
+  double rw[ldr * nw];
+  for (int q = 0; q < ldr * nw; ++q) rw[q] = 0.0;
+#define RW(i, j) rw[((i) - 1) + ((j) - 1) * ldr]
+  constexpr int z = 1, zz = z + (L + 1), y0 = zz + (L + 1), yl = y0 + 1, y = yl + 1;
+  { int q = 0; for (int i = 1; i <= L + 1; ++i) for (int j = 1; j <= i; ++j) RW(i, j) = sc[BL_GRAM + q++]; }
+  for (int j = 2; j <= L + 1; ++j) for (int i = 1; i <= j - 1; ++i) RW(i, j) = RW(j, i);
+  for (int j = 0; j <= L - 1; ++j) for (int i = 1; i <= L + 1; ++i) RW(i, zz + j) = RW(i, z + j);
+  // dgetrf on rwork(2:l, zz+1:zz+l-1): partial pivoting, unit lower
+  constexpr int m = L - 1;
+  double a[m * m]; int piv[m]; double tv[m];
+  for (int j = 1; j <= m; ++j) for (int i = 1; i <= m; ++i) a[(i - 1) + (j - 1) * m] = RW(i + 1, zz + j);
+  for (int j = 0; j < m; ++j) {
+    int p = j; double mx = fabs(a[j + j * m]);
+    for (int i = j + 1; i < m; ++i) if (fabs(a[i + j * m]) > mx) { mx = fabs(a[i + j * m]); p = i; }
+    piv[j] = p;
+    if (a[p + j * m] != 0.0) {
+      if (p != j) for (int k = 0; k < m; ++k) { const double t = a[j + k * m]; a[j + k * m] = a[p + k * m]; a[p + k * m] = t; }
+      const double r = 1.0 / a[j + j * m];
+      for (int i = j + 1; i < m; ++i) a[i + j * m] = __dmul_rn(a[i + j * m], r);
+    }
+    for (int k = j + 1; k < m; ++k) for (int i = j + 1; i < m; ++i) a[i + k * m] = __dsub_rn(a[i + k * m], __dmul_rn(a[i + j * m], a[j + k * m]));
+  }
+  auto lusolve = [&](double *b) {                              // dgetrs 'n'
+    for (int j = 0; j < m; ++j) if (piv[j] != j) { const double t = b[j]; b[j] = b[piv[j]]; b[piv[j]] = t; }
+    for (int j = 0; j < m; ++j) for (int i = j + 1; i < m; ++i) b[i] = __dsub_rn(b[i], __dmul_rn(b[j], a[i + j * m]));
+    for (int j = m - 1; j >= 0; --j) {
+      b[j] = b[j] / a[j + j * m];
+      for (int i = 0; i < j; ++i) b[i] = __dsub_rn(b[i], __dmul_rn(b[j], a[i + j * m]));
+    }
+  };
+  auto symv = [&](const double *A, const double *xv, double *yv) {   // dsymv 'u', reference BLAS loop order
+    for (int i = 0; i < L + 1; ++i) yv[i] = 0.0;
+    for (int j = 0; j < L + 1; ++j) {
+      const double t1 = xv[j]; double t2 = 0.0;
+      for (int i = 0; i < j; ++i) { yv[i] = __dadd_rn(yv[i], __dmul_rn(t1, A[i + j * ldr])); t2 = __dadd_rn(t2, __dmul_rn(A[i + j * ldr], xv[i])); }
+      yv[j] = __dadd_rn(__dadd_rn(yv[j], __dmul_rn(t1, A[j + j * ldr])), t2);
+    }
+  };
+  auto dots = [&](const double *xv, const double *yv) { double s = 0.0; for (int i = 0; i < L + 1; ++i) s = __dadd_rn(s, __dmul_rn(xv[i], yv[i])); return s; };
+  RW(1, y0) = -1.0;
+  for (int i = 2; i <= L; ++i) RW(i, y0) = RW(i, z);
+  for (int i = 1; i <= m; ++i) tv[i - 1] = RW(i + 1, y0);
+  lusolve(tv);
+  for (int i = 1; i <= m; ++i) RW(i + 1, y0) = tv[i - 1];
+  RW(L + 1, y0) = 0.0;
+  RW(1, yl) = 0.0;
+  for (int i = 1; i <= m; ++i) { RW(i + 1, yl) = RW(i + 1, z + L); tv[i - 1] = RW(i + 1, yl); }
+  lusolve(tv);
+  for (int i = 1; i <= m; ++i) RW(i + 1, yl) = tv[i - 1];
+  RW(L + 1, yl) = -1.0;
+  symv(&RW(1, z), &RW(1, y0), &RW(1, y));
+  double kappa0 = dots(&RW(1, y0), &RW(1, y));
+  if (kappa0 <= 0.0) { c->info = HUTI_HALTED; c->done = 1; return; }
+  kappa0 = sqrt(kappa0);
+  symv(&RW(1, z), &RW(1, yl), &RW(1, y));
+  double kappal = dots(&RW(1, yl), &RW(1, y));
+  if (kappal <= 0.0) { c->info = HUTI_HALTED; c->done = 1; return; }
+  kappal = sqrt(kappal);
+  symv(&RW(1, z), &RW(1, y0), &RW(1, y));
+  const double varrho = dots(&RW(1, yl), &RW(1, y)) / __dmul_rn(kappa0, kappal);
+  const double hatgamma = __dmul_rn(__dmul_rn(varrho / fabs(varrho), fmax(fabs(varrho), 7e-1)), kappa0) / kappal;
+  for (int i = 1; i <= L + 1; ++i) RW(i, y0) = __dsub_rn(RW(i, y0), __dmul_rn(hatgamma, RW(i, yl)));
+  sc[BL_OMEGA] = RW(L + 1, y0);
+  for (int j = 1; j <= L; ++j) sc[BL_GAM + j] = RW(j + 1, y0);
+  symv(&RW(1, z), &RW(1, y0), &RW(1, y));
+  double rnrm = dots(&RW(1, y0), &RW(1, y));
+  if (rnrm < 0.0) { c->info = HUTI_HALTED; c->done = 1; return; }
+  rnrm = sqrt(rnrm);
+  sc[BL_RNRM] = rnrm;
+  // 1050-1068
+  double mxx = fmax(sc[BL_MXX], rnrm), mxr = fmax(sc[BL_MXR], rnrm);
+  const double rnrm0 = sc[BL_RNRM0];
+  const bool xpdt = (rnrm < 1.0e-2 * rnrm0 && rnrm0 < mxx);
+  const bool rcmp = ((rnrm < 1.0e-2 * mxr && rnrm0 < mxr) || xpdt);
+  if (rcmp) mxr = rnrm;
+  if (xpdt) mxx = rnrm;
+  sc[BL_MXX] = mxx; sc[BL_MXR] = mxr; sc[BL_XPDT] = xpdt ? 1.0 : 0.0; sc[BL_RCMP] = rcmp ? 1.0 : 0.0;
+  c->residual = rnrm / sc[BL_BNRM];
+#undef RW
+}
+// 1016-1032: per element, for j = 1..l in order: u_0 -= g_j u_j ; x += g_j r_(j-1) ; r_0 -= g_j r_j
+__global__ void __launch_bounds__(256) k_bl_gamma(int n, const Ctrl *c, const double *sc, double *__restrict__ x, BlVecs v, int l) {
+  if (c->done) return;
+  double g[BL_MAXL + 1];
+  for (int j = 1; j <= l; ++j) g[j] = sc[BL_GAM + j];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double u0 = v.u[0][i], xi = x[i], r0 = v.r[0][i];
+    for (int j = 1; j <= l; ++j) {
+      u0 = __dsub_rn(u0, __dmul_rn(g[j], v.u[j][i]));
+      const double rjm1 = (j == 1) ? r0 : v.r[j - 1][i];       // j = 1: r_0 as it is before this j's own update (x is updated before r_0)
+      xi = __dadd_rn(xi, __dmul_rn(g[j], rjm1));
+      r0 = __dsub_rn(r0, __dmul_rn(g[j], v.r[j][i]));
+    }
+    v.u[0][i] = u0; x[i] = xi; v.r[0][i] = r0;
+  }
+}
+// opens / closes the conditional section of the reliable update: kernels in between see Ctrl::done != 0 and return
+__global__ void k_bl_section(Ctrl *c, const double *sc, int open) {
+  if (open) { if (c->done == 0 && sc[BL_RCMP] == 0.0) c->done = 2; }
+  else if (c->done == 2) c->done = 0;
+}
+// 1060-1068: r = b' - r ; flying restart: x' += t, x = 0, b' = r
+__global__ void __launch_bounds__(256) k_bl_rcmp(int n, const Ctrl *c, const double *sc, double *__restrict__ x, double *__restrict__ r, double *__restrict__ bp,
+                                                  double *__restrict__ xp, const double *__restrict__ t) {
+  if (c->done) return;
+  const bool xpdt = sc[BL_XPDT] != 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double ri = __dsub_rn(bp[i], r[i]);
+    r[i] = ri;
+    if (xpdt) { xp[i] = __dadd_rn(xp[i], t[i]); x[i] = 0.0; bp[i] = ri; }
+  }
+}
+// 1104-1131: end of a round
+__global__ void k_bl_roundend(Ctrl *c, double *sc, double Tol, double MaxTol, int MaxRounds) {
+  if (c->done) return;
+  const double errorind = sc[BL_RNRM] / sc[BL_BNRM];
+  c->residual = errorind;
+  const int Round = (int)sc[BL_ROUND];
+  c->iters = Round;
+  if (errorind < Tol) { c->info = HUTI_CONVERGENCE; c->done = 1; return; }
+  if (errorind > MaxTol || errorind != errorind) { c->info = HUTI_DIVERGENCE; c->done = 1; return; }
+  if (Round + 1 > MaxRounds) { c->info = HUTI_MAXITER; c->done = 1; return; }
+  sc[BL_ROUND] = (double)(Round + 1);
+}
+
+static HostResult run_bicgstabl_dev(Handle &h, const double *b, double *x, int pc, int MaxRounds, double Tol, double MaxTol, int l) {
+  HostResult res;
+  const int nw = 3 + 2 * (l + 1);
+  Solver S(h, pc, nw + 1);
+  const int n = S.n;
+  cudaStream_t st = S.st; Ctrl *ctrl = S.ctrl; double *sc = S.sc;
+  auto work = [&](int c) { return S.vec[c - 1]; };
+  double *t = S.vec[nw];
+  const int rr = 1, r = rr + 1, u = r + (l + 1), xp = u + (l + 1), bp = xp + 1;
+  { double nx2 = S.dot(x, x); if (nx2 == 0.0) copy_vec(h, n, b, x); }                 // 719
+  S.matvec(x, work(r));
+  S.lin(b, 1.0, work(r), -1.0);                               // r = b - r
+  double bnrm, rnrm0;
+  { const double *xs[2] = {b, work(r)}, *ys[2] = {b, work(r)}; double o[2]; S.dots(2, xs, ys, o); bnrm = sqrt(o[0]); rnrm0 = sqrt(o[1]); }
+  double errorind = rnrm0 / bnrm;
+  if (bnrm != bnrm || rnrm0 != rnrm0 || errorind != errorind) { res.info = HUTI_DIVERGENCE; res.residual = errorind; return res; }
+  if (errorind < Tol || errorind > MaxTol) { res.info = errorind < Tol ? HUTI_CONVERGENCE : HUTI_DIVERGENCE; res.residual = errorind; return res; }
+  copy_vec(h, n, work(r), work(rr)); copy_vec(h, n, work(r), work(bp));
+  copy_vec(h, n, x, work(xp));
+  fill_vec(h, n, x, 0.0);
+  k_bl_init<<<1, 1, 0, st>>>(sc, bnrm, rnrm0);
+  BlVecs V;
+  for (int j = 0; j <= BL_MAXL; ++j) { V.r[j] = work(r + std::min(j, l)); V.u[j] = work(u + std::min(j, l)); }
+  const double *gx[NRED], *gy[NRED]; int ng = 0;
+  for (int i = 1; i <= l + 1; ++i) for (int j = 1; j <= i; ++j) { gx[ng] = work(r + i - 1); gy[ng] = work(r + j - 1); ++ng; }
+  Poller poll(h);
+  auto pcond = [&](double *dst, double *src) -> double * { return S.precond(dst, src); };
+  int Round = 0;
+  for (Round = 1; Round <= MaxRounds; ++Round) {
+    dot1(h, n, work(rr), work(r), sc + BL_RHO1); reduce_scalars(h, sc + BL_RHO1, 1);          // rho1 of k = 1
+    for (int k = 1; k <= l; ++k) {
+      k_bl_rho<<<1, 1, 0, st>>>(ctrl, sc, k == 1 ? 1 : 0);
+      k_bl_uupd<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, V, k);
+      { double *tt = pcond(t, work(u + k - 1));
+        SpmvArgs a; a.x = tt; a.y = work(u + k); a.w = work(rr); a.out = sc + BL_SIGMA; a.ctrl = ctrl; spmv_any(h, a, EPI_DOT1); reduce_scalars(h, sc + BL_SIGMA, 1); }
+      k_bl_alpha<<<1, 1, 0, st>>>(ctrl, sc);
+      k_bl_xr<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, x, V, k, h.red_partials.p, h.red_counters.p);
+      { double *tt = pcond(t, work(r + k - 1));
+        SpmvArgs a; a.x = tt; a.y = work(r + k); a.w = work(rr); a.out = sc + BL_RHO1; a.ctrl = ctrl; spmv_any(h, a, EPI_DOT1); reduce_scalars(h, sc + BL_RNRM2, 2); }
+      k_bl_check<<<1, 1, 0, st>>>(ctrl, sc, Tol);
+      h.st_launch += 5;
+    }
+    dot_batch(h, n, ng, gx, gy, sc + BL_GRAM); reduce_scalars(h, sc + BL_GRAM, ng);
+    switch (l) {
+      case 2: k_bl_poly<2><<<1, 1, 0, st>>>(ctrl, sc); break;
+      case 3: k_bl_poly<3><<<1, 1, 0, st>>>(ctrl, sc); break;
+      case 4: k_bl_poly<4><<<1, 1, 0, st>>>(ctrl, sc); break;
+      default: k_bl_poly<5><<<1, 1, 0, st>>>(ctrl, sc); break;
+    }
+    k_bl_gamma<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, x, V, l);
+    k_bl_section<<<1, 1, 0, st>>>(ctrl, sc, 1);
+    { double *tt = pcond(t, x);
+      SpmvArgs a; a.x = tt; a.y = work(r); a.ctrl = ctrl; spmv_any(h, a, EPI_NONE);
+      k_bl_rcmp<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, x, work(r), work(bp), work(xp), tt); }
+    k_bl_section<<<1, 1, 0, st>>>(ctrl, sc, 0);
+    k_bl_roundend<<<1, 1, 0, st>>>(ctrl, sc, Tol, MaxTol, MaxRounds);
+    h.st_launch += 6;
+    B200_CUDA(cudaGetLastError());
+    {                                                          // poll one round behind; only done == 1 ends the solve (2 = section skip)
+      int cur = Round & 1, prev = cur ^ 1;
+      B200_CUDA(cudaMemcpyAsync(poll.slot[cur], h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaEventRecord(poll.ev[cur], st));
+      poll.pending[cur] = true;
+      if (poll.pending[prev]) {
+        B200_CUDA(cudaEventSynchronize(poll.ev[prev]));
+        poll.pending[prev] = false;
+        if (poll.slot[prev]->done == 1 || poll.slot[prev]->spin_timeout) break;
+      }
+    }
+  }
+  read_ctrl(h);
+  B200_REQUIRE(h.h_ctrl->done == 1 || h.h_ctrl->spin_timeout, "BiCGStab(l): the device loop ended without a verdict");
+  res.iters = std::min(MaxRounds, h.h_ctrl->iters);
+  res.residual = h.h_ctrl->residual;
+  res.info = h.h_ctrl->info;
+  // the kernels of the solve must not see done = 1 any more: the final assembly x = M^-1 x + x' (1156-1166) is unconditional
+  B200_CUDA(cudaMemsetAsync(&h.ctrl.p->done, 0, sizeof(int), st));
+  copy_vec(h, n, x, t);
+  if (pc != 0) { S.precond(x, t); } else h.st_pcond++;
+  S.lin(work(xp), 1.0, x, 1.0);
+  return res;
+}
+
 // IterativeMethods.F90:1260-1458
 static HostResult run_gcr(Handle &h, const double *b, double *x, int pc, int Rounds, double MinTol, double MaxTol, int m, int MinIter) {
   HostResult res;
@@ -648,7 +937,7 @@ static HostResult run_gmres(Handle &h, const double *b, double *x, int pc, int M
     double *rs = prec_residual();
     const double alpha = S.norm(rs);
     if (alpha == 0) { res.info = 40; break; }                     // HUTI_GMRES_ALPHA
-    copy_vec(h, n, rs, V(1)); S.lin(V(1), 0.0, V(1), 1.0 / alpha);
+    div_scalar(h, n, rs, V(1), alpha);                            // V(:,1) = R / alpha, huti_gmres.F90:189
     std::fill(Sv.begin(), Sv.end(), 0.0); Sv[0] = alpha;          // S = alpha * e1
     bool early = false, broke = false;
     for (int i = 1; i <= m; ++i) {
@@ -662,7 +951,7 @@ static HostResult run_gmres(Handle &h, const double *b, double *x, int pc, int M
       const double beta = S.norm(W);
       if (beta == 0) { res.info = 41; broke = true; break; }      // HUTI_GMRES_BETA
       Hh(i + 1, i) = beta;
-      copy_vec(h, n, W, V(i + 1)); S.lin(V(i + 1), 0.0, V(i + 1), 1.0 / beta);
+      div_scalar(h, n, W, V(i + 1), beta);
       for (int k = 1; k <= i - 1; ++k) {
         const double temp = CS[k] * Hh(k, i) + SN[k] * Hh(k + 1, i);
         Hh(k + 1, i) = -1 * SN[k] * Hh(k, i) + CS[k] * Hh(k + 1, i);
@@ -970,8 +1259,7 @@ static HostResult run_idrs(Handle &h, const double *b, double *x, int pc, int Ma
   for (int j = 1; j <= s; ++j) {                               // Gram-Schmidt on P, 1655-1661
     for (int k = 1; k <= j - 1; ++k) { alpha[k - 1] = S.dot(P(k), P(j)); S.lin(P(k), -alpha[k - 1], P(j), 1.0); }
     double nr = S.norm(P(j));
-    // P(:,j) = P(:,j)/norm: a true division in the reference
-    S.lin(P(j), 1.0 / nr, P(j), 0.0);
+    div_scalar(h, n, P(j), P(j), nr);                          // P(:,j) = P(:,j)/norm: a true division (1659)
   }
   while (!Converged && !Diverged) {
     {                                                          // f = P' r, one batched pass (1682-1684)
@@ -1100,9 +1388,12 @@ void solve_device(Handle &h, const double *d_b, double *d_x, int *ipar, double *
   RobustPar rb;                                               // huti_fdefs.h:132-135, 153-155
   rb.on = IPAR(26) == 1; rb.MaxBadIter = IPAR(27); rb.Start = IPAR(29); rb.Tol = DPAR(3); rb.Step = DPAR(4); rb.MaxTol = DPAR(5);
   switch (method) {
-    case B200_M_CG: run_cg(h, d_b, d_x, pc, IPAR(10)); break;
-    case B200_M_BICGSTAB: run_bicgstab(h, d_b, d_x, pc, IPAR(10)); break;
-    case B200_M_BICGSTABL: hr = run_bicgstabl(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(16), rb); break;
+    case B200_M_CG: run_cg(h, d_b, d_x, pc, IPAR(10), stopc); break;
+    case B200_M_BICGSTAB: run_bicgstab(h, d_b, d_x, pc, IPAR(10), stopc); break;
+    case B200_M_BICGSTABL:
+      if (!rb.on && IPAR(16) >= 2 && IPAR(16) <= BL_MAXL && !h.bl_host) hr = run_bicgstabl_dev(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(16));
+      else hr = run_bicgstabl(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(16), rb);
+      break;
     case B200_M_GCR: hr = run_gcr(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(17), IPAR(11)); break;
     case B200_M_IDRS: hr = run_idrs(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(18), IPAR(28) == 1, d_P, h.rank, rb); break;
     case B200_M_GMRES: hr = run_gmres(h, d_b, d_x, pc, IPAR(10), DPAR(1), DPAR(2), IPAR(15), stopc); break;

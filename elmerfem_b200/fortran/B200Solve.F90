@@ -225,6 +225,11 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   CALL AddLog( 'Linear System Symmetric ILU' )
   CALL AddLog( 'Linear System Left Preconditioning' )
   CALL AddLog( 'Linear System Robust' )
+  CALL AddReal( 'Linear System Robust Tolerance' )
+  CALL AddReal( 'Linear System Robust Limit' )
+  CALL AddReal( 'Linear System Robust Margin' )
+  CALL AddInt( 'Linear System Robust Max Iterations' )
+  CALL AddInt( 'Linear System Robust Start Iteration' )
   CALL AddLog( 'Linear System Componentwise Backward Error' )
   CALL AddLog( 'Linear System Normwise Backward Error' )
   CALL AddLog( 'Edge Basis' )

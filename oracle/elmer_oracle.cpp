@@ -126,6 +126,13 @@ static double dot_pairwise(const double *x, const double *y, long lo, long hi) {
   long mid = lo + (hi - lo) / 2;
   return dot_pairwise(x, y, lo, mid) + dot_pairwise(x, y, mid, hi);
 }
+// ddot on the small dense work arrays of BiCGStab(l) (IterativeMethods.F90:960-1037): always the reference's sequential order --
+// the device evaluates these in one thread, left to right, so the alternative summation orders do not apply to them.
+static double ref_ddot_small(int n, const double *dx, const double *dy) {
+  double dtemp = 0.0;
+  for (int i = 0; i < n; ++i) dtemp = dtemp + dx[i] * dy[i];       // ddot.f: m = n % 5 first, then groups of five -- all left to right
+  return dtemp;
+}
 double ref_ddot(int n, const double *dx, const double *dy) {
   double dtemp = 0.0;
   if (n <= 0) return 0.0;
@@ -1125,15 +1132,15 @@ void RealBiCGStabl(Ops &op, int n, double *x, const double *b, int MaxRounds, do
     // Convex combination
     double kappa0, kappal, varrho, hatgamma;
     small_dsymv_u(l + 1, &rwork(1, z), ldr, &rwork(1, y0), &rwork(1, y));
-    kappa0 = ref_ddot(l + 1, &rwork(1, y0), &rwork(1, y));
+    kappa0 = ref_ddot_small(l + 1, &rwork(1, y0), &rwork(1, y));
     if (kappa0 <= 0.0) { Halted = true; goto L100; }
     kappa0 = std::sqrt(kappa0);
     small_dsymv_u(l + 1, &rwork(1, z), ldr, &rwork(1, yl), &rwork(1, y));
-    kappal = ref_ddot(l + 1, &rwork(1, yl), &rwork(1, y));
+    kappal = ref_ddot_small(l + 1, &rwork(1, yl), &rwork(1, y));
     if (kappal <= 0.0) { Halted = true; goto L100; }
     kappal = std::sqrt(kappal);
     small_dsymv_u(l + 1, &rwork(1, z), ldr, &rwork(1, y0), &rwork(1, y));
-    varrho = ref_ddot(l + 1, &rwork(1, yl), &rwork(1, y)) / (kappa0 * kappal);
+    varrho = ref_ddot_small(l + 1, &rwork(1, yl), &rwork(1, y)) / (kappa0 * kappal);
     hatgamma = varrho / std::fabs(varrho) * std::max(std::fabs(varrho), 7e-1) * kappa0 / kappal;
     for (int i = 1; i <= l + 1; ++i) rwork(i, y0) = rwork(i, y0) - hatgamma * rwork(i, yl);
     // --- Update (1014-1033) ---
@@ -1151,7 +1158,7 @@ void RealBiCGStabl(Ops &op, int n, double *x, const double *b, int MaxRounds, do
       for (int i = 0; i < n; ++i) r0[i] = r0[i] - g * rj[i];
     }
     small_dsymv_u(l + 1, &rwork(1, z), ldr, &rwork(1, y0), &rwork(1, y));
-    rnrm = ref_ddot(l + 1, &rwork(1, y0), &rwork(1, y));
+    rnrm = ref_ddot_small(l + 1, &rwork(1, y0), &rwork(1, y));
     if (rnrm < 0.0) { Halted = true; goto L100; }
     rnrm = std::sqrt(rnrm);
     // --- The reliable update part (1050-1101) ---

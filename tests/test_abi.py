@@ -72,3 +72,19 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_shim_forwards_every_keyword_the_planner_reads():
+    """Every SIF keyword plan_from_sif (csrc/itersolver.cu) reads must be copied into the sif text by the Fortran shim
+    (fortran/B200Solve.F90 AddStr / AddInt / AddReal / AddLog); a key that is read but not forwarded silently falls back to its default
+    (IterSolve.F90:245-503 reads them from the Solver section)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "elmerfem_b200", "csrc", "itersolver.cu")).read()
+    shim = open(os.path.join(root, "elmerfem_b200", "fortran", "B200Solve.F90")).read()
+    read = set(re.findall(r'P\.(?:logical|real|integer|str|string|has)\(\s*"([^"]+)"', src))
+    read = {k for k in read if " " in k or k.startswith("IDRS") or k.startswith("BiCG")}      # keywords, not values
+    sent = {k.lower() for k in re.findall(r"CALL Add(?:Str|Int|Real|Log)\(\s*'([^']+)'", shim)}
+    sent |= {k.strip().lower() for k in re.findall(r"CALL Append\(\s*'([^=']+)=", shim)}
+    missing = sorted(k for k in read if k.lower() not in sent)
+    assert not missing, missing
