@@ -313,7 +313,7 @@ class Matrix:
         _check(lib().b200_get_stats(self.handle, _dp(s)), "b200_get_stats")
         return dict(solve_ms=s[0], matvec=int(s[1]), pcond=int(s[2]), factor_ms=s[3], launches=int(s[4]), h2d=int(s[5]),
                     d2h=int(s[6]), iters=int(s[7]), spmv_ms=s[8], lu_ms=s[9], residual=s[10], sell_entries=int(s[11]),
-                    levels_f=int(s[12]), levels_b=int(s[13]), factor_launches=int(s[14]))
+                    levels_f=int(s[12]), levels_b=int(s[13]), factor_launches=int(s[14]), tri_mode=int(s[15]))
 
     def time_matvec(self, reps=20):
         ms = C.c_double(0)

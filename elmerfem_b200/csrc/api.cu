@@ -571,6 +571,7 @@ int b200_get_stats(void **handle, double *s) {
     s[0] = h.st_solve_ms; s[1] = (double)h.st_matvec; s[2] = (double)h.st_pcond; s[3] = h.st_factor_ms;
     s[4] = (double)h.st_launch_last; s[5] = (double)h.st_h2d; s[6] = (double)h.st_d2h; s[7] = (double)h.st_iters;
     s[8] = h.st_spmv_ms; s[9] = h.st_lu_ms; s[10] = h.st_resid; s[11] = (double)h.A.nstore; s[12] = (double)h.nlev_f; s[13] = (double)h.nlev_b; s[14] = (double)h.st_factor_launch;
+    s[15] = (double)h.tri_mode;
   });
 }
 

@@ -224,7 +224,8 @@ int b200_initialize_structure(const int *k, const int *rows, const int *cols, co
  * applications, [3] last factorisation device ms, [4] kernels launched by the last solve,
  * [5] last solve H2D bytes, [6] D2H bytes, [7] iterations, [8] last SpMV-only device ms (b200_time_matvec),
  * [9] last LU-solve-only device ms, [10] final residual,
- * [11] SELL entries stored, [12]/[13] forward/backward levels, [14] kernels launched by the last factorisation. */
+ * [11] SELL entries stored, [12]/[13] forward/backward levels, [14] kernels launched by the last factorisation,
+ * [15] triangular-solve kernel in use (0 level sweeps, 1 warp tasks, 2 skewed lanes, 3 wave tiles; negative: not decided yet). */
 int b200_get_stats(void **handle, double *stats16);
 /* Time `reps` back-to-back v = A u launches on resident vectors with CUDA events; ms_out = mean ms. */
 int b200_time_matvec(void **handle, const int *reps, double *ms_out);

@@ -76,3 +76,37 @@ def split_rows(S, offsets):
         B = S[offsets[r]:offsets[r + 1]]
         parts.append((B.indptr.astype(np.int32), B.indices.astype(np.int32), B.data.copy()))
     return parts
+
+
+def send_lists_rank(rows, cols, index_offset, rank):
+    """The same construction for ONE rank, vectorised (numpy) so that it also runs at benchmark sizes: rank `rank`'s complete owned rows
+    (0-based CRS, GLOBAL continuous column ids) -> (neigh, send_ptr, send_idx).  rocalution.cpp:115-154 visits the rows in ascending
+    order and appends row i once per foreign owner of one of its columns, so the list towards rank q is the ascending set of rows with a
+    column owned by q; 266-274 concatenates the lists in ascending q."""
+    rows = np.asarray(rows, dtype=np.int64); cols = np.asarray(cols, dtype=np.int64)
+    off = np.asarray(index_offset, dtype=np.int64)
+    n = rows.size - 1
+    lo, hi = off[rank], off[rank + 1]
+    rowid = np.repeat(np.arange(n, dtype=np.int64), np.diff(rows))
+    ext = (cols < lo) | (cols >= hi)
+    q = np.searchsorted(off, cols[ext], side="right") - 1
+    key = np.unique(q * n + rowid[ext])                                       # ascending (q, row)
+    qs, idx = key // max(n, 1), key % max(n, 1)
+    neigh = np.unique(qs)
+    counts = np.array([np.count_nonzero(qs == r) for r in neigh], dtype=np.int64)
+    send_ptr = np.concatenate([[0], np.cumsum(counts)])
+    return neigh.astype(np.int32), send_ptr.astype(np.int32), idx.astype(np.int32)
+
+
+def plan_rank(all_send, index_offset, rank):
+    """all_send[r] = send_lists_rank(...) of every rank -> the full plan of `rank` in distribute()'s form (222-297): what rank receives
+    from neighbour q, in q's send order, are q's boundary rows towards `rank` as global ids; ghost slots follow the receive order."""
+    neigh, send_ptr, send_idx = all_send[rank]
+    recv, recv_ptr = [], [0]
+    for q in neigh:
+        nq, pq, iq = all_send[q]
+        k = int(np.flatnonzero(nq == rank)[0])
+        recv.append(iq[pq[k]:pq[k + 1]].astype(np.int64) + index_offset[q])
+        recv_ptr.append(recv_ptr[-1] + recv[-1].size)
+    ghost = np.concatenate(recv).astype(np.int32) if recv else np.zeros(0, dtype=np.int32)
+    return dict(neigh=neigh, send_ptr=send_ptr, send_idx=send_idx, recv_ptr=np.array(recv_ptr, dtype=np.int32), ghost_gid=ghost)

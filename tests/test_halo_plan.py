@@ -172,3 +172,23 @@ def test_two_process_gloo_halo_exchange(b200):
     for rank, ok, nneigh, nghost in res:
         assert ok, rank
         assert nneigh == 1 and nghost == 6 * 5          # one interface plane of (ex+1)*(ey+1) nodes
+
+
+def test_vectorised_restatement_equals_the_loop_restatement():
+    """oracle/halo_oracle.py: send_lists_rank + plan_rank (numpy, used by bench.py at full size) against distribute() (the literal
+    loops of rocalution.cpp:64-372) on random sparse matrices with uneven ownership ranges."""
+    import scipy.sparse as sp
+    from oracle import halo_oracle as HO
+    rs = np.random.RandomState(5)
+    for n, nparts in [(60, 2), (97, 3), (200, 5), (40, 8)]:
+        S = sp.random(n, n, density=0.08, random_state=rs, format="csr")
+        S = (S + S.T + sp.identity(n, format="csr")).tocsr()          # structurally symmetric, as finite-element matrices are (the reference relies on it)
+        cuts = np.sort(rs.choice(np.arange(1, n), nparts - 1, replace=False))
+        off = [0] + [int(c) for c in cuts] + [n]
+        parts = HO.split_rows(S, off)
+        ref = HO.distribute([(p[0], p[1]) for p in parts], off)
+        sends = [HO.send_lists_rank(p[0], p[1], off, r) for r, p in enumerate(parts)]
+        for r in range(nparts):
+            got = HO.plan_rank(sends, off, r)
+            for k in ["neigh", "send_ptr", "send_idx", "recv_ptr", "ghost_gid"]:
+                assert np.array_equal(got[k], ref[r][k]), (n, nparts, r, k)
