@@ -126,10 +126,13 @@ def _winkel_worker(rank, world, port, out_q, npz):
         dist.broadcast_object_list(ids, src=0)
         M = B.Matrix()
         M.comm_init(world, rank, ids[0])
-        M.set_partition(int(d["gn"]), d["rows%d" % rank], d["cols%d" % rank], d["goffset"], 0, 1)
+        ndeg = int(d["ndeg"]) if "ndeg" in d else 1
+        M.set_partition(int(d["gn"]), d["rows%d" % rank], d["cols%d" % rank], d["goffset"], 0, ndeg)
         M.set_values(d["vals%d" % rank])
-        got = M.solve(d["b%d" % rank], method="cg", precond="ilu0", tol=1e-8, maxit=1000)
-        out_q.put((rank, got["x"].tolist(), got["info"], got["iters"]))
+        method = str(d["method"]) if "method" in d else "cg"
+        got = M.solve(d["b%d" % rank], method=method, precond="ilu0", tol=1e-8, maxit=1000, bicgstabl_l=4)
+        plan = M.halo_plan()
+        out_q.put((rank, got["x"].tolist(), got["info"], got["iters"], {k: v.tolist() for k, v in plan.items()}))
         dist.barrier()
         M.close()
     finally:
@@ -185,3 +188,62 @@ def test_multi_gpu_winkel_metis(oracle, b200, WORLD, tmp_path):
     ref = oracle.itersolve(Ac, bc, method="cg", precond="ilu0", ilu=oracle.ilu0(Abd), tol=1e-8, maxit=1000)
     it = {r_[3] for r_ in res}
     assert len(it) == 1 and abs(it.pop() - ref["iters"]) <= max(1, int(np.ceil(0.02 * ref["iters"])))
+
+
+def test_multi_gpu_navier_metis_kway_3dof(oracle, b200, tmp_path):
+    """BASELINE configs[2] at test size, on the reference's own case and partitioner: fem/tests/WinkelBmNavier* (StressSolver, 3 dofs per
+    node) partitioned by `ElmerGrid -partdual -metiskway 4`, BiCGStab(l=4) + block-Jacobi ILU0 on 4 GPUs: halo lists bit-identical to the
+    restatement of elmer_distribute_matrix, the reference's norm 2.25252433E-02, and the oracle's round count at the same partition."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import winkel_case as W
+    from elmerfem_b200 import meshio
+    from oracle import halo_oracle as HO
+    WORLD = 4
+    n = C.c_int(0)
+    if b200.lib().b200_device_count(C.byref(n)) != 0 or n.value < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    if not W.available():
+        pytest.skip("oracle/_ref/ElmerGrid not built")
+    import torch.multiprocessing as mp
+    A, b = W.navier_system()
+    x = np.zeros(A.n)
+    Dv, bn = oracle.scale_system(A, b, x)
+    P = meshio.Partitioning(os.path.join(W.navier_mesh_dir(WORLD, "-metiskway"), "partitioning.%d" % WORLD), WORLD, ndof=3)
+    parts, Sc = P.owned_rows(A.to_scipy())
+    perm = P.dof_permutation()
+    bc = np.zeros(A.n); bc[perm] = b
+    arrays = dict(gn=P.gn, goffset=P.goffset, ndeg=3, method="bicgstabl")
+    for r, (rows, cols, vals) in enumerate(parts):
+        arrays["rows%d" % r] = rows; arrays["cols%d" % r] = cols; arrays["vals%d" % r] = vals
+        arrays["b%d" % r] = bc[P.goffset[r]:P.goffset[r + 1]]
+    npz = str(tmp_path / "navier_parts.npz")
+    np.savez(npz, **arrays)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_winkel_worker, args=(r, WORLD, port, q, npz)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    off = [int(v) for v in P.goffset]
+    sends = [HO.send_lists_rank(rows, cols, off, r) for r, (rows, cols, vals) in enumerate(parts)]
+    for r_ in res:
+        ref_plan = HO.plan_rank(sends, off, r_[0])
+        for k in ["neigh", "send_ptr", "send_idx", "recv_ptr", "ghost_gid"]:
+            assert np.array_equal(np.array(r_[4][k], dtype=np.int32), ref_plan[k]), (r_[0], k)
+    xc = np.concatenate([np.array(r_[1]) for r_ in res])
+    assert {r_[2] for r_ in res} == {1}
+    xnat = xc[perm] * Dv
+    assert abs(W.norm(xnat) - W.NAVIER_REFERENCE_NORM) <= 1e-6 * W.NAVIER_REFERENCE_NORM, W.norm(xnat)
+    Ac = oracle.CRS.from_scipy(Sc, 3)
+    block = np.searchsorted(P.goffset, np.arange(A.n), side="right") - 1
+    rowid = np.repeat(np.arange(A.n), np.diff(Ac.rows))
+    Abd = Ac.copy(); Abd.vals[block[rowid] != block[Ac.cols - 1]] = 0.0
+    ref = oracle.itersolve(Ac, bc, method="bicgstabl", precond="ilu0", ilu=oracle.ilu0(Abd), tol=1e-8, maxit=1000, bicgstabl_l=4)
+    it = {r_[3] for r_ in res}
+    assert ref["info"] == 1 and len(it) == 1 and abs(it.pop() - ref["iters"]) <= max(1, int(np.ceil(0.02 * ref["iters"]))), (it, ref["iters"])
