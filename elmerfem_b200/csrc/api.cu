@@ -63,6 +63,7 @@ static void ensure_runtime(Handle &h) {
   h.wv_cfg = env_int("B200_WAVE_CFG", 0);
   h.wv_e = env_int("B200_WAVE_E", 3);
   h.bl_host = env_int("B200_BICGSTABL_HOST", 0) != 0;
+  h.stage_uploads = env_int("B200_STAGE_UPLOADS", 1) != 0;
   h.tt_rows = env_int("B200_TT_ROWS", 0);
   h.tt_wpb = env_int("B200_TT_WPB", 0);
   h.tt_wait_ns = (unsigned)env_int("B200_TT_WAIT_NS", 100);
@@ -149,10 +150,32 @@ static void pin_values(Handle &h, const void *p, size_t bytes) {
   if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) { h.pinned_ptr = p; h.pinned_bytes = bytes; }
   else cudaGetLastError();
 }
+// Large pageable arrays (Values: 1.7 GB on C2) go through two page-locked bounce buffers: the host cores copy chunk c + 1 into one
+// buffer (OpenMP memcpy) while the DMA engine moves chunk c from the other at PCIe speed, instead of the driver's internal staging of a
+// pageable cudaMemcpyAsync (measured 11 GB/s).  Small arrays and already page-locked sources take the direct copy.
+constexpr size_t STAGE_BYTES = 64u << 20, STAGE_MIN = 256u << 20;
 static void upload(Handle &h, double *dst, const double *src, size_t n) {
   if (!n) return;
-  B200_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h.stream));
-  h.st_h2d += n * sizeof(double);
+  const size_t bytes = n * sizeof(double);
+  h.st_h2d += bytes;
+  const bool src_pinned = (src == h.pinned_ptr);
+  if (bytes < STAGE_MIN || src_pinned || !h.stage_uploads) { B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h.stream)); return; }
+  if (!h.stage_buf[0]) {
+    for (int k = 0; k < 2; ++k) { B200_CUDA(cudaMallocHost(&h.stage_buf[k], STAGE_BYTES)); B200_CUDA(cudaEventCreateWithFlags(&h.stage_ev[k], cudaEventDisableTiming)); }
+  }
+  const char *s = reinterpret_cast<const char *>(src); char *d = reinterpret_cast<char *>(dst);
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES, k ^= 1) {
+    const size_t len = std::min(STAGE_BYTES, bytes - off);
+    if (off >= 2 * STAGE_BYTES) B200_CUDA(cudaEventSynchronize(h.stage_ev[k]));     // the copy that last read this buffer has finished
+    char *buf = reinterpret_cast<char *>(h.stage_buf[k]);
+    const size_t piece = 1u << 20;
+    const long long np = (long long)((len + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < np; ++q) { const size_t o = (size_t)q * piece; memcpy(buf + o, s + off + o, std::min(piece, len - o)); }
+    B200_CUDA(cudaMemcpyAsync(d + off, buf, len, cudaMemcpyHostToDevice, h.stream));
+    B200_CUDA(cudaEventRecord(h.stage_ev[k], h.stream));
+  }
 }
 // ---- Linear System Scaling on the device (SolverUtils.F90:12976-13213, 13515-13643) ---------------------------
 __global__ void k_scale_diag(int n, const int *__restrict__ rows, const int *__restrict__ diag, const double *__restrict__ vals, double *__restrict__ D) {
@@ -260,6 +283,7 @@ int b200_destroy(void **handle) {
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    for (int k = 0; k < 2; ++k) { if (h->stage_buf[k]) cudaFreeHost(h->stage_buf[k]); if (h->stage_ev[k]) cudaEventDestroy(h->stage_ev[k]); }
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     cudaEvent_t evs[] = {h->ev0, h->ev1, h->ev2, h->ev_end, h->evf0, h->evf1};
     for (auto e : evs) if (e) cudaEventDestroy(e);

@@ -295,8 +295,11 @@ __device__ __forceinline__ bool last_block(unsigned int *ticket) {
   return last;
 }
 __global__ void __launch_bounds__(256) k_pack_push(int nsend, const int *__restrict__ idx, const double *__restrict__ x, const PeerDesc *__restrict__ peers,
-                                                    int nneigh, const unsigned long long *ack, unsigned long long seq, unsigned int *ticket, Ctrl *ctrl) {
-  // (no early exit on ctrl->done: the flag protocol must advance identically on every rank)
+                                                    int nneigh, const unsigned long long *ack, unsigned long long seq, unsigned int *ticket, Ctrl *ctrl, int honor_skip) {
+  // (no early exit on ctrl->done == 1: the flag protocol must advance identically on every rank.  done == 2 marks a section every rank
+  // skips as a whole -- the value derives from all-reduced scalars, identical on all ranks -- and a skipped exchange leaves ready / ack
+  // at their previous sequence numbers, which is exactly what the next exchange expects.)
+  if (honor_skip && ctrl->done == 2) return;
   // the buffer of this parity was last filled for exchange seq-2: wait until every neighbour has consumed that one
   if ((int)threadIdx.x < nneigh && seq > 2) {
     long long spins = 0;
@@ -316,7 +319,8 @@ __global__ void __launch_bounds__(256) k_pack_push(int nsend, const int *__restr
   if (last_block(ticket) && (int)threadIdx.x < nneigh) st_release_sys(peers[threadIdx.x].rready, seq);
 }
 __global__ void __launch_bounds__(256) k_spmv_ghost_p2p(SellView G, const double *xg, double *__restrict__ y, const unsigned long long *ready,
-                                                         const PeerDesc *__restrict__ peers, int nneigh, unsigned long long seq, unsigned int *ticket, Ctrl *ctrl) {
+                                                         const PeerDesc *__restrict__ peers, int nneigh, unsigned long long seq, unsigned int *ticket, Ctrl *ctrl, int honor_skip) {
+  if (honor_skip && ctrl->done == 2) return;
   if ((int)threadIdx.x < nneigh) {
     long long spins = 0;
     while (ld_acquire_sys(ready + threadIdx.x) < seq) {
@@ -367,10 +371,10 @@ void matvec_full(Handle &h, const double *x, double *y) {
     const unsigned long long seq = ++H.seq;
     const PeerDesc *peers = (const PeerDesc *)H.d_peers.p;
     k_pack_push<<<std::max(1, std::min((H.nsend + 255) / 256, NUM_SMS * 4)), 256, 0, h.stream>>>(H.nsend, H.d_send_idx.p, x, peers, H.nneigh, H.ack, seq,
-                                                                                                 H.d_ticket.p, h.ctrl.p);
-    { SpmvArgs a; a.x = x; a.y = y; spmv_launch(h, a, EPI_NONE); }   // owned x owned while the neighbours' entries arrive
+                                                                                                 H.d_ticket.p, h.ctrl.p, h.mv_honor_skip ? 1 : 0);
+    { SpmvArgs a; a.x = x; a.y = y; if (h.mv_honor_skip) a.ctrl = h.ctrl.p; spmv_launch(h, a, EPI_NONE); }   // owned x owned while the neighbours' entries arrive
     k_spmv_ghost_p2p<<<std::max(1, (H.G.nslots + 255) / 256), 256, 0, h.stream>>>(H.G.view(), H.recv[seq & 1ULL] - h.n, y, H.ready, peers, H.nneigh, seq,
-                                                                                   H.d_ticket.p + 1, h.ctrl.p);
+                                                                                   H.d_ticket.p + 1, h.ctrl.p, h.mv_honor_skip ? 1 : 0);
     B200_CUDA(cudaGetLastError());
     h.st_launch += 3;
     return;

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <algorithm>
 #include "skewgeom.h"
 #include "wavegeom.h"
 
@@ -159,6 +160,8 @@ struct Handle {
   // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
   SkewPlan sk; int sk_blocks_per_sm = 0, sk_cfg = 0, sk_wpb = 0;
   WavePlan wv; int wv_blocks_per_sm = 0, wv_cfg = 0, wv_e = 3;
+  void *stage_buf[2] = {nullptr, nullptr}; cudaEvent_t stage_ev[2] = {nullptr, nullptr}; bool stage_uploads = true;   // pinned bounce buffers of b200_set_values
+  bool mv_honor_skip = false;                     // partitioned SpMVs queued inside a conditional section (Ctrl::done == 2) return at once
   bool bl_host = false;                           // B200_BICGSTABL_HOST=1: host-driven BiCGStab(l) (the round-1 driver) instead of the device-resident one
   TriTask TL, TU; bool tt_ready = false; int tri_mode = 0, tri_mode_cfg = 0, tt_rows = 0, tt_wpb = 0; unsigned tt_wait_ns = 100; int tt_pf = 16; DBuf<double> d_ytask, d_xtask;
   double tt_ms_level = 0, tt_ms_task = 0;
@@ -174,6 +177,11 @@ struct Handle {
   // tuning (env overridable)
   int spmv_blocks = 0, tri_blocks_per_sm = 0, blas_blocks = NUM_SMS * 8;
   int grid_ilu = 0, grid_tri_l = 0, grid_tri_u = 0;   // co-resident grid sizes (occupancy x SMs)
+  const void *grid_ilu_kern = nullptr; int ilu_maxrow_cache = -1;
+  int ilu_maxrow() {                                 // longest row of the factor pattern
+    if (ilu_maxrow_cache < 0) { const std::vector<int> &r = lrows(); int m = 0; for (size_t i = 0; i + 1 < r.size(); ++i) m = std::max(m, r[i + 1] - r[i]); ilu_maxrow_cache = m; }
+    return ilu_maxrow_cache;
+  }
   // B200_PIN_VALUES=1: the caller's value array is page-locked (cudaHostRegister) the first time it is seen, so the
   // once-per-nonlinear-iteration upload runs at PCIe speed instead of through a staging copy
   int pin_values = 0; const void *pinned_ptr = nullptr; size_t pinned_bytes = 0;

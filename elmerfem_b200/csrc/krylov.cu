@@ -733,12 +733,12 @@ __global__ void k_bl_section(Ctrl *c, const double *sc, int open) {
   else if (c->done == 2) c->done = 0;
 }
 // 1060-1068: r = b' - r ; flying restart: x' += t, x = 0, b' = r
-__global__ void __launch_bounds__(256) k_bl_rcmp(int n, const Ctrl *c, const double *sc, double *__restrict__ x, double *__restrict__ r, double *__restrict__ bp,
-                                                  double *__restrict__ xp, const double *__restrict__ t) {
+__global__ void __launch_bounds__(256) k_bl_rcmp(int n, const Ctrl *c, const double *sc, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ rnew,
+                                                  double *__restrict__ bp, double *__restrict__ xp, const double *__restrict__ t) {
   if (c->done) return;
   const bool xpdt = sc[BL_XPDT] != 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double ri = __dsub_rn(bp[i], r[i]);
+    const double ri = __dsub_rn(bp[i], rnew[i]);
     r[i] = ri;
     if (xpdt) { xp[i] = __dadd_rn(xp[i], t[i]); x[i] = 0.0; bp[i] = ri; }
   }
@@ -759,11 +759,11 @@ __global__ void k_bl_roundend(Ctrl *c, double *sc, double Tol, double MaxTol, in
 static HostResult run_bicgstabl_dev(Handle &h, const double *b, double *x, int pc, int MaxRounds, double Tol, double MaxTol, int l) {
   HostResult res;
   const int nw = 3 + 2 * (l + 1);
-  Solver S(h, pc, nw + 1);
+  Solver S(h, pc, nw + 2);
   const int n = S.n;
   cudaStream_t st = S.st; Ctrl *ctrl = S.ctrl; double *sc = S.sc;
   auto work = [&](int c) { return S.vec[c - 1]; };
-  double *t = S.vec[nw];
+  double *t = S.vec[nw], *rnew = S.vec[nw + 1];                // rnew: A M^-1 x of the reliable update (partitioned SpMVs do not look at Ctrl::done)
   const int rr = 1, r = rr + 1, u = r + (l + 1), xp = u + (l + 1), bp = xp + 1;
   { double nx2 = S.dot(x, x); if (nx2 == 0.0) copy_vec(h, n, b, x); }                 // 719
   S.matvec(x, work(r));
@@ -808,8 +808,8 @@ static HostResult run_bicgstabl_dev(Handle &h, const double *b, double *x, int p
     k_bl_gamma<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, x, V, l);
     k_bl_section<<<1, 1, 0, st>>>(ctrl, sc, 1);
     { double *tt = pcond(t, x);
-      SpmvArgs a; a.x = tt; a.y = work(r); a.ctrl = ctrl; spmv_any(h, a, EPI_NONE);
-      k_bl_rcmp<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, x, work(r), work(bp), work(xp), tt); }
+      SpmvArgs a; a.x = tt; a.y = rnew; a.ctrl = ctrl; h.mv_honor_skip = true; spmv_any(h, a, EPI_NONE); h.mv_honor_skip = false;
+      k_bl_rcmp<<<S.blocks, 256, 0, st>>>(n, ctrl, sc, x, work(r), rnew, work(bp), work(xp), tt); }
     k_bl_section<<<1, 1, 0, st>>>(ctrl, sc, 0);
     k_bl_roundend<<<1, 1, 0, st>>>(ctrl, sc, Tol, MaxTol, MaxRounds);
     h.st_launch += 6;

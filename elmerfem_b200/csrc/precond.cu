@@ -116,6 +116,116 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int nslots, const int *__re
   }
 }
 
+// The same factorisation with the row held in REGISTERS (NPL entries per lane, rows of <= 32 NPL entries): the update of entry j by pivot
+// row k (3631-3636) is found by broadcasting the pivot row's upper entries one by one (two shuffles) and comparing columns in every
+// lane, instead of a binary search over the staged row in shared memory per update (5 dependent shared-memory reads, done by all 32
+// lanes: 85 instructions per stored entry, profiles/r01_ncu_summary.txt).  Same operations on the same operands in the same order:
+// bit-identical ILUValues.
+template <int NPL>
+__global__ void __launch_bounds__(256) k_ilu0_factor_reg(int nslots, const int *__restrict__ perm, const int *__restrict__ rows,
+                                                          const int *__restrict__ cols, const int *__restrict__ diag,
+                                                          const double *__restrict__ Avals, const int *__restrict__ src, double *LU, int *rowdone,
+                                                          Ctrl *ctrl) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slot = gwarp; slot < nslots; slot += nwarps) {
+    const int r = perm[slot];
+    if (r < 0) continue;
+    const int rs = rows[r], re = rows[r + 1], d = diag[r], len = re - rs, nlow = d - rs;
+    int col[NPL]; double val[NPL];
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      const int p = q * 32 + lane;
+      col[q] = -1; val[q] = 0.0;
+      if (p < len) {
+        col[q] = cols[rs + p];
+        if (src) { const int s = src[rs + p]; val[q] = s >= 0 ? Avals[s] : 0.0; } else val[q] = Avals[rs + p];
+      }
+    }
+    long long spins = 0;
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      if (q * 32 + lane < nlow) {
+        while (ld_acquire(rowdone + col[q]) == 0) {
+          if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+          __nanosleep(40);
+        }
+      }
+    }
+    __syncwarp();
+    auto at = [&](const int (&a)[NPL], int p) {                      // a[p >> 5] of lane p & 31, p warp-uniform
+      int v = a[0];
+#pragma unroll
+      for (int q = 1; q < NPL; ++q) if ((p >> 5) == q) v = a[q];
+      return __shfl_sync(FULL, v, p & 31);
+    };
+    auto atd = [&](const double (&a)[NPL], int p) {
+      double v = a[0];
+#pragma unroll
+      for (int q = 1; q < NPL; ++q) if ((p >> 5) == q) v = a[q];
+      return __shfl_sync(FULL, v, p & 31);
+    };
+    constexpr int MB = 8;
+    for (int m0 = 0; m0 < nlow; m0 += MB) {
+      // pivots and upper parts of the MB pivot rows, one L2 round trip for the batch
+      int kcol[MB];
+#pragma unroll
+      for (int t = 0; t < MB; ++t) kcol[t] = (m0 + t < nlow) ? at(col, m0 + t) : 0;
+      int mkd = 0, mke = 0; double mukk = 0.0;
+#pragma unroll
+      for (int t = 0; t < MB; ++t) if (lane == t && m0 + t < nlow) { mkd = diag[kcol[t]]; mke = rows[kcol[t] + 1]; mukk = __ldcg(LU + mkd); }
+      int pj0[MB], pj1[MB]; double pv0[MB], pv1[MB];
+#pragma unroll
+      for (int t = 0; t < MB; ++t) {
+        const int kd = __shfl_sync(FULL, mkd, t), ke = __shfl_sync(FULL, mke, t);
+        const int l0 = kd + 1 + lane, l1 = l0 + 32;
+        const bool in0 = (m0 + t < nlow) && l0 < ke, in1 = (m0 + t < nlow) && l1 < ke;
+        pj0[t] = in0 ? cols[l0] : -2; pv0[t] = in0 ? __ldcg(LU + l0) : 0.0;
+        pj1[t] = in1 ? cols[l1] : -2; pv1[t] = in1 ? __ldcg(LU + l1) : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < MB; ++t) {
+        const int m = m0 + t;
+        if (m < nlow) {
+          double skm = atd(val, m);
+          const double ukk = __shfl_sync(FULL, mukk, t);
+          const int kd = __shfl_sync(FULL, mkd, t), ke = __shfl_sync(FULL, mke, t);
+          if (skm != 0.0) {                                          // 3626
+            if (fabs(ukk) > AEPS) skm = __ddiv_rn(skm, ukk);         // 3628-3629
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) if (q * 32 + lane == m) val[q] = skm;
+            const int nu = ke - kd - 1;                              // upper entries of pivot row k
+            const int n0 = nu < 32 ? nu : 32;
+            for (int u = 0; u < n0; ++u) {                           // 3631-3636
+              const int pj = __shfl_sync(FULL, pj0[t], u); const double pv = __shfl_sync(FULL, pv0[t], u);
+#pragma unroll
+              for (int q = 0; q < NPL; ++q) if (col[q] == pj) val[q] = nfms(val[q], skm, pv);
+            }
+            const int n1 = nu < 64 ? nu - 32 : 32;
+            for (int u = 0; u < n1; ++u) {
+              const int pj = __shfl_sync(FULL, pj1[t], u); const double pv = __shfl_sync(FULL, pv1[t], u);
+#pragma unroll
+              for (int q = 0; q < NPL; ++q) if (col[q] == pj) val[q] = nfms(val[q], skm, pv);
+            }
+            for (int l = kd + 1 + 64; l < ke; ++l) {                 // pivot rows wider than 64 upper entries
+              const int pj = cols[l]; const double pv = __ldcg(LU + l);
+#pragma unroll
+              for (int q = 0; q < NPL; ++q) if (col[q] == pj) val[q] = nfms(val[q], skm, pv);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) if (q * 32 + lane < len) __stcg(LU + rs + q * 32 + lane, val[q]);   // 3643-3649
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(rowdone + r, 1);
+  }
+}
+
 // 3654-3660: store the inverse diagonal (1.0 when tiny)
 __global__ void k_ilu0_invert_diag(int n, const int *__restrict__ diag, double *LU) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -165,9 +275,16 @@ void ilu0_factor(Handle &h) {
     B200_CUDA(cudaMemsetAsync(h.d_rowdone.p, 0, (size_t)h.n * sizeof(int), st));
     B200_CUDA(cudaMemsetAsync(&h.ctrl.p->spin_timeout, 0, sizeof(int), st));
     const double *src = h.have_prec ? h.d_prec.p : h.d_vals.p;        // CRSMatrix.F90:3480-3484
-    if (!h.grid_ilu) h.grid_ilu = persistent_blocks((const void *)k_ilu0_factor, 256, 0);
+    // rows of <= 96 entries are factorised from registers (1, 2 or 3 entries per lane); longer rows keep the shared-memory kernel
+    const int maxrow = h.ilu_maxrow();
+    static const bool reg_ok = !(getenv("B200_ILU_REG") && atoi(getenv("B200_ILU_REG")) == 0);
+    const void *kern = (const void *)k_ilu0_factor;
+    if (reg_ok && maxrow <= 32) kern = (const void *)k_ilu0_factor_reg<1>;
+    else if (reg_ok && maxrow <= 64) kern = (const void *)k_ilu0_factor_reg<2>;
+    else if (reg_ok && maxrow <= 96) kern = (const void *)k_ilu0_factor_reg<3>;
+    if (h.grid_ilu_kern != kern) { h.grid_ilu = persistent_blocks(kern, 256, 0); h.grid_ilu_kern = kern; }
     int blocks = std::max(1, std::min(h.grid_ilu, (h.L.nslots + 7) / 8));
-    launch_coresident((const void *)k_ilu0_factor, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
+    launch_coresident(kern, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
                       (const int *)(h.ilu_sep() ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
     int eb = std::min((h.n + 255) / 256, NUM_SMS * 8);
     k_ilu0_invert_diag<<<eb, 256, 0, st>>>(h.n, h.d_ldiag(), h.d_ilu.p);
