@@ -278,7 +278,7 @@ int b200_destroy(void **handle) {
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
     h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
     h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
-    tritask_release(*h); skew_release(*h); wave_release(*h); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
+    tritask_release(*h); skew_release(*h); wave_release(*h); h->d_ilu_pos.release(); h->d_ilu_posptr.release(); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
     for (auto &w : h->work) w.release();
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();

@@ -177,11 +177,8 @@ struct Handle {
   // tuning (env overridable)
   int spmv_blocks = 0, tri_blocks_per_sm = 0, blas_blocks = NUM_SMS * 8;
   int grid_ilu = 0, grid_tri_l = 0, grid_tri_u = 0;   // co-resident grid sizes (occupancy x SMs)
-  const void *grid_ilu_kern = nullptr; int ilu_maxrow_cache = -1;
-  int ilu_maxrow() {                                 // longest row of the factor pattern
-    if (ilu_maxrow_cache < 0) { const std::vector<int> &r = lrows(); int m = 0; for (size_t i = 0; i + 1 < r.size(); ++i) m = std::max(m, r[i + 1] - r[i]); ilu_maxrow_cache = m; }
-    return ilu_maxrow_cache;
-  }
+  const void *grid_ilu_kern = nullptr;
+  DBuf<unsigned char> d_ilu_pos; DBuf<long long> d_ilu_posptr; int ilu_map_maxu = 0; bool ilu_map_tried = false;   // position map of the elimination (precond.cu)
   // B200_PIN_VALUES=1: the caller's value array is page-locked (cudaHostRegister) the first time it is seen, so the
   // once-per-nonlinear-iteration upload runs at PCIe speed instead of through a staging copy
   int pin_values = 0; const void *pinned_ptr = nullptr; size_t pinned_bytes = 0;

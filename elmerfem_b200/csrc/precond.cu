@@ -116,110 +116,91 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int nslots, const int *__re
   }
 }
 
-// The same factorisation with the row held in REGISTERS (NPL entries per lane, rows of <= 32 NPL entries): the update of entry j by pivot
-// row k (3631-3636) is found by broadcasting the pivot row's upper entries one by one (two shuffles) and comparing columns in every
-// lane, instead of a binary search over the staged row in shared memory per update (5 dependent shared-memory reads, done by all 32
-// lanes: 85 instructions per stored entry, profiles/r01_ncu_summary.txt).  Same operations on the same operands in the same order:
-// bit-identical ILUValues.
-template <int NPL>
-__global__ void __launch_bounds__(256) k_ilu0_factor_reg(int nslots, const int *__restrict__ perm, const int *__restrict__ rows,
+// ---- position map: the symbolic half of the elimination, once per structure -----------------------------------------------------------
+// For row i, its m-th lower entry (pivot row k) and the u-th upper entry (column j) of row k: the position of column j in row i, or 255.
+// k_ilu0_factor finds that position with a binary search over the staged row on every update and every factorisation (85 instructions
+// per stored entry, profiles/r01_ncu_summary.txt); with the map a refactorisation only streams one byte per update.  Layout: row i owns
+// nlow_i * maxu bytes at posptr[i].  Built when it fits (see ilu0_factor); otherwise the searching kernel stays.
+__global__ void __launch_bounds__(256) k_ilu_posmap(int n, const int *__restrict__ rows, const int *__restrict__ cols, const int *__restrict__ diag,
+                                                     const long long *__restrict__ posptr, int maxu, unsigned char *__restrict__ pos) {
+  const int lane = threadIdx.x & 31;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+    const int rs = rows[i], len = rows[i + 1] - rs, nlow = diag[i] - rs;
+    unsigned char *out = pos + posptr[i];
+    for (int m = 0; m < nlow; ++m) {
+      const int k = cols[rs + m], kd = diag[k], ke = rows[k + 1];
+      for (int u = lane; u < maxu; u += 32) {
+        unsigned char p = 255;
+        if (kd + 1 + u < ke) {
+          const int j = cols[kd + 1 + u];
+          int lo = m + 1, hi = len;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (cols[rs + mid] < j) lo = mid + 1; else hi = mid; }
+          if (lo < len && cols[rs + lo] == j) p = (unsigned char)lo;
+        }
+        out[(size_t)m * maxu + u] = p;
+      }
+    }
+  }
+}
+// The factorisation with the map (rows staged in shared memory, pivot rows of <= 64 upper entries): same operations on the same operands
+// in the same order as k_ilu0_factor -- bit-identical ILUValues.
+__global__ void __launch_bounds__(256) k_ilu0_factor_map(int nslots, const int *__restrict__ perm, const int *__restrict__ rows,
                                                           const int *__restrict__ cols, const int *__restrict__ diag,
                                                           const double *__restrict__ Avals, const int *__restrict__ src, double *LU, int *rowdone,
-                                                          Ctrl *ctrl) {
-  constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+                                                          Ctrl *ctrl, const long long *__restrict__ posptr, int maxu, const unsigned char *__restrict__ pos) {
+  __shared__ double s_val[8][ILU_MAXROW];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double *vrow = s_val[wib];
   for (int slot = gwarp; slot < nslots; slot += nwarps) {
     const int r = perm[slot];
     if (r < 0) continue;
     const int rs = rows[r], re = rows[r + 1], d = diag[r], len = re - rs, nlow = d - rs;
-    int col[NPL]; double val[NPL];
-#pragma unroll
-    for (int q = 0; q < NPL; ++q) {
-      const int p = q * 32 + lane;
-      col[q] = -1; val[q] = 0.0;
-      if (p < len) {
-        col[q] = cols[rs + p];
-        if (src) { const int s = src[rs + p]; val[q] = s >= 0 ? Avals[s] : 0.0; } else val[q] = Avals[rs + p];
-      }
+    const unsigned char *pm = pos + posptr[r];
+    for (int t = lane; t < len; t += 32) {
+      double a;
+      if (src) { const int q = src[rs + t]; a = q >= 0 ? Avals[q] : 0.0; } else a = Avals[rs + t];
+      vrow[t] = a;
     }
     long long spins = 0;
-#pragma unroll
-    for (int q = 0; q < NPL; ++q) {
-      if (q * 32 + lane < nlow) {
-        while (ld_acquire(rowdone + col[q]) == 0) {
-          if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
-          __nanosleep(40);
-        }
+    for (int t = lane; t < nlow; t += 32) {
+      const int k = cols[rs + t];
+      while (ld_acquire(rowdone + k) == 0) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        __nanosleep(40);
       }
     }
     __syncwarp();
-    auto at = [&](const int (&a)[NPL], int p) {                      // a[p >> 5] of lane p & 31, p warp-uniform
-      int v = a[0];
-#pragma unroll
-      for (int q = 1; q < NPL; ++q) if ((p >> 5) == q) v = a[q];
-      return __shfl_sync(FULL, v, p & 31);
-    };
-    auto atd = [&](const double (&a)[NPL], int p) {
-      double v = a[0];
-#pragma unroll
-      for (int q = 1; q < NPL; ++q) if ((p >> 5) == q) v = a[q];
-      return __shfl_sync(FULL, v, p & 31);
-    };
     constexpr int MB = 8;
     for (int m0 = 0; m0 < nlow; m0 += MB) {
-      // pivots and upper parts of the MB pivot rows, one L2 round trip for the batch
-      int kcol[MB];
-#pragma unroll
-      for (int t = 0; t < MB; ++t) kcol[t] = (m0 + t < nlow) ? at(col, m0 + t) : 0;
       int mkd = 0, mke = 0; double mukk = 0.0;
-#pragma unroll
-      for (int t = 0; t < MB; ++t) if (lane == t && m0 + t < nlow) { mkd = diag[kcol[t]]; mke = rows[kcol[t] + 1]; mukk = __ldcg(LU + mkd); }
-      int pj0[MB], pj1[MB]; double pv0[MB], pv1[MB];
+      if (lane < MB && m0 + lane < nlow) { const int k = cols[rs + m0 + lane]; mkd = diag[k]; mke = rows[k + 1]; mukk = __ldcg(LU + mkd); }
+      unsigned char pp0[MB], pp1[MB]; double pv0[MB], pv1[MB];
 #pragma unroll
       for (int t = 0; t < MB; ++t) {
-        const int kd = __shfl_sync(FULL, mkd, t), ke = __shfl_sync(FULL, mke, t);
+        const int kd = __shfl_sync(0xffffffffu, mkd, t), ke = __shfl_sync(0xffffffffu, mke, t);
         const int l0 = kd + 1 + lane, l1 = l0 + 32;
         const bool in0 = (m0 + t < nlow) && l0 < ke, in1 = (m0 + t < nlow) && l1 < ke;
-        pj0[t] = in0 ? cols[l0] : -2; pv0[t] = in0 ? __ldcg(LU + l0) : 0.0;
-        pj1[t] = in1 ? cols[l1] : -2; pv1[t] = in1 ? __ldcg(LU + l1) : 0.0;
+        pp0[t] = in0 ? pm[(size_t)(m0 + t) * maxu + lane] : (unsigned char)255; pv0[t] = in0 ? __ldcg(LU + l0) : 0.0;
+        pp1[t] = in1 ? pm[(size_t)(m0 + t) * maxu + 32 + lane] : (unsigned char)255; pv1[t] = in1 ? __ldcg(LU + l1) : 0.0;
       }
 #pragma unroll
       for (int t = 0; t < MB; ++t) {
         const int m = m0 + t;
-        if (m < nlow) {
-          double skm = atd(val, m);
-          const double ukk = __shfl_sync(FULL, mukk, t);
-          const int kd = __shfl_sync(FULL, mkd, t), ke = __shfl_sync(FULL, mke, t);
-          if (skm != 0.0) {                                          // 3626
-            if (fabs(ukk) > AEPS) skm = __ddiv_rn(skm, ukk);         // 3628-3629
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) if (q * 32 + lane == m) val[q] = skm;
-            const int nu = ke - kd - 1;                              // upper entries of pivot row k
-            const int n0 = nu < 32 ? nu : 32;
-            for (int u = 0; u < n0; ++u) {                           // 3631-3636
-              const int pj = __shfl_sync(FULL, pj0[t], u); const double pv = __shfl_sync(FULL, pv0[t], u);
-#pragma unroll
-              for (int q = 0; q < NPL; ++q) if (col[q] == pj) val[q] = nfms(val[q], skm, pv);
-            }
-            const int n1 = nu < 64 ? nu - 32 : 32;
-            for (int u = 0; u < n1; ++u) {
-              const int pj = __shfl_sync(FULL, pj1[t], u); const double pv = __shfl_sync(FULL, pv1[t], u);
-#pragma unroll
-              for (int q = 0; q < NPL; ++q) if (col[q] == pj) val[q] = nfms(val[q], skm, pv);
-            }
-            for (int l = kd + 1 + 64; l < ke; ++l) {                 // pivot rows wider than 64 upper entries
-              const int pj = cols[l]; const double pv = __ldcg(LU + l);
-#pragma unroll
-              for (int q = 0; q < NPL; ++q) if (col[q] == pj) val[q] = nfms(val[q], skm, pv);
-            }
-          }
-        }
+        if (m >= nlow) break;
+        double skm = vrow[m];
+        const double ukk = __shfl_sync(0xffffffffu, mukk, t);
+        if (skm == 0.0) continue;                                   // 3626
+        if (fabs(ukk) > AEPS) skm = __ddiv_rn(skm, ukk);           // 3628-3629
+        __syncwarp();
+        if (lane == 0) vrow[m] = skm;
+        if (pp0[t] != 255) vrow[pp0[t]] = nfms(vrow[pp0[t]], skm, pv0[t]);   // 3631-3636: every target column once per pivot row
+        if (pp1[t] != 255) vrow[pp1[t]] = nfms(vrow[pp1[t]], skm, pv1[t]);
+        __syncwarp();
       }
     }
-#pragma unroll
-    for (int q = 0; q < NPL; ++q) if (q * 32 + lane < len) __stcg(LU + rs + q * 32 + lane, val[q]);   // 3643-3649
+    for (int t = lane; t < len; t += 32) __stcg(LU + rs + t, vrow[t]);   // 3643-3649
     __threadfence();
     __syncwarp();
     if (lane == 0) st_release(rowdone + r, 1);
@@ -275,17 +256,37 @@ void ilu0_factor(Handle &h) {
     B200_CUDA(cudaMemsetAsync(h.d_rowdone.p, 0, (size_t)h.n * sizeof(int), st));
     B200_CUDA(cudaMemsetAsync(&h.ctrl.p->spin_timeout, 0, sizeof(int), st));
     const double *src = h.have_prec ? h.d_prec.p : h.d_vals.p;        // CRSMatrix.F90:3480-3484
-    // rows of <= 96 entries are factorised from registers (1, 2 or 3 entries per lane); longer rows keep the shared-memory kernel
-    const int maxrow = h.ilu_maxrow();
-    static const bool reg_ok = !(getenv("B200_ILU_REG") && atoi(getenv("B200_ILU_REG")) == 0);
-    const void *kern = (const void *)k_ilu0_factor;
-    if (reg_ok && maxrow <= 32) kern = (const void *)k_ilu0_factor_reg<1>;
-    else if (reg_ok && maxrow <= 64) kern = (const void *)k_ilu0_factor_reg<2>;
-    else if (reg_ok && maxrow <= 96) kern = (const void *)k_ilu0_factor_reg<3>;
+    // position map (symbolic, once per structure / ILU order) when it fits: rows staged in shared memory, pivot rows of <= 64 upper
+    // entries, at most 4 GB of one-byte positions; otherwise the kernel that searches on every update
+    static const bool map_ok = !(getenv("B200_ILU_MAP") && atoi(getenv("B200_ILU_MAP")) == 0);
+    if (map_ok && !h.ilu_map_tried) {
+      h.ilu_map_tried = true;
+      const std::vector<int> &R = h.lrows(), &Dg = h.ldiag();
+      int maxu = 0, maxrow = 0; long long nlow_tot = 0;
+      for (int i = 0; i < h.n; ++i) { maxu = std::max(maxu, R[i + 1] - Dg[i] - 1); maxrow = std::max(maxrow, R[i + 1] - R[i]); nlow_tot += Dg[i] - R[i]; }
+      if (maxu >= 1 && maxu <= 64 && maxrow <= ILU_MAXROW && maxrow < 255 && nlow_tot * maxu <= (4LL << 30)) {
+        std::vector<long long> pp((size_t)h.n + 1, 0);
+        for (int i = 0; i < h.n; ++i) pp[i + 1] = pp[i] + (long long)(Dg[i] - R[i]) * maxu;
+        h.d_ilu_posptr.ensure((size_t)h.n + 1); h.d_ilu_pos.ensure((size_t)std::max(1LL, pp[h.n]));
+        B200_CUDA(cudaMemcpyAsync(h.d_ilu_posptr.p, pp.data(), ((size_t)h.n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        k_ilu_posmap<<<NUM_SMS * 8, 256, 0, st>>>(h.n, h.d_lrows(), h.d_lcols(), h.d_ldiag(), h.d_ilu_posptr.p, maxu, h.d_ilu_pos.p);
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaStreamSynchronize(st));                      // pp goes out of scope
+        h.ilu_map_maxu = maxu;
+      }
+    }
+    const bool use_map = map_ok && h.ilu_map_maxu > 0;
+    const void *kern = use_map ? (const void *)k_ilu0_factor_map : (const void *)k_ilu0_factor;
     if (h.grid_ilu_kern != kern) { h.grid_ilu = persistent_blocks(kern, 256, 0); h.grid_ilu_kern = kern; }
     int blocks = std::max(1, std::min(h.grid_ilu, (h.L.nslots + 7) / 8));
-    launch_coresident(kern, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
-                      (const int *)(h.ilu_sep() ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
+    B200_CUDA(cudaEventRecord(h.evf0, st));                          // (the one-time symbolic map is not part of the factorisation time)
+    if (use_map)
+      launch_coresident(kern, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
+                        (const int *)(h.ilu_sep() ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p, (const long long *)h.d_ilu_posptr.p, h.ilu_map_maxu,
+                        (const unsigned char *)h.d_ilu_pos.p);
+    else
+      launch_coresident(kern, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
+                        (const int *)(h.ilu_sep() ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
     int eb = std::min((h.n + 255) / 256, NUM_SMS * 8);
     k_ilu0_invert_diag<<<eb, 256, 0, st>>>(h.n, h.d_ldiag(), h.d_ilu.p);
     sell_refresh_values(h, h.L, h.d_ilu.p);

@@ -646,3 +646,23 @@ def test_sgs(oracle, b200, heat, heat_gpu):
     assert got is not None and got["info"] == ref["info"] == 1 and iters_close(got["iters"], ref["iters"]), (got["iters"], ref["iters"])
     assert abs(compute_norm(got["x"]) - 4.0) <= 1e-5 * 4.0
     M.close()
+
+
+@pytest.mark.parametrize("ndeg", [2, 5, 6, 8, 10])
+def test_spmv_ndeg_variants_bit_exact(oracle, b200, ndeg):
+    """CRS_MatrixVectorProd's ndeg loops that no benchmark operand exercises (CRSMatrix.F90:4794-4856): ndeg = 2 -> 2 partial sums,
+    5 and 10 -> 5, 6 -> 3, 8 -> 4; one column index per group of consecutive columns.  Node-block matrices (ndeg interleaved dofs per node
+    of a hex8 grid, dense ndeg x ndeg blocks, random values): the device product equals the oracle's bit for bit, and scipy's to rounding."""
+    from elmerfem_b200 import synth
+    xyz, elems = synth.grid_hex8(5, 4, 3)
+    rows, cols, diag = synth.crs_structure(xyz.shape[0], elems, ndeg)
+    rs = np.random.RandomState(100 + ndeg)
+    A = synth.CRS(rows, cols, diag, rs.standard_normal(cols.size), ndeg)
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, ndeg); M.set_values(A.vals)
+    for _ in range(2):
+        u = rs.standard_normal(A.n)
+        got, ref = M.matvec(u), oracle.matvec(A, u)
+        assert np.array_equal(got, ref), ndeg
+        sref = A.to_scipy() @ u
+        assert np.abs(got - sref).max() <= 1e-12 * np.abs(sref).max()
+    M.close()
