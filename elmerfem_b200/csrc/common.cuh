@@ -154,6 +154,7 @@ struct Handle {
   DBuf<int> d_order_f; DBuf<int> d_rowdone;      // factorisation order (rows sorted by forward level)
   std::vector<int> h_level_f;
   Sell L, U; DBuf<double> d_dinv_slot;           // U slots carry the inverted diagonal
+  int tri_node = 0; bool tri_node_u = false, tri_node_off = false;    // tri_node > 0: L/U plans are in the node-lane layout with this many dofs per node (structure.cu); off: never use it
   DBuf<int> tri_counters; int tri_maxw = 0, tri_lookahead = 2; unsigned tri_gate_sleep = 100, tri_spin_sleep = 0;
   DBuf<int> d_lvlcnt_f, d_lvlcnt_b;              // slices per level (forward / backward)
   DBuf<int> d_urhs; DBuf<double> d_yl, d_xu;     // backward rhs map (U slot -> L slot); slot-ordered solve vectors

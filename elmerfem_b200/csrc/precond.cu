@@ -604,6 +604,171 @@ __global__ void __launch_bounds__(256, 1) k_sptrsv_wide(SellView T, const int *_
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same sweep on the node-lane layout (structure.cu node_lane_layout: ND interleaved dofs per node, lane = ni * ND + d).  The rows
+// of a node are solved in ONE pass of a warp: everything a row needs from OTHER nodes is gathered / polled exactly as in k_sptrsv_wide
+// (all lanes in parallel), what it needs from its own node -- the entries adjacent to the diagonal: the last d entries of a lower row,
+// the first ND-1-d of an upper row -- is passed between lanes by shuffle in ND short rounds.  One L2 hand-off per NODE level instead of
+// one per row level.  Arithmetic: the reference's left-to-right order (own-node columns come last in a lower row and first in an upper
+// row, which is why the upper rows of a node are summed one after the other); the value another row receives by shuffle is the
+// canonicalised one it would have read from memory.  Bit-identical to k_sptrsv / CRS_LUSolve.
+template <bool UPPER, int NCH, int ND>
+__global__ void __launch_bounds__(256, 1) k_sptrsv_wide_node(SellView T, const int *__restrict__ slice_level, const int *__restrict__ lvl_slices,
+                                                              int *lvl_done, int lookahead, unsigned gate_sleep, unsigned spin_sleep,
+                                                              const double *__restrict__ dinv_slot, const double *__restrict__ rhs,
+                                                              const int *__restrict__ rhs_idx, double *out, double *__restrict__ nat_out,
+                                                              Ctrl *ctrl) {
+  if (ctrl->done) return;
+  constexpr int WT = 16 * NCH;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int ni = lane / ND, d = lane - ni * ND, nbase = ni * ND;     // node of the lane inside the slice, dof, first lane of the node
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slice = gwarp; slice < T.nslices; slice += nwarps) {
+    const long long p0 = T.ptr[slice];
+    const int W = (int)((T.ptr[slice + 1] - p0) >> 5);
+    const int slot = slice * 32 + lane;
+    const int row = T.perm[slot];
+    const int len = T.len[slot];
+    const int *__restrict__ cp = T.cols + p0 + lane;
+    const double *__restrict__ vp = T.vals + p0 + lane;
+    const double r0 = row >= 0 ? rhs[rhs_idx ? rhs_idx[slot] : row] : 0.0;
+    const double dinv = (UPPER && row >= 0) ? dinv_slot[slot] : 1.0;
+    long long spins = 0;
+    const int sh = UPPER ? 0 : WT - W;
+    const int lo = UPPER ? 0 : WT - len, hi = UPPER ? len : WT;
+    const int wl = max(W - 1, 0);
+    constexpr int K0 = UPPER ? 0 : WT - TRI_TAIL;                    // first tail position
+    int ct[TRI_TAIL]; double vt[TRI_TAIL], xt[TRI_TAIL];
+#pragma unroll
+    for (int t = 0; t < TRI_TAIL; ++t) {
+      const int pos = min(max(K0 + t - sh, 0), wl);
+      ct[t] = W ? ld_stream(cp + pos * 32) : 0;
+      vt[t] = W ? ld_stream(vp + pos * 32) : 0.0;
+    }
+    {                                                             // throttle: wait for the wavefront to come near
+      const int wlv = slice_level[slice] - lookahead;
+      if (lane == 0 && wlv >= 0) {
+        const int need = lvl_slices[wlv];
+        while (ld_relaxed_i(lvl_done + wlv * 32) < need) {
+          if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+          if (gate_sleep) __nanosleep(gate_sleep);
+        }
+      }
+      __syncwarp();
+    }
+    // tail entries that belong to the node itself: lower row, the last d ; upper row, the first ND-1-d
+    unsigned thas = 0, town = 0;
+#pragma unroll
+    for (int t = 0; t < TRI_TAIL; ++t) {
+      const bool has = (K0 + t >= lo) && (K0 + t < hi);
+      const bool own = has && row >= 0 && (UPPER ? (t < ND - 1 - d) : (t >= TRI_TAIL - d));
+      thas |= (unsigned)has << t; town |= (unsigned)own << t;
+      xt[t] = ld_relaxed_pred(out + ct[t], has && !own, 0.0);
+    }
+    unsigned tpend = thas & ~town;
+    double s = r0;
+    double p[UPPER ? WT : 1];
+#pragma unroll
+    for (int k = 0; k < (UPPER ? WT : 1); ++k) p[k] = 0.0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (UPPER ? (ch * 16 >= W) : (ch * 16 + 15 < WT - W)) continue;   // (warp-uniform) nothing stored in this chunk
+      int c[16]; double v[16], x[16];
+      unsigned has = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = ch * 16 + j;
+        const bool tail = UPPER ? (k < TRI_TAIL) : (k >= WT - TRI_TAIL);
+        const int pos = min(max(k - sh, 0), wl);
+        c[j] = W ? ld_stream(cp + pos * 32) : 0;
+        v[j] = W ? ld_stream(vp + pos * 32) : 0.0;
+        has |= (unsigned)(!tail && k >= lo && k < hi) << j;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = ld_relaxed_pred(out + c[j], (has >> j) & 1u, 0.0);
+      unsigned pend = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pend |= (unsigned)(is_sentinel(x[j])) << j;
+      pend &= has;
+      while (__any_sync(FULL, pend != 0)) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        if (spin_sleep) __nanosleep(spin_sleep);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = ld_relaxed_pred(out + c[j], (pend >> j) & 1u, x[j]); if (!is_sentinel(x[j])) pend &= ~(1u << j); }
+      }
+      if (!UPPER) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const double t = __dsub_rn(s, __dmul_rn(v[j], x[j])); s = (has >> j) & 1u ? t : s; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[ch * 16 + j] = (has >> j) & 1u ? __dmul_rn(v[j], x[j]) : 0.0;
+      }
+    }
+    // tail operands of OTHER nodes: the previous level
+#pragma unroll
+    for (int t = 0; t < TRI_TAIL; ++t) if (!is_sentinel(xt[t])) tpend &= ~(1u << t);
+    while (__any_sync(FULL, tpend != 0)) {
+      if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+      if (spin_sleep) __nanosleep(spin_sleep);
+#pragma unroll
+      for (int t = 0; t < TRI_TAIL; ++t) { xt[t] = ld_relaxed_pred(out + ct[t], (tpend >> t) & 1u, xt[t]); if (!is_sentinel(xt[t])) tpend &= ~(1u << t); }
+    }
+    double res = 0.0;
+    if (!UPPER) {
+      // the tail entries of other nodes, then the node's own dofs 0 .. d-1 (column order), one shuffle round per dof
+#pragma unroll
+      for (int t = 0; t < TRI_TAIL; ++t) { const double u = __dsub_rn(s, __dmul_rn(vt[t], xt[t])); s = ((thas & ~town) >> t) & 1u ? u : s; }
+#pragma unroll
+      for (int r = 0; r < ND - 1; ++r) {
+        double fin = s;                                           // final for the lanes with d <= r
+        if (fin != fin) fin = __longlong_as_double((long long)CANON_NAN);
+        const double xr = __shfl_sync(FULL, fin, nbase + r);
+        // own entry of dof r sits at tail index TRI_TAIL - d + r
+        double vo = 0.0; bool ho = false;
+#pragma unroll
+        for (int t = 0; t < TRI_TAIL; ++t) if (t == TRI_TAIL - d + r) { vo = vt[t]; ho = (town >> t) & 1u; }
+        if (d > r && ho) s = __dsub_rn(s, __dmul_rn(vo, xr));
+      }
+      res = s;
+    } else {
+      // upper rows of a node one after the other, dof ND-1 first: own dofs d+1 .. ND-1 (column order), other nodes' tail, the products
+      double xo[ND];
+#pragma unroll
+      for (int r = 0; r < ND; ++r) xo[r] = 0.0;
+#pragma unroll
+      for (int r = ND - 1; r >= 0; --r) {
+        double a = r0;
+#pragma unroll
+        for (int t = 0; t < TRI_TAIL; ++t) {
+          double xv = xt[t];
+          if ((town >> t) & 1u) {                                 // own entry: dof d + 1 + t
+            xv = xo[ND - 1];
+#pragma unroll
+            for (int q = 0; q < ND - 1; ++q) if (d + 1 + t == q) xv = xo[q];
+          }
+          const double u = __dsub_rn(a, __dmul_rn(vt[t], xv));
+          a = (thas >> t) & 1u ? u : a;
+        }
+#pragma unroll
+        for (int k = TRI_TAIL; k < WT; ++k) { const double u = __dsub_rn(a, p[k]); a = (k < hi) ? u : a; }
+        double fin = __dmul_rn(dinv, a);
+        if (fin != fin) fin = __longlong_as_double((long long)CANON_NAN);
+        if (d == r) res = fin;
+        xo[r] = __shfl_sync(FULL, fin, nbase + r);
+      }
+    }
+    if (row >= 0) {
+      if (res != res) res = __longlong_as_double((long long)CANON_NAN);
+      st_relaxed(out + slot, res);
+      if (nat_out) nat_out[row] = res;
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(lvl_done + slice_level[slice] * 32, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Symmetric Gauss-Seidel sweeps of itermethod_sgs (IterativeMethods.F90:219-283): forward i = 1..n, then backward i = n..1,
 //   s = sum_j A_ij x_j (current x, left to right) ;  x_i = x_i + Omega * (b_i - s) / a_ii.
 // The same wavefront as the triangular solves, on the matrix itself: rows in dependency-level order (the L / U plans of the
@@ -664,6 +829,7 @@ void sgs_sweeps(Handle &h, const double *b, double *x, double *t1, double *t2, d
   B200_REQUIRE(h.have_vals, "SGS before b200_set_values");
   if (h.n == 0) return;
   if (h.ilu_sep()) { h.ilu_order = 0; h.bilu_blocks = 0; ilu_invalidate(h); }     // the sweeps need the plans of the matrix pattern itself
+  if (h.tri_node) { h.tri_node_off = true; ilu_invalidate(h); }                   // ... in the row-level layout (k_sgs_sweep polls per row)
   tri_analyse(h);
   cudaStream_t st = h.stream;
   static int grid_f = 0, grid_b = 0;
@@ -716,6 +882,33 @@ void lu_apply(Handle &h, double *u, const double *v) {
   if (h.tri_mode == 3 && h.wv.ready) { lu_apply_wave(h, u, v); return; }   // grid stencils; not detected -> level kernel
   if (h.tri_mode == 1) { lu_apply_task(h, u, v); return; }
   k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
+  if (h.tri_node >= 2) {                                           // node-lane plans: only the node-aware sweeps may run on them
+    const int nch = (h.tri_maxw + 15) / 16;
+    B200_REQUIRE(nch >= 1 && nch <= 4, "node-lane plan with rows wider than 64 entries");
+    const void *kl = nullptr, *ku = nullptr;
+#define B200_NODE_CASE(ND_)                                                                                                       \
+    case ND_:                                                                                                                       \
+      kl = nch == 1 ? (const void *)k_sptrsv_wide_node<false, 1, ND_> : nch == 2 ? (const void *)k_sptrsv_wide_node<false, 2, ND_>    \
+         : nch == 3 ? (const void *)k_sptrsv_wide_node<false, 3, ND_> : (const void *)k_sptrsv_wide_node<false, 4, ND_>;             \
+      ku = nch == 1 ? (const void *)k_sptrsv_wide_node<true, 1, ND_> : nch == 2 ? (const void *)k_sptrsv_wide_node<true, 2, ND_>      \
+         : nch == 3 ? (const void *)k_sptrsv_wide_node<true, 3, ND_> : (const void *)k_sptrsv_wide_node<true, 4, ND_>;               \
+      break;
+    switch (h.tri_node) {
+      B200_NODE_CASE(2) B200_NODE_CASE(3) B200_NODE_CASE(4) B200_NODE_CASE(5) B200_NODE_CASE(6)
+      default: B200_REQUIRE(false, "node-lane plan: unsupported dofs per node");
+    }
+#undef B200_NODE_CASE
+    if (!h.tri_node_u) {                                            // backward plan in the row-level layout: the row-per-thread sweeps
+      if (h.tri_maxw <= 8) ku = (const void *)k_sptrsv<true, 8>;
+      else if (h.tri_maxw <= 16 || h.tri_maxw > 48) ku = (const void *)k_sptrsv<true, 16>;
+      else if (h.tri_maxw <= 32) ku = (const void *)k_sptrsv_wide<true, 2>;
+      else ku = (const void *)k_sptrsv_wide<true, 3>;
+    }
+    lu_launch_kernels(h, kl, ku, u, v);
+    B200_CUDA(cudaGetLastError());
+    h.st_launch += 3; h.st_pcond++;
+    return;
+  }
   static const bool wide_ok = !(getenv("B200_TRI_WIDE") && atoi(getenv("B200_TRI_WIDE")) == 0);
   if (h.tri_maxw <= 8) lu_launch_kernels(h, (const void *)k_sptrsv<false, 8>, (const void *)k_sptrsv<true, 8>, u, v);
   else if (h.tri_maxw <= 16 || !wide_ok || h.tri_maxw > 48) lu_launch_kernels(h, (const void *)k_sptrsv<false, 16>, (const void *)k_sptrsv<true, 16>, u, v);

@@ -134,6 +134,41 @@ static void level_layout(int n, const std::vector<int> &level, int nlev, std::ve
   }
 }
 
+// Node-lane layout for matrices with ND interleaved dofs per node (h.ndeg > 1; rows of node I are I*ND .. I*ND+ND-1, and every row holds
+// its node's full diagonal block): levels are those of the NODE graph, and the ND rows of a node sit in ADJACENT LANES of one slice
+// (lane = ni * ND + d, 32 / ND nodes per slice).  k_sptrsv_wide_node then passes a node's own results between lanes by shuffle, so the
+// dependency chain through L2 has one hop per NODE level instead of one per row level (3784 -> 946 on the 4-dof cavity operand,
+// 2904 -> 968 on the 3-dof beam).  Slices of this layout hold mutually dependent rows: only the node-aware sweeps may run on it (the
+// row-per-thread polling kernels would wait for a value of their own warp); the factorisation (warp per row, slot order = a topological
+// order) is unaffected.
+static void node_lane_layout(int nnodes, int ND, const std::vector<int> &nlevel, int nlev, std::vector<int> &perm, int &nslots, bool backward,
+                             std::vector<int> &gate, std::vector<int> &lvl_slices) {
+  const int NPW = 32 / ND;
+  std::vector<long long> cnt(nlev + 1, 0);
+  for (int I = 0; I < nnodes; ++I) cnt[nlevel[I] + 1]++;
+  std::vector<long long> slice0(nlev + 1, 0);
+  for (int l = 0; l < nlev; ++l) slice0[l + 1] = slice0[l] + (cnt[l + 1] + NPW - 1) / NPW;
+  const long long ns = slice0[nlev] * 32;
+  B200_REQUIRE(ns < 2147483647LL, "node layout exceeds int32 slots");
+  nslots = (int)ns;
+  perm.assign(nslots, -1);
+  gate.assign(nslots / 32, 0);
+  lvl_slices.assign(nlev, 0);
+  for (int l = 0; l < nlev; ++l) {
+    lvl_slices[l] = (int)(slice0[l + 1] - slice0[l]);
+    for (long long sl = slice0[l]; sl < slice0[l + 1]; ++sl) gate[sl] = l;
+  }
+  std::vector<long long> fill(nlev, 0);
+  auto place = [&](int I) {
+    const int l = nlevel[I];
+    const long long k = fill[l]++;
+    const long long sl = slice0[l] + k / NPW; const int ni = (int)(k % NPW);
+    for (int d = 0; d < ND; ++d) perm[sl * 32 + ni * ND + d] = I * ND + d;
+  };
+  if (!backward) for (int I = 0; I < nnodes; ++I) place(I);
+  else for (int I = nnodes - 1; I >= 0; --I) place(I);
+}
+
 // One round of InitializeILU1 (CRSMatrix.F90:3664-3795) on a 0-based pattern: row i keeps its entries and gains the
 // columns of the upper parts of the rows k < i it held BEFORE the round (fills of the round do not cascade);
 // columns ascending.
@@ -225,11 +260,58 @@ void tri_analyse(Handle &h) {
     lb[i] = l; nlb = std::max(nlb, l + 1);
   }
   if (n == 0) { nlf = nlb = 0; }
-  h.nlev_f = nlf; h.nlev_b = nlb;
   std::vector<int> pf, pb; int nsf = 0, nsb = 0;
   std::vector<int> gf, gb, cf, cb;
-  level_layout(n, lf, nlf, pf, nsf, false, gf, cf);
-  level_layout(n, lb, nlb, pb, nsb, true, gb, cb);
+  // Node-lane plans are used where they were measured to win: rows wider than 48 entries per triangle (4-dof Navier-Stokes operands:
+  // 17.3 -> 8.0 ms per ILU0 application on the 96^3 cavity), for which the row-level path is the chunked generic loop.  On the 3-dof beam
+  // (rows of 40: register-resident row-level kernel) forward wins (4.1 -> 2.7 ms) but backward loses (4.1 -> 7.3 ms) and a mixed plan is
+  // no faster overall (8.5 vs 8.2 ms): the row-level layout stays.  B200_TRI_NODE = 0 never, 2 whenever the structure allows.
+  const int node_cfg = getenv("B200_TRI_NODE") ? atoi(getenv("B200_TRI_NODE")) : 1;
+  const bool node_ok = node_cfg != 0;
+  const int ND = h.ndeg;
+  int maxw = 0;
+  for (int i = 0; i < n; ++i) maxw = std::max(maxw, std::max(diag[i] - rows[i], rows[i + 1] - diag[i] - 1));
+  h.tri_node = 0;
+  bool node = node_ok && !h.tri_node_off && ND >= 2 && ND <= 6 && n > 0 && n % ND == 0 && maxw <= 64 && (maxw > 48 || node_cfg == 2);
+  if (node) {                                                     // every row must hold its node's full diagonal block, adjacent to the diagonal
+#pragma omp parallel for schedule(static) reduction(&& : node)
+    for (int i = 0; i < n; ++i) {
+      const int I = i / ND, d = i - I * ND;
+      bool ok = (diag[i] - rows[i] >= d) && (rows[i + 1] - diag[i] - 1 >= ND - 1 - d);
+      for (int t = 0; ok && t < d; ++t) ok = cols[diag[i] - d + t] == I * ND + t;
+      for (int t = 0; ok && t < ND - 1 - d; ++t) ok = cols[diag[i] + 1 + t] == i + 1 + t;
+      node = node && ok;
+    }
+  }
+  if (node) {
+    const int nn = n / ND;
+    std::vector<int> nf(nn, 0), nb(nn, 0);
+    int nnf = 0, nnb = 0;
+    for (int I = 0; I < nn; ++I) {
+      int l = 0;
+      for (int i = I * ND; i < I * ND + ND; ++i)
+        for (int p = rows[i]; p < diag[i]; ++p) { const int J = cols[p] / ND; if (J != I) l = std::max(l, nf[J] + 1); }
+      nf[I] = l; nnf = std::max(nnf, l + 1);
+    }
+    for (int I = nn - 1; I >= 0; --I) {
+      int l = 0;
+      for (int i = I * ND; i < I * ND + ND; ++i)
+        for (int p = diag[i] + 1; p < rows[i + 1]; ++p) { const int J = cols[p] / ND; if (J != I) l = std::max(l, nb[J] + 1); }
+      nb[I] = l; nnb = std::max(nnb, l + 1);
+    }
+    // (B200_TRI_NODE_U = 0: backward plan in the row-level layout, for experiments)
+    bool node_u = true;
+    if (getenv("B200_TRI_NODE_U")) node_u = atoi(getenv("B200_TRI_NODE_U")) != 0;
+    node_lane_layout(nn, ND, nf, nnf, pf, nsf, false, gf, cf);
+    nlf = nnf;
+    if (node_u) { node_lane_layout(nn, ND, nb, nnb, pb, nsb, true, gb, cb); nlb = nnb; }
+    else level_layout(n, lb, nlb, pb, nsb, true, gb, cb);
+    h.tri_node = ND; h.tri_node_u = node_u;
+  } else {
+    level_layout(n, lf, nlf, pf, nsf, false, gf, cf);
+    level_layout(n, lb, nlb, pb, nsb, true, gb, cb);
+  }
+  h.nlev_f = nlf; h.nlev_b = nlb;
   h.L.perm.ensure(nsf); h.U.perm.ensure(nsb);
   h.L.gate.ensure(gf.size()); h.U.gate.ensure(gb.size());
   h.d_lvlcnt_f.ensure(cf.size()); h.d_lvlcnt_b.ensure(cb.size());

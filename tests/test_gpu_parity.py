@@ -666,3 +666,44 @@ def test_spmv_ndeg_variants_bit_exact(oracle, b200, ndeg):
         sref = A.to_scipy() @ u
         assert np.abs(got - sref).max() <= 1e-12 * np.abs(sref).max()
     M.close()
+
+
+@pytest.mark.parametrize("ndeg", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("node_u", ["0", "1"])
+def test_node_lane_sweeps_bit_exact(oracle, b200, monkeypatch, ndeg, node_u):
+    """Node-lane triangular solves (structure.cu node_lane_layout, precond.cu k_sptrsv_wide_node) forced on (B200_TRI_NODE=2) for every
+    dof count they are instantiated for: node-block matrices with dense ndeg x ndeg blocks, ILU0 factor and both sweeps bit-identical to
+    CRS_IncompleteLU / CRS_LUSolve (CRSMatrix.F90:3604-3660, 4642-4660), with the backward plan in the node-lane and in the row-level layout."""
+    from elmerfem_b200 import synth
+    monkeypatch.setenv("B200_TRI_NODE", "2")
+    monkeypatch.setenv("B200_TRI_NODE_U", node_u)
+    ex = 2 if ndeg >= 5 else (3 if ndeg == 4 else 4)              # rows of at most 64 entries per triangle: 27 * ndeg / 2
+    xyz, elems = synth.grid_hex8(ex + 5, ex + 1, ex)
+    if 27 * ndeg > 128:                                           # 5 and 6 dofs: a bar of single elements (12-node stencils) keeps the rows narrow enough
+        xyz, elems = synth.grid_hex8(14, 1, 1)
+    rows, cols, diag = synth.crs_structure(xyz.shape[0], elems, ndeg)
+    rs = np.random.RandomState(200 + ndeg)
+    vals = 0.05 * rs.standard_normal(cols.size)
+    vals[diag - 1] = 1.0 + rs.random_sample(diag.size)
+    A = synth.CRS(rows, cols, diag, vals, ndeg)
+    assert int(np.max(np.maximum(A.diag - A.rows[:-1], A.rows[1:] - A.diag - 1))) <= 64
+    M = b200.Matrix(); M.set_structure(A.rows, A.cols, A.diag, 1, ndeg); M.set_values(A.vals)
+    try:
+        M.factorize()
+        ilu = oracle.ilu0(A)
+        assert np.array_equal(M.ilu_values(), ilu)
+        lv = M.levels()
+        nn = A.n // ndeg
+        assert lv["forward"] < A.n and lv["forward"] <= nn       # node levels, not row levels
+        for seed in (1, 2):
+            v = rs.standard_normal(A.n)
+            if seed == 2:
+                v[::4] = 0.0
+            got, ref = M.lu_precondition(v), oracle.lu_precond(A, ilu, v)
+            assert np.array_equal(got.view(np.int64), ref.view(np.int64)), (ndeg, node_u)
+        b = rs.standard_normal(A.n)
+        ref = oracle.itersolve(A, b, method="bicgstab", precond="ilu0", tol=1e-10, maxit=200)
+        got = M.solve(b, method="bicgstab", precond="ilu0", tol=1e-10, maxit=200)
+        assert got["info"] == ref["info"] and abs(got["iters"] - ref["iters"]) <= 1
+    finally:
+        M.close()
