@@ -668,7 +668,7 @@ def test_spmv_ndeg_variants_bit_exact(oracle, b200, ndeg):
     M.close()
 
 
-@pytest.mark.parametrize("ndeg", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("ndeg", [2, 3, 4, 5])
 @pytest.mark.parametrize("node_u", ["0", "1"])
 def test_node_lane_sweeps_bit_exact(oracle, b200, monkeypatch, ndeg, node_u):
     """Node-lane triangular solves (structure.cu node_lane_layout, precond.cu k_sptrsv_wide_node) forced on (B200_TRI_NODE=2) for every
