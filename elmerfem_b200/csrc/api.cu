@@ -55,13 +55,16 @@ static void ensure_runtime(Handle &h) {
   h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 16));
   h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", 100);
   h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
-  h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", -2);  // 0 level kernel, 1 task kernel, 2 skewed lanes, 3 wave tiles, -1 time level/task and pick, -2 (default) wave tiles where the grid stencil is detected and they win
+  h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", -2);  // 0 level kernel, 1 task kernel, 2 skewed lanes, 3 wave tiles, 4 lane tiles, -1 time level/task and pick, -2 (default) time level / wave tiles / lane tiles where the grid stencil is detected and keep the fastest
   h.sk_blocks_per_sm = env_int("B200_SKEW_BLOCKS_PER_SM", 0);
   h.sk_cfg = env_int("B200_SKEW_CFG", 0);
   h.sk_wpb = env_int("B200_SKEW_WPB", 0);
   h.wv_blocks_per_sm = env_int("B200_WAVE_BLOCKS_PER_SM", 0);
   h.wv_cfg = env_int("B200_WAVE_CFG", 0);
   h.wv_e = env_int("B200_WAVE_E", 3);
+  h.lt_tc = env_int("B200_LANE_TC", 2);
+  h.lt_warps = env_int("B200_LANE_WARPS", 0);
+  h.lt_depth = env_int("B200_LANE_DEPTH", 0);
   h.bl_host = env_int("B200_BICGSTABL_HOST", 0) != 0;
   h.stage_uploads = env_int("B200_STAGE_UPLOADS", 1) != 0;
   h.tt_rows = env_int("B200_TT_ROWS", 0);
@@ -278,7 +281,7 @@ int b200_destroy(void **handle) {
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
     h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
     h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
-    tritask_release(*h); skew_release(*h); wave_release(*h); h->d_ilu_pos.release(); h->d_ilu_posptr.release(); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
+    tritask_release(*h); skew_release(*h); wave_release(*h); lane_release(*h); h->d_ilu_pos.release(); h->d_ilu_posptr.release(); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
     for (auto &w : h->work) w.release();
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include "skewgeom.h"
 #include "wavegeom.h"
+#include "lanegeom.h"
 
 namespace b200 {
 
@@ -121,6 +122,12 @@ struct WavePlan {
   bool ready = false, tried = false, trace_on = false;
 };
 
+// lane-tile triangular solve (lane.cu, B200_TRI_MODE=4): geometry, tile tables, the two per-step entry streams, work vectors
+struct LanePlan {
+  LaneGeom g; DBuf<int> tile_of, tile_sig, tile_grp; DBuf<double> SL, SU, y, x; DBuf<long long> trace;
+  bool ready = false, tried = false, trace_on = false, traced = false;
+};
+
 struct Handle {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -161,6 +168,7 @@ struct Handle {
   // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
   SkewPlan sk; int sk_blocks_per_sm = 0, sk_cfg = 0, sk_wpb = 0;
   WavePlan wv; int wv_blocks_per_sm = 0, wv_cfg = 0, wv_e = 3;
+  LanePlan lt; int lt_tc = 2, lt_warps = 0, lt_depth = 0;
   void *stage_buf[2] = {nullptr, nullptr}; cudaEvent_t stage_ev[2] = {nullptr, nullptr}; bool stage_uploads = true;   // pinned bounce buffers of b200_set_values
   bool mv_honor_skip = false;                     // partitioned SpMVs queued inside a conditional section (Ctrl::done == 2) return at once
   bool bl_host = false;                           // B200_BICGSTABL_HOST=1: host-driven BiCGStab(l) (the round-1 driver) instead of the device-resident one
@@ -294,6 +302,12 @@ void wave_analyse(Handle &h);                          // wave-tile plan (host d
 void wave_refresh_values(Handle &h);
 void wave_release(Handle &h);
 void lu_apply_wave(Handle &h, double *u, const double *v);
+void lane_analyse(Handle &h);                          // lane-tile plan (same detection; no-op when it does not apply)
+void lane_refresh_values(Handle &h);
+void lane_release(Handle &h);
+void lu_apply_lane(Handle &h, double *u, const double *v);
+void lane_trace_enable(Handle &h, bool on);
+void lane_trace_fetch(Handle &h, std::vector<long long> &out);
 void wave_trace_enable(Handle &h, bool on);
 void wave_trace_fetch(Handle &h, std::vector<long long> &out);
 void halo_release(Handle &h);

@@ -247,7 +247,9 @@ void ilu0_factor(Handle &h) {
   B200_REQUIRE(h.have_vals, "ILU0 requested before b200_set_values");
   tri_analyse(h);
   if (h.tri_mode == 2) skew_analyse(h);
-  else if (h.tri_mode == 3 || h.tri_mode == -2) wave_analyse(h);
+  else if (h.tri_mode == 3) wave_analyse(h);
+  else if (h.tri_mode == 4) lane_analyse(h);
+  else if (h.tri_mode == -2) { wave_analyse(h); lane_analyse(h); }
   else if (h.tri_mode != 0) tritask_analyse(h);
   cudaStream_t st = h.stream;
   h.d_ilu.ensure(h.lnnz());
@@ -295,6 +297,7 @@ void ilu0_factor(Handle &h) {
     if (h.tt_ready) tritask_refresh_values(h);
     if (h.sk.ready) skew_refresh_values(h);
     if (h.wv.ready) wave_refresh_values(h);
+    if (h.lt.ready) lane_refresh_values(h);
     B200_CUDA(cudaGetLastError());
   }
   B200_CUDA(cudaEventRecord(h.evf1, st));
@@ -880,6 +883,7 @@ void lu_apply(Handle &h, double *u, const double *v) {
   if (h.n == 0) return;
   if (h.tri_mode == 2 && h.sk.ready) { lu_apply_skew(h, u, v); return; }   // experimental, opt-in; not ready -> level kernel
   if (h.tri_mode == 3 && h.wv.ready) { lu_apply_wave(h, u, v); return; }   // grid stencils; not detected -> level kernel
+  if (h.tri_mode == 4 && h.lt.ready) { lu_apply_lane(h, u, v); return; }   // grid stencils; not detected -> level kernel
   if (h.tri_mode == 1) { lu_apply_task(h, u, v); return; }
   k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
   if (h.tri_node >= 2) {                                           // node-lane plans: only the node-aware sweeps may run on them
@@ -945,17 +949,21 @@ static void tri_autotune(Handle &h) {
   a.release(); b.release();
 }
 
-// Default (B200_TRI_MODE unset): when the factor is that of a structured-grid stencil, the level kernel and the wave-tile kernel
-// (bit-identical results) are timed once on the real factor and the faster one is kept; the loser's plan is released.
+// Default (B200_TRI_MODE unset): when the factor is that of a structured-grid stencil, the level kernel, the wave-tile kernel and the
+// lane-tile kernel (bit-identical results) are timed once on the real factor and the fastest is kept; the losers' plans are released.
 static void tri_autotune_wave(Handle &h) {
-  if (h.n == 0 || !h.wv.ready) { h.tri_mode = 0; return; }
+  if (h.n == 0 || !(h.wv.ready || h.lt.ready)) { h.tri_mode = 0; return; }
   cudaStream_t st = h.stream;
+  const long long launch0 = h.st_launch, pcond0 = h.st_pcond;
   DBuf<double> a, b; a.ensure(h.n); b.ensure(h.n);
   B200_CUDA(cudaMemsetAsync(h.ctrl.p, 0, sizeof(Ctrl), st));
   B200_CUDA(cudaMemsetAsync(a.p, 0, (size_t)h.n * sizeof(double), st));
-  float ms[2] = {0, 0};
-  const int modes[2] = {0, 3};
-  for (int m = 0; m < 2; ++m) {
+  float ms[3] = {0, 0, 0};
+  const int modes[3] = {0, 3, 4};
+  const bool have[3] = {true, h.wv.ready, h.lt.ready};
+  int best = 0, napp = 0;
+  for (int m = 0; m < 3; ++m) {
+    if (!have[m]) continue;
     h.tri_mode = modes[m];
     lu_apply(h, b.p, a.p);
     B200_CUDA(cudaEventRecord(h.evf0, st));
@@ -963,15 +971,20 @@ static void tri_autotune_wave(Handle &h) {
     B200_CUDA(cudaEventRecord(h.evf1, st));
     B200_CUDA(cudaStreamSynchronize(st));
     B200_CUDA(cudaEventElapsedTime(&ms[m], h.evf0, h.evf1));
+    if (ms[m] < ms[best]) best = m;
+    napp += 4;
   }
   B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
   B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "triangular solve: dependency wait timed out while tuning");
-  h.tt_ms_level = ms[0] / 3; h.tt_ms_task = ms[1] / 3;
-  h.tri_mode = ms[1] < ms[0] ? 3 : 0;
-  if (h.tri_mode == 0) wave_release(h);
-  if (getenv("B200_WAVE_DEBUG")) fprintf(stderr, "[wave] autotune: level kernel %.3f ms, wave tiles %.3f ms per application -> mode %d\n", ms[0] / 3, ms[1] / 3, h.tri_mode);
-  h.st_launch -= 28; h.st_pcond -= 8;
+  h.tt_ms_level = ms[0] / 3; h.tt_ms_task = ms[best ? best : (have[2] ? 2 : 1)] / 3;
+  h.tri_mode = modes[best];
+  if (h.tri_mode != 3) wave_release(h);
+  if (h.tri_mode != 4) lane_release(h);
+  if (getenv("B200_WAVE_DEBUG"))
+    fprintf(stderr, "[tri] autotune: level kernel %.3f ms, wave tiles %.3f ms, lane tiles %.3f ms per application -> mode %d\n", ms[0] / 3, ms[1] / 3, ms[2] / 3, h.tri_mode);
+  h.st_launch = launch0; h.st_pcond = pcond0;                      // tuning applications are not the caller's
+  (void)napp;
   a.release(); b.release();
 }
 

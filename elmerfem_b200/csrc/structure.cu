@@ -239,6 +239,7 @@ void ilu_invalidate(Handle &h) {
   tritask_release(h);
   skew_release(h);
   wave_release(h);
+  lane_release(h);
   h.tri_mode = h.tri_mode_cfg;
 }
 
