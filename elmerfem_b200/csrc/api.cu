@@ -62,9 +62,9 @@ static void ensure_runtime(Handle &h) {
   h.wv_blocks_per_sm = env_int("B200_WAVE_BLOCKS_PER_SM", 0);
   h.wv_cfg = env_int("B200_WAVE_CFG", 0);
   h.wv_e = env_int("B200_WAVE_E", 3);
-  h.lt_tc = env_int("B200_LANE_TC", 2);
+  h.lt_tc = env_int("B200_LANE_TC", 1);
   h.lt_warps = env_int("B200_LANE_WARPS", 0);
-  h.lt_depth = env_int("B200_LANE_DEPTH", 0);
+  h.lt_e = env_int("B200_LANE_E", 3);
   h.bl_host = env_int("B200_BICGSTABL_HOST", 0) != 0;
   h.stage_uploads = env_int("B200_STAGE_UPLOADS", 1) != 0;
   h.tt_rows = env_int("B200_TT_ROWS", 0);

@@ -83,6 +83,9 @@ __device__ __forceinline__ bool lt_mbar_test(unsigned bar, unsigned parity) {   
 }
 __device__ __forceinline__ void lt_mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void lt_prefetch_l2(const void *p, unsigned bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void lt_prefetch_l2_if(const void *p, unsigned bytes, bool ok) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q cp.async.bulk.prefetch.L2.global [%0], %1;\n }" ::"l"(p), "r"(bytes), "r"((int)ok) : "memory");
+}
 __device__ __forceinline__ void lt_st_relaxed(double *p, double v) { asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v)); }
 __device__ __forceinline__ double lt_ld_relaxed(const double *p) {
   double v; asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v;
@@ -99,6 +102,8 @@ __device__ __forceinline__ void lt_st_relaxed_if(double *p, double v, bool ok) {
 __device__ __forceinline__ void lt_st_if(double *p, double v, bool ok) {
   asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.global.f64 [%0], %1;\n }" ::"l"(p), "d"(v), "r"((int)ok));
 }
+// High word of the sentinel: no value the sweeps store has it (NaN results are canonicalised before they are stored)
+__device__ __forceinline__ bool lt_is_sentinel(double v) { return __double2hiint(v) == (int)(SENTINEL >> 32); }
 __device__ __forceinline__ long long lt_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // ---- the sweep ------------------------------------------------------------------------------------------------------------------------
@@ -106,57 +111,24 @@ __device__ __forceinline__ long long lt_gtime() { long long t; asm volatile("mov
 //   backward (UPPER = true) : out_i = Dinv_i * (rhs_i - sum_{j>i} U_ij out_j)       (4653-4660)
 // S: this sweep's stream (entries + right-hand sides at pos(sweep coordinates)); Q: result at pos(mirrored sweep coordinates), pre-filled
 // with the sentinel; R2: the backward stream, whose right-hand-side rows the forward sweep fills (nullptr for the backward sweep).
-// D: ring depth (slots per warp).  Block = W consumer warps, one tile each at a time, + one producer warp whose lane w feeds the ring of
-// consumer w with one bulk copy per tile step (full / empty mbarrier pair per slot).  Consumer (block, w) takes tiles block + grid * w,
-// + grid * W, ...: consecutive tiles (neighbouring start levels) sit on different SMs.
-template <bool UPPER, int TC>
+// Block = W warps, one tile each at a time; warp (block, w) takes tiles block + grid * w, + grid * W, ...: consecutive tiles
+// (neighbouring start levels) sit on different SMs.
+// Matrix entries: every lane reads ITS column of the tile step's block straight into registers (coalesced 256-byte warp loads, L1
+// bypassed) LT_LEAD steps before use, from L2, where lane 0 has put the block LT_PF steps earlier with one cp.async.bulk.prefetch.L2
+// per four steps.  [Measured first: a shared-memory ring fed by bulk copies, with a producer warp and a full / empty mbarrier pair per
+// slot -- the consumer's mbarrier test + LDS + arrive cost 265 of 690 cycles per step.]
+constexpr int LT_LEAD = 2;
+template <bool UPPER, int TC, int E, int ABL = 0>   // ABL: timing ablations of profiles/tools/lane_lab.py (wrong results): 1 no entry loads, 2 no row arithmetic, 3 no replay, 4 no stores
 __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restrict__ tile_of, const int *__restrict__ tile_sig, const int *__restrict__ tile_grp,
-                                                 const double *__restrict__ S, double *Q, double *R2, Ctrl *ctrl, int D, long long *trace) {
+                                                 const double *__restrict__ S, double *Q, double *R2, Ctrl *ctrl, long long *trace) {
   if (ctrl->done) return;
   constexpr int NE = UPPER ? 14 : 13, NROW = NE + 1;
   constexpr unsigned SLOT = TC * NROW * 256u;                       // bytes of a tile step
   constexpr long long BLKD = TC * NROW * 32;                        // doubles of a tile step
   constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(128) unsigned char lt_smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = (blockDim.x >> 5) - 1;
-  const unsigned ring0 = lt_smem_u32(lt_smem), full0 = ring0 + (unsigned)(W * D) * SLOT, empty0 = full0 + (unsigned)(W * D) * 8u;
-  if (threadIdx.x == 0) {
-    for (int d = 0; d < W * D; ++d) { lt_mbar_init(full0 + 8u * d, 1); lt_mbar_init(empty0 + 8u * d, 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int NT = g.NT, NR = g.NR, ntiles = g.ntiles, kstep = gridDim.x * W;
-
-  if (wib == W) {
-    // ---------------- producer warp: lane w serves consumer w ----------------
-    bool act = lane < W;
-    int k = blockIdx.x + gridDim.x * lane;
-    if (k >= ntiles) act = false;
-    int tau = 0, slot = 0; unsigned par = 0;
-    const unsigned ring = ring0 + (unsigned)(lane * D) * SLOT, full = full0 + (unsigned)(lane * D) * 8u, empty = empty0 + (unsigned)(lane * D) * 8u;
-    while (__any_sync(FULL, act)) {
-      if (act && lt_mbar_test(empty + 8u * slot, par ^ 1u)) {
-        const double *src = S + ((long long)k * NT + tau) * BLKD;
-        lt_mbar_expect_tx(full + 8u * slot, SLOT);
-        lt_bulk_g2s(ring + (unsigned)slot * SLOT, src, SLOT, full + 8u * slot);
-        if ((tau & 3) == 0) {                                       // L2 prefetch LT_PF steps ahead, into the next tile of this consumer at the end
-          int tp = tau + LT_PF, kp = k;
-          if (tp >= NT) { tp -= NT; kp += kstep; }
-          if (kp < ntiles && tp + 4 <= NT) lt_prefetch_l2(S + ((long long)kp * NT + tp) * BLKD, 4u * SLOT);
-        }
-        if (++slot == D) { slot = 0; par ^= 1u; }
-        if (++tau == NT) { tau = 0; k += kstep; if (k >= ntiles) act = false; }
-      }
-    }
-    return;
-  }
-
-  // ---------------- consumer warp ----------------
-  const unsigned ring = ring0 + (unsigned)(wib * D) * SLOT, full = full0 + (unsigned)(wib * D) * 8u, empty = empty0 + (unsigned)(wib * D) * 8u;
-  const unsigned char *ring_g = lt_smem + (size_t)(wib * D) * SLOT;
-  (void)ring;
-  const long long stride = g.stride();
-  int slot = 0; unsigned par = 0;                                   // ring position / phase of the next step to load
+  constexpr long long STRIDE = TC * 32, RSTR = TC * LT_ROWS_U * 32;   // distance of consecutive rows of a line: result vector, backward stream
   long long spins = 0;
   for (int k = blockIdx.x + gridDim.x * wib; k < ntiles; k += kstep) {
     const int sig = tile_sig[k], C = tile_grp[k];
@@ -170,42 +142,44 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
       nrq[p] = (ln.valid && rep) ? (unsigned)NR : 0u;
       nrs[p] = (ln.valid && !rep) ? (unsigned)NR : 0u;
       const long long q0 = ln.valid ? lt_pos_mirror(g, tile_of, 0, ln.b, ln.c) : 0;
-      qp[p] = Q + q0 + (long long)(2 * lane + 2 * p) * stride;
-      rp[p] = UPPER ? nullptr : R2 + lt_rhs_index(q0, LT_ROWS_U) + (long long)(2 * lane + 2 * p) * (TC * LT_ROWS_U * 32);
+      qp[p] = Q + q0 + (long long)(2 * lane + 2 * p) * STRIDE;
+      rp[p] = UPPER ? nullptr : R2 + lt_rhs_index(q0, LT_ROWS_U) + (long long)(2 * lane + 2 * p) * RSTR;
     }
-    const long long eoff = (long long)LT_E * stride;
-    int ab = -2 * lane;                                             // tau - 2 lane
-    long long tr0 = 0, tr_polls = 0, tr_mbar = 0, tr_poll = 0, tr_first = 0, ph[5] = {0, 0, 0, 0, 0}, pc = 0;
+    int ab = -2 * lane;                                             // t0 - 2 lane (t0: first step of the unrolled group of 8)
+    const double *sp = S + (long long)k * NT * BLKD + lane;          // the lane's column of the current step's block
+    long long tr0 = 0, tr_polls = 0, tr_poll = 0, tr_first = 0, ph[5] = {0, 0, 0, 0, 0}, pc = 0;
     if (trace && lane == 0) tr0 = lt_gtime();
+    if (lane == 0) lt_prefetch_l2(sp, (unsigned)(LT_PF < NT ? LT_PF : NT) * SLOT);
     LaneHist<TC> h;
     lt_hist_clear(h);
-    double Hh[TC + 1][LT_E + 1];
+    double Hh[TC + 1][E + 1];
 #pragma unroll
     for (int p = 0; p <= TC; ++p) {
 #pragma unroll
-      for (int u = 0; u < LT_E; ++u) Hh[p][u] = lt_ld_relaxed_if(qp[p] - (long long)u * stride, (unsigned)(ab + u - 2 * p) < nrq[p]);
-      Hh[p][LT_E] = 0.0;
+      for (int u = 0; u < E; ++u) Hh[p][u] = lt_ld_relaxed_if(qp[p] - u * STRIDE, (unsigned)(ab + u - 2 * p) < nrq[p]);
+      Hh[p][E] = 0.0;
     }
-    double V[TC][NROW];                                             // entries + right-hand side of the step about to run
-    auto load_step = [&](bool ready) {                              // ring slot -> registers, slot handed back to the producer
-      if (!ready) {
-        if (trace) { const long long c0 = clock64(); lt_mbar_wait(full + 8u * slot, par); tr_mbar += clock64() - c0; }
-        else lt_mbar_wait(full + 8u * slot, par);
-      }
-      const double *sl = reinterpret_cast<const double *>(ring_g + (size_t)slot * SLOT) + lane;
+    double V[4][TC][NROW];                                          // entries + right-hand side of steps tau .. tau + LT_LEAD
 #pragma unroll
-      for (int p = 0; p < TC; ++p) {
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int e = 0; e < NROW; ++e) V[p][e] = sl[(p * NROW + e) * 32];
-      }
-      __syncwarp();
-      if (lane == 0) lt_mbar_arrive(empty + 8u * slot);
-      if (++slot == D) { slot = 0; par ^= 1u; }
-    };
-    load_step(false);
+      for (int p = 0; p < TC; ++p)
+#pragma unroll
+        for (int e = 0; e < NROW; ++e) V[q][p][e] = (q < LT_LEAD) ? ld_stream(sp + q * BLKD + (p * NROW + e) * 32) : 0.0;
     auto step = [&](auto Uc, int tau) {
       constexpr int U = decltype(Uc)::value;
       if (trace) pc = clock64();
+      // replayed values of step tau + LT_E.  FIRST: a strong (L1-bypassing) load does not issue before the warp's earlier loads have
+      // returned (measured: 500-900 cycles behind the 15 streaming loads of a step, 70 when it comes before them)
+#pragma unroll
+      for (int p = 0; p <= TC; ++p) Hh[p][(U + E) % (E + 1)] = (ABL == 3) ? 0.0 : lt_ld_relaxed_if(qp[p] - (U + E) * STRIDE, (unsigned)(ab + U + E - 2 * p) < nrq[p]);
+      // entries of step tau + LT_LEAD (the stream is padded by LT_LEAD steps: no guard at the end of the last tile)
+#pragma unroll
+      for (int p = 0; p < TC; ++p)
+#pragma unroll
+        for (int e = 0; e < NROW; ++e) if (ABL != 1) V[(U + LT_LEAD) & 3][p][e] = ld_stream(sp + (U + LT_LEAD) * BLKD + (p * NROW + e) * 32);
+      if ((U & 3) == 0) lt_prefetch_l2_if(sp + (long long)(U + LT_PF) * BLKD, 4u * SLOT, lane == 0 && tau + LT_PF + 4 <= NT);
+      if (trace) { const long long c = clock64(); ph[3] += c - pc; pc = c; }
       // the two shuffles
       LaneMsg<TC> m;
       lt_send<TC, U>(h, m);
@@ -215,46 +189,39 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
       for (int p = 0; p < TC; ++p) m.t[p] = __shfl_up_sync(FULL, m.t[p], 1);
       lt_recv<TC, U>(h, m);
       if (trace) { const long long c = clock64(); ph[0] += c - pc; pc = c; }
-      // replayed values of step tau + LT_E; is the next step's block there?
-#pragma unroll
-      for (int p = 0; p <= TC; ++p) Hh[p][(U + LT_E) & LT_E] = lt_ld_relaxed_if(qp[p] - eoff, (unsigned)(ab + LT_E - 2 * p) < nrq[p]);
-      const bool more = tau + 1 < NT;
-      const bool ready = more && lt_mbar_try(full + 8u * slot, par);
       if (trace) { const long long c = clock64(); ph[1] += c - pc; pc = c; }
       // rows
       double out[TC + 1];
       out[0] = 0.0;
 #pragma unroll
       for (int p = 1; p <= TC; ++p) {
-        double acc = lt_row<UPPER, TC, U>(h, p, V[p - 1], V[p - 1][NE]);
+        double acc = (ABL == 2) ? V[U & 3][p - 1][NE] + V[U & 3][p - 1][0] * h.X[p][(U + 7) & 7] + h.R[p][(U + 7) & 7] + h.T[p - 1][(U + 3) & 7] : lt_row<UPPER, TC, U>(h, p, V[U & 3][p - 1], V[U & 3][p - 1][NE]);
         if (acc != acc) acc = __longlong_as_double((long long)CANON_NAN);
-        const bool active = (unsigned)(ab - 2 * p) < nrs[p];
+        const bool active = (unsigned)(ab + U - 2 * p) < nrs[p];
         if (!active) acc = 0.0;
         out[p] = acc;
-        lt_st_relaxed_if(qp[p], acc, active);
-        if (!UPPER) lt_st_if(rp[p], acc, active);
+        if (ABL != 4) lt_st_relaxed_if(qp[p] - U * STRIDE, acc, active);
+        if (!UPPER && ABL != 4) lt_st_if(rp[p] - U * RSTR, acc, active);
       }
       if (trace) { const long long c = clock64(); ph[2] += c - pc; pc = c; }
-      if (more) load_step(ready);
-      if (trace) { const long long c = clock64(); ph[3] += c - pc; pc = c; }
       // replayed values of this step (requested LT_E steps ago; a producer that is not that far ahead yet is polled)
       double hv[TC + 1];
       bool need = false;
 #pragma unroll
-      for (int p = 0; p <= TC; ++p) { hv[p] = Hh[p][U & LT_E]; need = need || is_sentinel(hv[p]); }
-      if (__any_sync(FULL, need)) {
+      for (int p = 0; p <= TC; ++p) { hv[p] = Hh[p][U % (E + 1)]; need = need || lt_is_sentinel(hv[p]); }
+      if (ABL != 3 && __any_sync(FULL, need)) {
         const long long c0 = trace ? clock64() : 0;
         unsigned tries = 0;
         do {
           need = false;
 #pragma unroll
           for (int p = 0; p <= TC; ++p)
-            if (is_sentinel(hv[p])) { hv[p] = lt_ld_relaxed(qp[p]); need = need || is_sentinel(hv[p]); ++tr_polls; }
+            if (lt_is_sentinel(hv[p])) { hv[p] = lt_ld_relaxed(qp[p] - U * STRIDE); need = need || lt_is_sentinel(hv[p]); ++tr_polls; }
           if (need) {
             if (++spins > LT_SPIN_LIMIT) {
               ctrl->spin_timeout = 1;
 #pragma unroll
-              for (int p = 0; p <= TC; ++p) if (is_sentinel(hv[p])) hv[p] = 0.0;
+              for (int p = 0; p <= TC; ++p) if (lt_is_sentinel(hv[p])) hv[p] = 0.0;
               need = false;
             } else if (++tries > 8) __nanosleep(tries > 64 ? 400 : 100);
           }
@@ -264,12 +231,12 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
 #pragma unroll
       for (int p = 0; p <= TC; ++p) {
         h.X[p][U & 7] = (p == 0 || lane < LT_GH) ? hv[p] : out[p];
-        qp[p] -= stride;
-        if (!UPPER) rp[p] -= TC * LT_ROWS_U * 32;
+        if (U == 7) { qp[p] -= 8 * STRIDE; if (!UPPER) rp[p] -= 8 * RSTR; }
       }
-      ++ab;
+      if (U == 7) { ab += 8; sp += 8 * BLKD; }
       if (trace) { const long long c = clock64(); ph[4] += c - pc; pc = c; }
     };
+    static_assert(8 % (E + 1) == 0, "replay ring must divide the unroll factor");
     for (int t0 = 0; t0 < NT; t0 += 8) {
       step(std::integral_constant<int, 0>{}, t0); step(std::integral_constant<int, 1>{}, t0 + 1);
       step(std::integral_constant<int, 2>{}, t0 + 2); step(std::integral_constant<int, 3>{}, t0 + 3);
@@ -278,7 +245,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
     }
     if (trace) {
       long long *r = trace + ((UPPER ? g.ntiles : 0) + (long long)k) * 16;
-      if (lane == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); r[0] = tr0; r[1] = lt_gtime(); r[3] = smid; r[4] = tr_mbar; r[5] = tr_poll; r[6] = tr_first; for (int q = 0; q < 5; ++q) r[8 + q] = ph[q]; }
+      if (lane == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); r[0] = tr0; r[1] = lt_gtime(); r[3] = smid; r[5] = tr_poll; r[6] = tr_first; for (int q = 0; q < 5; ++q) r[8 + q] = ph[q]; }
       if (tr_polls) atomicAdd((unsigned long long *)(r + 2), (unsigned long long)tr_polls);
     }
   }
@@ -304,7 +271,7 @@ void lane_analyse(Handle &h) {
     if (getenv("B200_WAVE_DEBUG")) fprintf(stderr, "[lane] not usable (%s): level kernel stays\n", why);
     return;
   }
-  const int TC = std::max(1, std::min(4, h.lt_tc));
+  const int TC = std::max(1, std::min(2, h.lt_tc));
   LaneTiles T;
   lt_plan(w.g, sg.NR, sg.NL, sg.NP, TC, T);
   const LaneGeom &g = w.g;
@@ -314,9 +281,10 @@ void lane_analyse(Handle &h) {
   B200_CUDA(cudaMemcpyAsync(w.tile_grp.p, T.grp.data(), T.grp.size() * sizeof(int), cudaMemcpyHostToDevice, h.stream));
   B200_CUDA(cudaStreamSynchronize(h.stream));                      // T goes out of scope
   const size_t nv = (size_t)g.vlen();
-  w.SL.ensure(nv * LT_ROWS_L); w.SU.ensure(nv * LT_ROWS_U);
-  B200_CUDA(cudaMemsetAsync(w.SL.p, 0, nv * LT_ROWS_L * sizeof(double), h.stream));
-  B200_CUDA(cudaMemsetAsync(w.SU.p, 0, nv * LT_ROWS_U * sizeof(double), h.stream));
+  const size_t pad = (size_t)4 * g.TC * 32;                          // the sweeps read LT_LEAD steps past the last tile
+  w.SL.ensure((nv + pad) * LT_ROWS_L); w.SU.ensure((nv + pad) * LT_ROWS_U);
+  B200_CUDA(cudaMemsetAsync(w.SL.p, 0, (nv + pad) * LT_ROWS_L * sizeof(double), h.stream));
+  B200_CUDA(cudaMemsetAsync(w.SU.p, 0, (nv + pad) * LT_ROWS_U * sizeof(double), h.stream));
   w.y.ensure(nv); w.x.ensure(nv);
   k_lane_sentinel<<<NUM_SMS * 8, 256, 0, h.stream>>>((long long)nv, w.x.p);
   B200_CUDA(cudaGetLastError());
@@ -334,39 +302,35 @@ void lane_refresh_values(Handle &h) {
 
 template <bool UPPER, int TC>
 static void lane_launch_tc(Handle &h, const double *S, double *out, double *r2) {
-  const void *kern = (const void *)k_lane<UPPER, TC>;
-  constexpr size_t SLOT = (size_t)TC * (UPPER ? LT_ROWS_U : LT_ROWS_L) * 256;
-  int dev = 0, sms = 0, smem_max = 0;
+  const void *kern = h.lt_e == 1 ? (const void *)k_lane<UPPER, TC, 1> : (h.lt_e == 7 ? (const void *)k_lane<UPPER, TC, 7> : (const void *)k_lane<UPPER, TC, 3>);
+  if (TC == 1) {                                                     // timing ablations (lane_lab.py); results are wrong by construction
+    static const int abl = getenv("B200_LANE_ABL") ? atoi(getenv("B200_LANE_ABL")) : 0;
+    if (abl == 1) kern = (const void *)k_lane<UPPER, 1, 1, 1>;
+    if (abl == 2) kern = (const void *)k_lane<UPPER, 1, 1, 2>;
+    if (abl == 3) kern = (const void *)k_lane<UPPER, 1, 1, 3>;
+    if (abl == 4) kern = (const void *)k_lane<UPPER, 1, 1, 4>;
+  }
+  int dev = 0, sms = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  B200_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int ntiles = h.lt.g.ntiles;
   int W = h.lt_warps > 0 ? h.lt_warps : (ntiles + sms - 1) / sms;   // all tiles co-resident when they fit
-  W = std::max(1, std::min(7, W));                                 // + the producer warp = 256 threads: the whole register file for 8 warps
-  int D = (int)(((size_t)smem_max - 1024) / ((size_t)W * (SLOT + 16)));
-  if (h.lt_depth > 0) D = std::min(D, h.lt_depth);
-  D = std::min(D, 16);
-  B200_REQUIRE(D >= 2, "lane-tile triangular solve: ring does not fit in shared memory");
-  const size_t smem = (size_t)W * D * (SLOT + 16);
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  W = std::max(1, std::min(8, W));
   int per_sm = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (W + 1) * 32, smem));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, 0));
   B200_REQUIRE(per_sm >= 1, "lane-tile triangular solve: kernel does not fit on an SM");
   const int blocks = std::max(1, std::min(sms, (ntiles + W - 1) / W));
   LaneGeom g = h.lt.g; Ctrl *ctrl = h.ctrl.p; long long *trace = h.lt.trace_on ? h.lt.trace.p : nullptr;
   const int *tile_of = h.lt.tile_of.p, *tsig = h.lt.tile_sig.p, *tgrp = h.lt.tile_grp.p;
-  int depth = D;
-  void *argv[] = {(void *)&g, (void *)&tile_of, (void *)&tsig, (void *)&tgrp, (void *)&S, (void *)&out, (void *)&r2, (void *)&ctrl, (void *)&depth, (void *)&trace};
-  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3((W + 1) * 32), argv, smem, h.stream));
+  void *argv[] = {(void *)&g, (void *)&tile_of, (void *)&tsig, (void *)&tgrp, (void *)&S, (void *)&out, (void *)&r2, (void *)&ctrl, (void *)&trace};
+  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(W * 32), argv, 0, h.stream));
 }
 
 template <bool UPPER>
 static void lane_launch(Handle &h, const double *S, double *out, double *r2) {
   switch (h.lt.g.TC) {
-    case 1: lane_launch_tc<UPPER, 1>(h, S, out, r2); break;
-    case 3: lane_launch_tc<UPPER, 3>(h, S, out, r2); break;
-    case 4: lane_launch_tc<UPPER, 4>(h, S, out, r2); break;
-    default: lane_launch_tc<UPPER, 2>(h, S, out, r2); break;
+    case 2: lane_launch_tc<UPPER, 2>(h, S, out, r2); break;
+    default: lane_launch_tc<UPPER, 1>(h, S, out, r2); break;
   }
 }
 

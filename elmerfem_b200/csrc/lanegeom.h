@@ -41,7 +41,6 @@ namespace b200 {
 
 constexpr int LT_BW = 30;      // real lines per tile
 constexpr int LT_GH = 2;       // ghost lanes
-constexpr int LT_E = 3;        // steps a replayed value is requested ahead (ring of LT_E + 1)
 constexpr int LT_ROWS_L = 14, LT_ROWS_U = 15;   // rows of 32 doubles per (tile step, plane slot) in the forward / backward stream
 
 struct LaneGeom {

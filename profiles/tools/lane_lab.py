@@ -9,7 +9,7 @@ dims = tuple(int(a) for a in sys.argv[1:4])
 for kv in sys.argv[4:]:
     k, v = kv.split("="); os.environ[k] = v
 os.environ.setdefault("B200_TRI_MODE", "4")
-trace = os.path.join(tempfile.gettempdir(), "lane_trace.txt")
+trace = os.environ.get("LANE_LAB_TRACE", os.path.join(tempfile.gettempdir(), "lane_trace.txt"))
 os.environ["B200_LANE_TRACE"] = trace
 import elmerfem_b200 as B
 from elmerfem_b200 import synth
@@ -21,6 +21,7 @@ for _ in range(4):
 ms = M.time_lu(5)
 print("dims", dims, "n", A.n, " ".join(sys.argv[4:]), " lu %.3f ms per application, tri_mode %d" % (ms, M.stats()["tri_mode"]), flush=True)
 M.close()
+STEPS = (dims[0] + 1 + 62 + 2 * int(os.environ.get("B200_LANE_TC", "1")) + 7) // 8 * 8
 if os.path.exists(trace):
     T = np.loadtxt(trace, ndmin=2)
     for sw in (0, 1):
@@ -39,5 +40,8 @@ if os.path.exists(trace):
         if T.shape[1] >= 16:
             print("   cycles per tile (median) in: shuffles %.0fk, requests + ring test %.0fk, rows + stores %.0fk, ring -> registers %.0fk, replay resolve + update %.0fk" %
                   tuple(np.median(t[:, 11 + q]) / 1e3 for q in range(5)))
+            for i in (0, nt // 2):
+                print("   tile %d: life %.1f us, cycles/step: shuffles %.0f requests %.0f rows %.0f entry loads %.0f resolve %.0f (polls %d)" %
+                      ((t[i, 1], (t[i, 5] - t[i, 4]) / 1e3) + tuple(t[i, 11 + q] / STEPS for q in range(5)) + (t[i, 6],)))
         idx = np.linspace(0, nt - 1, 12).astype(int)
         print("   tile: start/first/end us:", " ".join("%d:%.0f/%.0f/%.0f" % (t[i, 1], t[i, 4] / 1e3, t[i, 10] / 1e3, t[i, 5] / 1e3) for i in idx))

@@ -1,5 +1,5 @@
 """Lane-tile triangular solve (csrc/lane.cu, B200_TRI_MODE=4) on the GPU through the C ABI: bit-identical to the oracle's CRS_LUSolve on
-grids that exercise single tiles, many tiles, partial strips, several tiles per warp and every plane count per lane; BiCGStab + ILU0 on top
+grids that exercise single tiles, many tiles, partial strips, several tiles per warp and one and two planes per lane; BiCGStab + ILU0 on top
 of it takes the oracle's iteration count; anything that is not the 27-point grid stencil falls back to the level kernel.  CPU
 counterpart: tests/test_lane_plan.py."""
 import numpy as np
@@ -15,7 +15,7 @@ def _case(oracle, dims):
     return A, b
 
 
-@pytest.mark.parametrize("tc", [1, 2, 3, 4])
+@pytest.mark.parametrize("tc", [1, 2])
 @pytest.mark.parametrize("dims", [(6, 6, 6), (9, 4, 5), (40, 40, 3), (33, 70, 12), (50, 20, 40)])
 def test_lane_mode_bit_exact(oracle, b200, monkeypatch, dims, tc):
     monkeypatch.setenv("B200_TRI_MODE", "4")
@@ -39,13 +39,13 @@ def test_lane_mode_bit_exact(oracle, b200, monkeypatch, dims, tc):
         M.close()
 
 
-@pytest.mark.parametrize("warps,depth", [(1, 2), (3, 3), (8, 0)])
+@pytest.mark.parametrize("warps,depth", [(1, 1), (3, 3), (8, 7)])
 def test_lane_mode_few_warps_many_rounds(oracle, b200, monkeypatch, warps, depth):
-    """More tiles than co-resident warps (static round-robin over start levels) and the smallest ring."""
+    """More tiles than co-resident warps (static round-robin over start levels) and every request lead."""
     monkeypatch.setenv("B200_TRI_MODE", "4")
     monkeypatch.setenv("B200_LANE_TC", "1")
     monkeypatch.setenv("B200_LANE_WARPS", str(warps))
-    monkeypatch.setenv("B200_LANE_DEPTH", str(depth))
+    monkeypatch.setenv("B200_LANE_E", str(depth))
     A, b = _case(oracle, (20, 70, 90))
     M = b200.Matrix()
     try:
