@@ -64,7 +64,7 @@ static void ensure_runtime(Handle &h) {
   h.wv_e = env_int("B200_WAVE_E", 3);
   h.lt_tc = env_int("B200_LANE_TC", 1);
   h.lt_warps = env_int("B200_LANE_WARPS", 0);
-  h.lt_e = env_int("B200_LANE_E", 3);
+  h.lt_e = env_int("B200_LANE_E", 1);
   h.bl_host = env_int("B200_BICGSTABL_HOST", 0) != 0;
   h.stage_uploads = env_int("B200_STAGE_UPLOADS", 1) != 0;
   h.tt_rows = env_int("B200_TT_ROWS", 0);

@@ -168,7 +168,7 @@ struct Handle {
   // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
   SkewPlan sk; int sk_blocks_per_sm = 0, sk_cfg = 0, sk_wpb = 0;
   WavePlan wv; int wv_blocks_per_sm = 0, wv_cfg = 0, wv_e = 3;
-  LanePlan lt; int lt_tc = 1, lt_warps = 0, lt_e = 3;
+  LanePlan lt; int lt_tc = 1, lt_warps = 0, lt_e = 1;
   void *stage_buf[2] = {nullptr, nullptr}; cudaEvent_t stage_ev[2] = {nullptr, nullptr}; bool stage_uploads = true;   // pinned bounce buffers of b200_set_values
   bool mv_honor_skip = false;                     // partitioned SpMVs queued inside a conditional section (Ctrl::done == 2) return at once
   bool bl_host = false;                           // B200_BICGSTABL_HOST=1: host-driven BiCGStab(l) (the round-1 driver) instead of the device-resident one
