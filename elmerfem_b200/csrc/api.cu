@@ -501,6 +501,16 @@ int b200_set_ilu_order(void **handle, const int *order) {
     ilu_invalidate(h);
   });
 }
+int b200_set_symmetric_ilu(void **handle, const int *flag) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(flag, "b200_set_symmetric_ilu: null argument");
+    const bool f = *flag != 0;
+    if (f == h.cholesky) return;
+    h.cholesky = f;
+    ilu_invalidate(h);
+  });
+}
 int b200_set_bilu_blocks(void **handle, const int *blocks) {
   return guarded([&] {
     Handle &h = H(handle);

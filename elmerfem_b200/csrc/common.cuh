@@ -165,6 +165,10 @@ struct Handle {
   DBuf<int> tri_counters; int tri_maxw = 0, tri_lookahead = 2; unsigned tri_gate_sleep = 100, tri_spin_sleep = 0;
   DBuf<int> d_lvlcnt_f, d_lvlcnt_b;              // slices per level (forward / backward)
   DBuf<int> d_urhs; DBuf<double> d_yl, d_xu;     // backward rhs map (U slot -> L slot); slot-ordered solve vectors
+  // incomplete Cholesky ('Linear System Symmetric ILU', A % Cholesky): the factor's lower part by columns (rows descending: the order
+  // in which CRS_LUSolve's column-oriented backward loop updates an unknown) and the level plan of that sweep
+  bool cholesky = false, ch_ready = false; int ch_nlev = 0, ch_nslices = 0;
+  DBuf<int> ch_ptr, ch_row, ch_pos, ch_perm, ch_gate, ch_lvlcnt, ch_counters; DBuf<double> ch_y, ch_x;
   // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
   SkewPlan sk; int sk_blocks_per_sm = 0, sk_cfg = 0, sk_wpb = 0;
   WavePlan wv; int wv_blocks_per_sm = 0, wv_cfg = 0, wv_e = 3;
@@ -302,6 +306,8 @@ void wave_analyse(Handle &h);                          // wave-tile plan (host d
 void wave_refresh_values(Handle &h);
 void wave_release(Handle &h);
 void lu_apply_wave(Handle &h, double *u, const double *v);
+void ichol_analyse(Handle &h);                         // column lists + backward level plan of the incomplete Cholesky solve
+void ichol_release(Handle &h);
 void lane_analyse(Handle &h);                          // lane-tile plan (same detection; no-op when it does not apply)
 void lane_refresh_values(Handle &h);
 void lane_release(Handle &h);

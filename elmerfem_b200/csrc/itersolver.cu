@@ -85,6 +85,7 @@ struct SolvePlan {
   int ipar[50] = {0}; double dpar[10] = {0};
   int ilu_order = -1;       // >= 0 when an ILU(n) / BILU preconditioner is selected
   int bilu_blocks = 0;      // > 1: ILU(0) of the block-diagonal part with that many blocks
+  bool cholesky = false;    // Linear System Symmetric ILU
 };
 
 static void plan_from_sif(const Sif &P, int n, int ndeg, SolvePlan &pl) {
@@ -170,7 +171,7 @@ static void plan_from_sif(const Sif &P, int n, int ndeg, SolvePlan &pl) {
     throw Declined{"left-oriented preconditioning"};
   std::string pcs = P.str("Linear System Preconditioning", "none");
   int &pc = pl.pc;
-  if (P.logical("Linear System Symmetric ILU")) throw Declined{"'Linear System Symmetric ILU' (incomplete Cholesky)"};
+  pl.cholesky = P.logical("Linear System Symmetric ILU");             // 526: A % Cholesky
   if (pcs == "none") pc = B200_PRECOND_NONE;
   else if (pcs == "diagonal") pc = B200_PRECOND_DIAGONAL;
   else if (pcs == "ilut") throw Declined{"ILUT"};
@@ -234,8 +235,8 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     plan_from_sif(P, h.n, h.ndeg, pl);
     int *ipar = pl.ipar; double *dpar = pl.dpar;
     int method = pl.method, pc = pl.pc;
-    if (pl.ilu_order >= 0 && (pl.ilu_order != h.ilu_order || pl.bilu_blocks != h.bilu_blocks)) {
-      B200_CUDA(cudaSetDevice(h.device)); h.ilu_order = pl.ilu_order; h.bilu_blocks = pl.bilu_blocks; ilu_invalidate(h);
+    if (pl.ilu_order >= 0 && (pl.ilu_order != h.ilu_order || pl.bilu_blocks != h.bilu_blocks || pl.cholesky != h.cholesky)) {
+      B200_CUDA(cudaSetDevice(h.device)); h.ilu_order = pl.ilu_order; h.bilu_blocks = pl.bilu_blocks; h.cholesky = pl.cholesky; ilu_invalidate(h);
     }
     // ---- recompute policy (579-587): factorise when no factor exists or Refactorize and SolveCount mod n == 0
     int sc = solve_count ? *solve_count : 0;

@@ -116,6 +116,76 @@ __global__ void __launch_bounds__(256) k_ilu0_factor(int nslots, const int *__re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Incomplete Cholesky, CRS_IncompleteLU with A % Cholesky (CRSMatrix.F90:3539-3602; 'Linear System Symmetric ILU').  One warp per row in
+// forward-level order, the lower part of the row (T, then S) staged in shared memory.  For the m-th lower entry j, in column order:
+//   S(j) = (T(j) - sum_l S(k_l) L(j, k_l)) * Linv(j, j)  over the whole lower part of row j, S(k) = 0 outside row i's pattern,
+//   S(i) = S(i) - S(j)^2;                        finally Linv(i, i) = 1 / sqrt(S(i))   (1 when S(i) <= AEPS).
+// The lanes form the products S(k_l) L(j, k_l) of 32 entries of row j at once (one rounding each, as the reference); the subtractions
+// run in the reference's order from shuffled products.  Only the lower part and the diagonal are written (upper part: 0).
+__global__ void __launch_bounds__(256) k_ichol_factor(int nslots, const int *__restrict__ perm, const int *__restrict__ rows, const int *__restrict__ cols,
+                                                       const int *__restrict__ diag, const double *__restrict__ Avals, const int *__restrict__ src, double *LU,
+                                                       int *rowdone, Ctrl *ctrl) {
+  __shared__ double s_val[8][ILU_MAXROW];
+  __shared__ int s_col[8][ILU_MAXROW];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slot = gwarp; slot < nslots; slot += nwarps) {
+    const int r = perm[slot];
+    if (r < 0) continue;
+    const int rs = rows[r], re = rows[r + 1], d = diag[r], nlow = d - rs;       // nlow <= ILU_MAXROW - 1 (checked by the host)
+    for (int t = lane; t <= nlow; t += 32) {                                    // 3553-3556, 3566: T, on the factor's pattern
+      double a;
+      if (src) { const int q = src[rs + t]; a = q >= 0 ? Avals[q] : 0.0; } else a = Avals[rs + t];
+      s_val[wib][t] = a; s_col[wib][t] = cols[rs + t];
+    }
+    __syncwarp();
+    long long spins = 0;
+    for (int t = lane; t < nlow; t += 32) {
+      const int k = s_col[wib][t];
+      while (ld_acquire(rowdone + k) == 0) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        __nanosleep(40);
+      }
+    }
+    __syncwarp();
+    double Si = s_val[wib][nlow];
+    for (int m = 0; m < nlow; ++m) {                                            // 3567-3576
+      const int j = s_col[wib][m], jr = rows[j], jd = diag[j], jl = jd - jr;
+      double acc = s_val[wib][m];
+      for (int c0 = 0; c0 < jl; c0 += 32) {
+        const int l = c0 + lane;
+        double prod = 0.0;
+        if (l < jl) {
+          const int k = cols[jr + l];
+          const double Lv = __ldcg(LU + jr + l);
+          int lo = 0, hi = m;                                                   // columns < j of row i sit left of position m
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_col[wib][mid] < k) lo = mid + 1; else hi = mid; }
+          const double Sk = (lo < m && s_col[wib][lo] == k) ? s_val[wib][lo] : 0.0;
+          prod = __dmul_rn(Sk, Lv);
+        }
+        const int cnt = jl - c0 < 32 ? jl - c0 : 32;
+        for (int t = 0; t < cnt; ++t) acc = __dsub_rn(acc, __shfl_sync(0xffffffffu, prod, t));
+      }
+      acc = __dmul_rn(acc, __ldcg(LU + jd));
+      __syncwarp();
+      if (lane == 0) s_val[wib][m] = acc;
+      __syncwarp();
+      Si = __dsub_rn(Si, __dmul_rn(acc, acc));
+    }
+    if (Si <= AEPS) Si = 1.0;                                                   // 3578-3587
+    else Si = __ddiv_rn(1.0, __dsqrt_rn(Si));
+    for (int t = lane; t < nlow; t += 32) __stcg(LU + rs + t, s_val[wib][t]);   // 3596-3601
+    if (lane == 0) __stcg(LU + d, Si);
+    for (int t = d + 1 + lane; t < re; t += 32) __stcg(LU + t, 0.0);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(rowdone + r, 1);
+  }
+}
+
+
 // ---- position map: the symbolic half of the elimination, once per structure -----------------------------------------------------------
 // For row i, its m-th lower entry (pivot row k) and the u-th upper entry (column j) of row k: the position of column j in row i, or 255.
 // k_ilu0_factor finds that position with a binary search over the staged row on every update and every factorisation (85 instructions
@@ -243,9 +313,43 @@ static void launch_coresident(const void *kernel, int blocks, int threads, cudaS
 static void tri_autotune(Handle &h);
 static void tri_autotune_wave(Handle &h);
 
+// CRS_IncompleteLU with A % Cholesky set: the factor lives in the lower part + diagonal of d_ilu (same pattern as the LU factor)
+static void ichol_factor(Handle &h) {
+  ichol_analyse(h);
+  cudaStream_t st = h.stream;
+  h.d_ilu.ensure(h.lnnz());
+  B200_CUDA(cudaEventRecord(h.evf0, st));
+  if (h.n > 0) {
+    const std::vector<int> &R = h.lrows(), &Dg = h.ldiag();
+    int maxlow = 0;
+    for (int i = 0; i < h.n; ++i) maxlow = std::max(maxlow, Dg[i] - R[i]);
+    B200_REQUIRE(maxlow + 1 <= ILU_MAXROW, "incomplete Cholesky: a row has more than 127 entries left of the diagonal");
+    B200_CUDA(cudaMemsetAsync(h.d_rowdone.p, 0, (size_t)h.n * sizeof(int), st));
+    B200_CUDA(cudaMemsetAsync(&h.ctrl.p->spin_timeout, 0, sizeof(int), st));
+    const double *src = h.have_prec ? h.d_prec.p : h.d_vals.p;        // CRSMatrix.F90:3480-3484
+    static int grid = 0;
+    if (!grid) grid = persistent_blocks((const void *)k_ichol_factor, 256, 0);
+    const int blocks = std::max(1, std::min(grid, (h.L.nslots + 7) / 8));
+    launch_coresident((const void *)k_ichol_factor, blocks, 256, st, h.L.nslots, (const int *)h.L.perm.p, h.d_lrows(), h.d_lcols(), h.d_ldiag(), src,
+                      (const int *)(h.ilu_sep() ? h.dl_src.p : nullptr), h.d_ilu.p, h.d_rowdone.p, h.ctrl.p);
+    B200_CUDA(cudaGetLastError());
+  }
+  B200_CUDA(cudaEventRecord(h.evf1, st));
+  B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  float ms = 0; B200_CUDA(cudaEventElapsedTime(&ms, h.evf0, h.evf1));
+  h.st_factor_ms = ms;
+  B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "incomplete Cholesky factorisation: dependency wait timed out");
+  h.ilu_valid = true; h.ilu_exists = true;
+  h.st_factor_launch = h.n > 0 ? 1 : 0;
+  h.tri_mode = 0;                                                   // the Cholesky sweeps are the only solve path of this factor
+}
+
 void ilu0_factor(Handle &h) {
   B200_REQUIRE(h.have_vals, "ILU0 requested before b200_set_values");
+  if (h.cholesky) { ichol_factor(h); return; }
   tri_analyse(h);
+
   if (h.tri_mode == 2) skew_analyse(h);
   else if (h.tri_mode == 3) wave_analyse(h);
   else if (h.tri_mode == 4) lane_analyse(h);
@@ -862,6 +966,81 @@ __global__ void k_tri_prepare(int na, double *a, int nb, double *b, int *counter
   for (int i = i0; i < ncounters; i += st) counters[i * 32] = 0;
 }
 
+// Incomplete Cholesky solve, CRS_LUSolve with A % Cholesky (CRSMatrix.F90:4618-4638), as two wavefront sweeps over natural-order vectors
+// (k_sgs_sweep's scheme: rows in dependency-level order, operands polled from the sentinel-filled result vector, one lane per row so that
+// every sum runs in the reference's order with separate roundings).
+//   forward  (4621-4628): z_i = (b_i - sum_{j<i} L_ij z_j) * Linv_ii, columns ascending;
+//   backward (4632-4638): x_c = (z_c - sum_{i>c} L_ic x_i) * Linv_cc, rows i DESCENDING (the order in which the column-oriented loop
+//                         reaches b(c)); the lists come from ichol_analyse.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256, 2) k_ichol_sweep(int nslices, const int *__restrict__ perm, const int *__restrict__ slice_level,
+                                                         const int *__restrict__ lvl_slices, int *lvl_done, int lookahead, unsigned gate_sleep,
+                                                         const int *__restrict__ ptr, const int *__restrict__ idx, const int *__restrict__ pos,
+                                                         const int *__restrict__ diag, const double *__restrict__ LU, const double *__restrict__ rhs,
+                                                         double *out, double *copy, Ctrl *ctrl) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slice = gwarp; slice < nslices; slice += nwarps) {
+    const int r = perm[slice * 32 + lane];
+    long long spins = 0;
+    const int wl = slice_level[slice] - lookahead;
+    if (lane == 0 && wl >= 0) {
+      const int need = lvl_slices[wl];
+      while (ld_relaxed_i(lvl_done + wl * 32) < need) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        if (gate_sleep) __nanosleep(gate_sleep);
+      }
+    }
+    __syncwarp();
+    if (r >= 0) {
+      double s = rhs[r];
+      const int p0 = BACKWARD ? ptr[r] : ptr[r], p1 = BACKWARD ? ptr[r + 1] : diag[r];     // forward: ptr = Rows, the strict lower part
+      for (int p = p0; p < p1; ++p) {
+        const int c = idx[p];
+        double xv = ld_relaxed(out + c);
+        while (is_sentinel(xv)) {
+          if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+          xv = ld_relaxed(out + c);
+        }
+        s = nfms(s, LU[BACKWARD ? pos[p] : p], xv);
+      }
+      double xn = __dmul_rn(s, LU[diag[r]]);
+      if (xn != xn) xn = __longlong_as_double((long long)CANON_NAN);
+      st_relaxed(out + r, xn);
+      if (copy) copy[r] = xn;
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(lvl_done + slice_level[slice] * 32, 1);
+  }
+}
+__global__ void k_ichol_prepare(int n, double *a, double *b2, int *counters, int ncounters) {
+  const double sent = __longlong_as_double((long long)SENTINEL);
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
+  for (int i = i0; i < n; i += st) { a[i] = sent; b2[i] = sent; }
+  for (int i = i0; i < ncounters; i += st) counters[i * 32] = 0;
+}
+static void lu_apply_ichol(Handle &h, double *u, const double *v) {
+  B200_REQUIRE(h.ch_ready, "incomplete Cholesky solve without a plan");
+  cudaStream_t st = h.stream;
+  static int grid_f = 0, grid_b = 0;
+  if (!grid_f) {
+    grid_f = persistent_blocks((const void *)k_ichol_sweep<false>, 256, 0);
+    grid_b = persistent_blocks((const void *)k_ichol_sweep<true>, 256, 0);
+  }
+  k_ichol_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, st>>>(h.n, h.ch_y.p, h.ch_x.p, h.ch_counters.p, h.nlev_f + h.ch_nlev + 2);
+  const int la = h.tri_lookahead; const unsigned gs = h.tri_gate_sleep;
+  const int bf = std::max(1, std::min(grid_f, (h.L.nslices + 7) / 8)), bb = std::max(1, std::min(grid_b, (h.ch_nslices + 7) / 8));
+  launch_coresident((const void *)k_ichol_sweep<false>, bf, 256, st, h.L.nslices, (const int *)h.L.perm.p, (const int *)h.L.gate.p, (const int *)h.d_lvlcnt_f.p,
+                    h.ch_counters.p, la, gs, h.d_lrows(), h.d_lcols(), (const int *)nullptr, h.d_ldiag(), (const double *)h.d_ilu.p, v, h.ch_y.p,
+                    (double *)nullptr, h.ctrl.p);
+  launch_coresident((const void *)k_ichol_sweep<true>, bb, 256, st, h.ch_nslices, (const int *)h.ch_perm.p, (const int *)h.ch_gate.p, (const int *)h.ch_lvlcnt.p,
+                    h.ch_counters.p + (size_t)(h.nlev_f + 1) * 32, la, gs, (const int *)h.ch_ptr.p, (const int *)h.ch_row.p, (const int *)h.ch_pos.p, h.d_ldiag(),
+                    (const double *)h.d_ilu.p, (const double *)h.ch_y.p, h.ch_x.p, u, h.ctrl.p);
+  B200_CUDA(cudaGetLastError());
+  h.st_launch += 3; h.st_pcond++;
+}
+
 static void lu_launch_kernels(Handle &h, const void *kl, const void *ku, double *u, const double *v) {
   cudaStream_t st = h.stream;
   if (!h.grid_tri_l) {
@@ -881,6 +1060,7 @@ static void lu_launch_kernels(Handle &h, const void *kl, const void *ku, double 
 void lu_apply(Handle &h, double *u, const double *v) {
   B200_REQUIRE(h.ilu_valid, "LU preconditioner applied without a valid ILU0 factor");
   if (h.n == 0) return;
+  if (h.cholesky) { lu_apply_ichol(h, u, v); return; }
   if (h.tri_mode == 2 && h.sk.ready) { lu_apply_skew(h, u, v); return; }   // experimental, opt-in; not ready -> level kernel
   if (h.tri_mode == 3 && h.wv.ready) { lu_apply_wave(h, u, v); return; }   // grid stencils; not detected -> level kernel
   if (h.tri_mode == 4 && h.lt.ready) { lu_apply_lane(h, u, v); return; }   // grid stencils; not detected -> level kernel

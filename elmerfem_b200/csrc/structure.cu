@@ -240,7 +240,52 @@ void ilu_invalidate(Handle &h) {
   skew_release(h);
   wave_release(h);
   lane_release(h);
+  ichol_release(h);
   h.tri_mode = h.tri_mode_cfg;
+}
+
+// Incomplete Cholesky solve (CRSMatrix.F90:4618-4638).  The backward loop is column-oriented: row i, taken from n down to 1, scales
+// b(i) and subtracts L(i, c) b(i) from every b(c) of its lower part.  Unknown c therefore receives its updates from the rows i > c that
+// hold column c, in DESCENDING i, before it is scaled.  ch_ptr / ch_row / ch_pos list exactly that per column (the gather form of the
+// same sums, same order); the dependency levels of the sweep follow from the lists.  Needs the row-level forward plan.
+void ichol_release(Handle &h) {
+  h.ch_ptr.release(); h.ch_row.release(); h.ch_pos.release(); h.ch_perm.release(); h.ch_gate.release(); h.ch_lvlcnt.release(); h.ch_counters.release();
+  h.ch_y.release(); h.ch_x.release(); h.ch_ready = false;
+}
+void ichol_analyse(Handle &h) {
+  if (h.ch_ready) return;
+  if (h.tri_node) { h.tri_node_off = true; ilu_invalidate(h); }     // the sweeps poll per row: row-level layout only
+  tri_analyse(h);
+  const int n = h.n;
+  const std::vector<int> &rows = h.lrows(), &cols = h.lcols(), &diag = h.ldiag();
+  std::vector<int> ptr((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) for (int p = rows[i]; p < diag[i]; ++p) ptr[cols[p] + 1]++;
+  for (int c = 0; c < n; ++c) ptr[c + 1] += ptr[c];
+  std::vector<int> row(std::max(ptr[n], 1)), pos(std::max(ptr[n], 1)), fill(ptr.begin(), ptr.end() - 1);
+  for (int i = n - 1; i >= 0; --i) for (int p = rows[i]; p < diag[i]; ++p) { const int q = fill[cols[p]]++; row[q] = i; pos[q] = p; }   // rows descending
+  std::vector<int> lv(n, 0); int nlev = 0;
+  for (int c = n - 1; c >= 0; --c) {
+    int l = 0;
+    for (int q = ptr[c]; q < ptr[c + 1]; ++q) l = std::max(l, lv[row[q]] + 1);
+    lv[c] = l; nlev = std::max(nlev, l + 1);
+  }
+  if (n == 0) nlev = 0;
+  std::vector<int> perm, gate, cnt; int nslots = 0;
+  level_layout(n, lv, nlev, perm, nslots, true, gate, cnt);
+  h.ch_nlev = nlev; h.ch_nslices = nslots / 32;
+  h.ch_ptr.ensure(ptr.size()); h.ch_row.ensure(row.size()); h.ch_pos.ensure(pos.size());
+  h.ch_perm.ensure(std::max(nslots, 1)); h.ch_gate.ensure(std::max<size_t>(gate.size(), 1)); h.ch_lvlcnt.ensure(std::max<size_t>(cnt.size(), 1));
+  h.ch_counters.ensure(((size_t)h.nlev_f + nlev + 2) * 32);
+  h.ch_y.ensure(n); h.ch_x.ensure(n);
+  cudaStream_t st = h.stream;
+  B200_CUDA(cudaMemcpyAsync(h.ch_ptr.p, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(h.ch_row.p, row.data(), row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(h.ch_pos.p, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (nslots) B200_CUDA(cudaMemcpyAsync(h.ch_perm.p, perm.data(), (size_t)nslots * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!gate.empty()) B200_CUDA(cudaMemcpyAsync(h.ch_gate.p, gate.data(), gate.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!cnt.empty()) B200_CUDA(cudaMemcpyAsync(h.ch_lvlcnt.p, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  h.ch_ready = true;
 }
 
 void tri_analyse(Handle &h) {

@@ -106,6 +106,11 @@ int b200_factorize(void **handle);                 /* ILU(order) of PrecValues (
  * factorises on the matrix pattern; n > 0 first adds n rounds of first-order fill (InitializeILU1, 3664-3795).
  * Changing the order drops the current factor. */
 int b200_set_ilu_order(void **handle, const int *order);
+/* A % Cholesky ("Linear System Symmetric ILU", IterSolve.F90:526): the incomplete factorisation and its solve take the Cholesky branches
+ * of CRS_IncompleteLU (fem/src/CRSMatrix.F90:3539-3602: L L^T on the lower part of the ILU(n) pattern, diagonal stored as 1/sqrt) and of
+ * CRS_LUSolve (4618-4638: row-oriented forward sweep, column-oriented backward sweep).  b200_get_ilu_values then returns the lower part
+ * and the diagonal (the reference leaves the upper part of ILUValues unwritten; here it is 0).  Changing the flag drops the factor. */
+int b200_set_symmetric_ilu(void **handle, const int *flag);
 /* BILU ("Linear System Preconditioning = BILU"): the incomplete factorisation acts on the block-diagonal part of the matrix,
  * entries with MOD(i,blocks) == MOD(j,blocks) (CRS_BlockDiagonal, fem/src/CRSMatrix.F90:2382-2420; IterSolve.F90:745-765), blocks =
  * Solver % Variable % Dofs.  blocks <= 1 switches it off.  Order 0 only through the keyword front-end (see b200_itersolver). */

@@ -369,7 +369,46 @@ int crs_ilun_factor(int N, const int *Rows, const int *Cols, const double *Value
   return 1;
 }
 
-// CRSMatrix.F90:4590-4663 CRS_LUSolve, non-Cholesky branch (4642-4660); diagonal fallback 4610-4616.
+// CRSMatrix.F90:3539-3602: the Cholesky branch of CRS_IncompleteLU (A % Cholesky, set from 'Linear System Symmetric ILU',
+// IterSolve.F90:526).  Row by row: T = row i of the matrix (lower part and diagonal) in full form; for every lower entry j of the ILU
+// pattern, in column order, S(j) = (T(j) - sum_l S(k_l) L(j, k_l)) * L(j, j)^-1 over the WHOLE lower part of row j (S is zero outside
+// row i's pattern), and S(i) = T(i) - sum_j S(j)^2; the diagonal is stored as 1 / sqrt(S(i)) (1 when S(i) <= AEPS).  Only the lower
+// part and the diagonal of ILUValues are written (the reference leaves the rest of the freshly allocated array untouched; here 0).
+int crs_ichol_factor(int N, const int *Rows, const int *Cols, const int *Diag, const double *Values, const int *ILURows, const int *ILUCols,
+                     const int *ILUDiag, double *ILUValues) {
+  if (N == 0) return 1;
+  std::vector<double> S(N + 1, 0.0), T(N + 1, 0.0);
+  for (long q = 0; q < (long)ILURows[N] - 1; ++q) ILUValues[q] = 0.0;
+  for (int i = 1; i <= N; ++i) {
+    for (int k = Rows[i - 1]; k <= Diag[i - 1]; ++k) T[Cols[k - 1]] = Values[k - 1];                     // 3553-3556
+    for (int k = ILURows[i - 1]; k <= ILUDiag[i - 1]; ++k) S[ILUCols[k - 1]] = ILUValues[k - 1];          // 3558-3562
+    S[i] = T[i];                                                                                          // 3566
+    for (int m = ILURows[i - 1]; m <= ILUDiag[i - 1] - 1; ++m) {                                          // 3567-3576
+      const int j = ILUCols[m - 1];
+      S[j] = T[j];
+      for (int l = ILURows[j - 1]; l <= ILUDiag[j - 1] - 1; ++l) {
+        const int k = ILUCols[l - 1];
+        S[j] = S[j] - S[k] * ILUValues[l - 1];
+      }
+      S[j] = S[j] * ILUValues[ILUDiag[j - 1] - 1];
+      S[i] = S[i] - S[j] * S[j];
+    }
+    if (S[i] <= AEPS) S[i] = 1.0;                                                                         // 3578-3587
+    else S[i] = 1.0 / std::sqrt(S[i]);
+    for (int k = Rows[i - 1]; k <= Diag[i - 1]; ++k) T[Cols[k - 1]] = 0.0;                                // 3591-3594
+    for (int k = ILURows[i - 1]; k <= ILUDiag[i - 1]; ++k) {                                              // 3596-3601
+      const int j = ILUCols[k - 1];
+      ILUValues[k - 1] = S[j];
+      S[j] = 0.0;
+    }
+  }
+  return 1;
+}
+
+// A % Cholesky of the matrix the callbacks below work on ('Linear System Symmetric ILU')
+static int g_cholesky = 0;
+
+// CRSMatrix.F90:4590-4663 CRS_LUSolve: Cholesky branch 4618-4638, LU branch 4642-4660; diagonal fallback 4610-4616.
 void crs_lusolve(const Matrix &A, double *b) {
   const int n = A.n;
   const int *Rows = A.ILURows ? A.ILURows : A.Rows, *Cols = A.ILUCols ? A.ILUCols : A.Cols, *Diag = A.ILUDiag ? A.ILUDiag : A.Diag;
@@ -379,6 +418,18 @@ void crs_lusolve(const Matrix &A, double *b) {
     for (int i = 1; i <= n; ++i) {
       double s = A.Values[A.Diag[i - 1] - 1];
       if (s != 0) B[i] = B[i] / s;
+    }
+    return;
+  }
+  if (g_cholesky) {
+    for (int i = 1; i <= n; ++i) {                                   // 4621-4628: L z = b
+      double s = B[i];
+      for (int j = Rows[i - 1]; j <= Diag[i - 1] - 1; ++j) s = s - Values[j - 1] * B[Cols[j - 1]];
+      B[i] = s * Values[Diag[i - 1] - 1];
+    }
+    for (int i = n; i >= 1; --i) {                                   // 4632-4638: L^T x = z, column-oriented
+      B[i] = B[i] * Values[Diag[i - 1] - 1];
+      for (int j = Rows[i - 1]; j <= Diag[i - 1] - 1; ++j) B[Cols[j - 1]] = B[Cols[j - 1]] - Values[j - 1] * B[i];
     }
     return;
   }
@@ -1490,6 +1541,11 @@ void orc_crs_diag_precond(int n, const int *rows, const int *cols, const int *di
 int orc_crs_ilu0(int n, const int *rows, const int *cols, const int *diag, const double *vals,
                  double *iluvals) {
   return crs_ilu0(n, rows, cols, diag, vals, iluvals);
+}
+void orc_set_cholesky(int flag) { g_cholesky = flag; }
+int orc_crs_ichol_factor(int n, const int *rows, const int *cols, const int *diag, const double *vals, const int *ilurows, const int *ilucols,
+                         const int *iludiag, double *iluvals) {
+  return crs_ichol_factor(n, rows, cols, diag, vals, ilurows, ilucols, iludiag, iluvals);
 }
 long orc_crs_ilu1_pattern(int n, const int *rows, const int *cols, const int *diag, int *ilurows, int *ilucols, int *iludiag) {
   return crs_ilu1_pattern(n, rows, cols, diag, ilurows, ilucols, iludiag);

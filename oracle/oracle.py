@@ -58,6 +58,8 @@ def lib():
     L.orc_make_list_matrix.argtypes = [C.c_int, _ip, _ip, _ip, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_optimize_bandwidth.argtypes = [C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, C.c_int]
     L.orc_initialize_matrix.argtypes = [C.c_int, _ip, _ip, C.c_int, C.c_void_p, C.c_void_p, _ip, _ip, _ip]
+    L.orc_set_cholesky.argtypes = [C.c_int]
+    L.orc_crs_ichol_factor.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _ip, _ip, _ip, _dp]
     L.orc_set_threads.argtypes = [C.c_int]
     L.orc_max_threads.restype = C.c_int
     _LIB = L
@@ -74,6 +76,17 @@ def set_dot_order(mode):
     (grid-stride thread partials, xor-shuffle trees, block partials: elmerfem_b200/csrc/common.cuh grid_reduce), under
     which a single-rank device solve must agree with the oracle bit for bit."""
     lib().orc_set_dot_order(int(mode))
+
+
+_CHOLESKY = False
+
+
+def set_cholesky(flag):
+    """A % Cholesky ('Linear System Symmetric ILU', IterSolve.F90:526): ilu0 / ilun / lu_precond / itersolve take the incomplete
+    Cholesky branches of CRS_IncompleteLU (CRSMatrix.F90:3539-3602) and CRS_LUSolve (4618-4638)."""
+    global _CHOLESKY
+    _CHOLESKY = bool(flag)
+    lib().orc_set_cholesky(int(bool(flag)))
 
 
 def set_device_blocks(blocks=148 * 8):
@@ -104,7 +117,10 @@ def diag_precond(A, v):
 
 def ilu0(A):
     ilu = np.zeros(A.nnz)
-    lib().orc_crs_ilu0(A.n, A.rows, A.cols, A.diag, A.vals, ilu)
+    if _CHOLESKY:
+        lib().orc_crs_ichol_factor(A.n, A.rows, A.cols, A.diag, A.vals, A.rows, A.cols, A.diag, ilu)
+    else:
+        lib().orc_crs_ilu0(A.n, A.rows, A.cols, A.diag, A.vals, ilu)
     return ilu
 
 
@@ -118,7 +134,10 @@ def ilun(A, order):
         lib().orc_crs_ilu1_pattern(A.n, rows, cols, diag, r2.ctypes.data_as(C.c_void_p), c2.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
         rows, cols, diag = r2, c2, d2
     vals = np.zeros(cols.size)
-    lib().orc_crs_ilun_factor(A.n, A.rows, A.cols, A.vals, rows, cols, diag, vals)
+    if _CHOLESKY:
+        lib().orc_crs_ichol_factor(A.n, A.rows, A.cols, A.diag, A.vals, rows, cols, diag, vals)
+    else:
+        lib().orc_crs_ilun_factor(A.n, A.rows, A.cols, A.vals, rows, cols, diag, vals)
     return CRS(rows, cols, diag, vals, A.ndeg)
 
 

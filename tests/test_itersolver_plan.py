@@ -113,7 +113,6 @@ def test_the_reference_sif_sections():
     ("Linear System Preconditioning = vanka", "vanka"),
     ("Linear System Normwise Backward Error = True", "backward-error"),
     ("Linear System Componentwise Backward Error = True", "backward-error"),
-    ("Linear System Symmetric ILU = True", "Symmetric ILU"),
     ("Linear System ILU Factor = 0.1", "ILU Factor"),
     ("Edge Basis = True", "Edge Basis"),
     ("Linear System Iterative Method = CG\nLinear System Left Preconditioning = True", "left"),
@@ -121,6 +120,13 @@ def test_the_reference_sif_sections():
 def test_declined_combinations(line, why):
     assert _plan("Linear System Max Iterations = 10\n" + line + "\n") is None
     assert why.lower() in B.last_error().lower()
+
+
+def test_symmetric_ilu_is_accepted():
+    """'Linear System Symmetric ILU' (A % Cholesky, IterSolve.F90:526) no longer declines: the incomplete Cholesky branches are built."""
+    p = _plan("Linear System Max Iterations = 10\nLinear System Iterative Method = CG\nLinear System Preconditioning = ILU0\n"
+              "Linear System Symmetric ILU = True\n")
+    assert p is not None and (p["method"], p["precond"], p["ilu_order"]) == (1, 2, 0)
 
 
 def test_left_preconditioning_is_kept_where_itersolver_does_it():
