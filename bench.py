@@ -348,7 +348,7 @@ def measure(args, workload, rank, world, local, dist):
         lu_traffic = traffic.get({0: "lu_level", 3: "lu_wave", 4: "lu_lane"}.get(tri_mode, "lu"), traffic.get("lu"))
         roof = {"spmv": {"kernel": "k_spmv_sell", "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
                          "traffic": traffic.get("spmv"), "bytes_per_launch": bs, "ms_per_launch": spmv_ms_max, "share_of_step": share_spmv, "peak_source": peak_src},
-                "lu": {"kernel": {0: "k_sptrsv (level sweeps, L then U)", 1: "k_tritask", 2: "k_skew", 3: "k_wave (wave tiles, L then U, + layout conversion)",
+                "lu": {"kernel": {0: "k_sptrsv (level sweeps, L then U)", 3: "k_wave (wave tiles, L then U, + layout conversion)",
                                   4: "k_lane (lane tiles, L then U, + layout conversion)"}.get(tri_mode, "k_sptrsv"), "bound": "hbm", "achieved": lu_gbs, "peak": peak, "unit": "GB/s", "frac": lu_gbs / peak,
                        "traffic": lu_traffic, "bytes_per_launch": bl, "ms_per_launch": lu_ms_max, "share_of_step": share_lu, "peak_source": peak_src}}
         out = {

@@ -1,6 +1,7 @@
 // C ABI of the library (include/elmer_b200.h).  Thin: argument checks, host<->device staging and
 // exception -> return-code translation.  All numerical work is in the kernel translation units.
 #include "common.cuh"
+#include <cstring>
 #include "kernels.cuh"
 #include "krylov.h"
 #include "../../include/elmer_b200.h"
@@ -55,10 +56,7 @@ static void ensure_runtime(Handle &h) {
   h.tri_lookahead = std::max(1, env_int("B200_TRI_LOOKAHEAD", 16));
   h.tri_gate_sleep = (unsigned)env_int("B200_TRI_GATE_SLEEP", 100);
   h.tri_spin_sleep = (unsigned)env_int("B200_TRI_SPIN_SLEEP", 0);
-  h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", -2);  // 0 level kernel, 1 task kernel, 2 skewed lanes, 3 wave tiles, 4 lane tiles, -1 time level/task and pick, -2 (default) time level / wave tiles / lane tiles where the grid stencil is detected and keep the fastest
-  h.sk_blocks_per_sm = env_int("B200_SKEW_BLOCKS_PER_SM", 0);
-  h.sk_cfg = env_int("B200_SKEW_CFG", 0);
-  h.sk_wpb = env_int("B200_SKEW_WPB", 0);
+  h.tri_mode_cfg = h.tri_mode = env_int("B200_TRI_MODE", -2);  // 0 level kernel, 3 wave tiles, 4 lane tiles, -2 (default) time level / wave tiles / lane tiles where the grid stencil is detected and keep the fastest
   h.wv_blocks_per_sm = env_int("B200_WAVE_BLOCKS_PER_SM", 0);
   h.wv_cfg = env_int("B200_WAVE_CFG", 0);
   h.wv_e = env_int("B200_WAVE_E", 3);
@@ -67,10 +65,6 @@ static void ensure_runtime(Handle &h) {
   h.lt_e = env_int("B200_LANE_E", 1);
   h.bl_host = env_int("B200_BICGSTABL_HOST", 0) != 0;
   h.stage_uploads = env_int("B200_STAGE_UPLOADS", 1) != 0;
-  h.tt_rows = env_int("B200_TT_ROWS", 0);
-  h.tt_wpb = env_int("B200_TT_WPB", 0);
-  h.tt_wait_ns = (unsigned)env_int("B200_TT_WAIT_NS", 100);
-  h.tt_pf = env_int("B200_TT_PF", 16);
   h.pin_values = env_int("B200_PIN_VALUES", 0);
   h.blas_blocks = env_int("B200_BLAS_BLOCKS", NUM_SMS * 8);
   if (h.blas_blocks > MAX_RED_BLOCKS) h.blas_blocks = MAX_RED_BLOCKS;
@@ -281,7 +275,7 @@ int b200_destroy(void **handle) {
     h->d_rows.release(); h->d_cols.release(); h->d_diag.release();
     h->d_vals.release(); h->d_prec.release(); h->d_ilu.release(); h->d_dvals.release();
     h->A.release(); h->L.release(); h->U.release(); h->d_dinv_slot.release(); h->tri_counters.release(); h->d_lvlcnt_f.release(); h->d_lvlcnt_b.release(); h->d_urhs.release(); h->d_yl.release(); h->d_xu.release(); h->d_order_f.release(); h->d_rowdone.release();
-    tritask_release(*h); skew_release(*h); wave_release(*h); lane_release(*h); h->d_ilu_pos.release(); h->d_ilu_posptr.release(); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
+    wave_release(*h); lane_release(*h); h->d_ilu_pos.release(); h->d_ilu_posptr.release(); h->dl_rows.release(); h->dl_cols.release(); h->dl_diag.release(); h->dl_src.release();
     for (auto &w : h->work) w.release();
     h->d_b.release(); h->d_x.release(); h->d_tmp.release(); h->d_P.release();
     h->red_partials.release(); h->red_counters.release(); h->scal.release(); h->ctrl.release();
@@ -580,10 +574,19 @@ void b200_spmv(void **spmv, int *n, int *rows, int *cols, double *vals, double *
       install_structure(h, N, nnz, std::move(r0), std::move(c0), std::move(d0), 1);
       fresh = true;
     }
-    // the reference never signals that Values changed (reinit is always 0): detect it
-    double cs = 0.0;
-    for (long long p = 0; p < nnz; ++p) cs += vals[p] * (double)((p & 1023) + 1);
-    if (fresh || h.hook_vals_ptr != vals || cs != h.hook_checksum) {
+    // The reference never signals that Values changed (reinit is always 0): detect it with an exact hash of the raw bits (position-
+    // dependent 64-bit mix, all host threads; any single changed or swapped entry changes it -- what remains is the 2^-64 collision
+    // risk of a 64-bit hash, for which b200_set_values is the explicit path).
+    unsigned long long hv = 0;
+    const unsigned long long *bits = reinterpret_cast<const unsigned long long *>(vals);
+#pragma omp parallel for schedule(static) reduction(^ : hv)
+    for (long long p = 0; p < nnz; ++p) {
+      unsigned long long z = bits[p] + 0x9E3779B97F4A7C15ULL * (unsigned long long)(p + 1);
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+      hv ^= z ^ (z >> 31);
+    }
+    double cs; memcpy(&cs, &hv, sizeof cs);
+    if (fresh || h.hook_vals_ptr != vals || memcmp(&cs, &h.hook_checksum, sizeof cs) != 0) {
       h.d_vals.ensure(nnz);
       upload(h, h.d_vals.p, vals, nnz);
       h.have_prec = false;

@@ -101,21 +101,6 @@ constexpr int NSCAL = 64;
 
 struct Halo;   // multi-GPU plan (comm.cu)
 
-// Task-mode triangular solve plan (tritask.cu): one byte stream of per-step blocks per sweep.
-constexpr int TT_D = 16;     // depth (steps) of the per-warp shared-memory result ring
-constexpr int TT_CH = 16;    // operands per row requested one step ahead (registers)
-struct TriTask {
-  int ntasks = 0, rows_per_task = 0, slot_bytes = 16, maxw = 0; bool upper = false;
-  long long nsteps = 0, nfill = 0; size_t nbytes = 0;
-  DBuf<int> step0;                 // ntasks+1: first step of each task
-  DBuf<uint2> desc;                // per step: {offset, size} of its block in 16-byte units
-  DBuf<unsigned char> stream;      // the blocks
-  DBuf<unsigned> fill_dst; DBuf<int> fill_src;   // stream double index <- position in the ILU value array
-};
-
-// skewed-lane triangular solve (skew.cu, opt-in B200_TRI_MODE=2): geometry + the two per-step entry streams + work vectors
-struct SkewPlan { SkewGeom g; DBuf<double> SL, SU, yin, y, x; DBuf<long long> trace; bool ready = false, tried = false, trace_on = false; };
-
 // wave-tile triangular solve (wave.cu, B200_TRI_MODE=3): geometry, tile tables, the two per-step entry streams, work vectors
 struct WavePlan {
   WaveGeom g; DBuf<int> tile_of, tile_sig, tile_grp; DBuf<double> SL, SU, yin, y, x; DBuf<long long> trace;
@@ -169,15 +154,13 @@ struct Handle {
   // in which CRS_LUSolve's column-oriented backward loop updates an unknown) and the level plan of that sweep
   bool cholesky = false, ch_ready = false; int ch_nlev = 0, ch_nslices = 0;
   DBuf<int> ch_ptr, ch_row, ch_pos, ch_perm, ch_gate, ch_lvlcnt, ch_counters; DBuf<double> ch_y, ch_x;
-  // task-mode plans (tritask.cu); tri_mode: 0 level kernel, 1 task kernel, -1 pick the faster at the first factorisation
-  SkewPlan sk; int sk_blocks_per_sm = 0, sk_cfg = 0, sk_wpb = 0;
+  // tri_mode: 0 level kernel, 3 wave tiles, 4 lane tiles, -2 time them at the first factorisation and keep the fastest
   WavePlan wv; int wv_blocks_per_sm = 0, wv_cfg = 0, wv_e = 3;
   LanePlan lt; int lt_tc = 1, lt_warps = 0, lt_e = 1;
   void *stage_buf[2] = {nullptr, nullptr}; cudaEvent_t stage_ev[2] = {nullptr, nullptr}; bool stage_uploads = true;   // pinned bounce buffers of b200_set_values
   bool mv_honor_skip = false;                     // partitioned SpMVs queued inside a conditional section (Ctrl::done == 2) return at once
   bool bl_host = false;                           // B200_BICGSTABL_HOST=1: host-driven BiCGStab(l) (the round-1 driver) instead of the device-resident one
-  TriTask TL, TU; bool tt_ready = false; int tri_mode = 0, tri_mode_cfg = 0, tt_rows = 0, tt_wpb = 0; unsigned tt_wait_ns = 100; int tt_pf = 16; DBuf<double> d_ytask, d_xtask;
-  double tt_ms_level = 0, tt_ms_task = 0;
+  int tri_mode = 0, tri_mode_cfg = 0;
   // workspace
   std::vector<DBuf<double>> work; DBuf<double> d_b, d_x, d_tmp, d_P;
   DBuf<double> red_partials; DBuf<unsigned int> red_counters; DBuf<double> scal; DBuf<Ctrl> ctrl;
@@ -291,17 +274,6 @@ void ilu0_factor(Handle &h);                           // d_ilu from d_prec/d_va
 void lu_apply(Handle &h, double *u, const double *v);  // u = (LU)^-1 v   (device pointers)
 void diag_apply(Handle &h, double *u, const double *v);
 void sgs_sweeps(Handle &h, const double *b, double *x, double *t1, double *t2, double omega);   // one forward + one backward Gauss-Seidel sweep
-void tritask_analyse(Handle &h);                       // task-mode plans for both sweeps (host, once per structure)
-void tritask_refresh_values(Handle &h);                // copy the ILU values into the plans' streams
-void tritask_release(Handle &h);
-bool tritask_usable(Handle &h);
-void skew_analyse(Handle &h);                          // skewed-lane plan (host detection of the grid stencil; no-op when it does not apply)
-void skew_refresh_values(Handle &h);
-void skew_release(Handle &h);
-void lu_apply_skew(Handle &h, double *u, const double *v);
-void skew_trace_enable(Handle &h, bool on);
-void skew_trace_fetch(Handle &h, std::vector<long long> &out);
-void lu_apply_task(Handle &h, double *u, const double *v);
 void wave_analyse(Handle &h);                          // wave-tile plan (host detection of the grid stencil; no-op when it does not apply)
 void wave_refresh_values(Handle &h);
 void wave_release(Handle &h);

@@ -310,7 +310,6 @@ static void launch_coresident(const void *kernel, int blocks, int threads, cudaS
   B200_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(threads), argv, 0, st));   // (a plain launch measured no faster)
 }
 
-static void tri_autotune(Handle &h);
 static void tri_autotune_wave(Handle &h);
 
 // CRS_IncompleteLU with A % Cholesky set: the factor lives in the lower part + diagonal of d_ilu (same pattern as the LU factor)
@@ -350,11 +349,10 @@ void ilu0_factor(Handle &h) {
   if (h.cholesky) { ichol_factor(h); return; }
   tri_analyse(h);
 
-  if (h.tri_mode == 2) skew_analyse(h);
-  else if (h.tri_mode == 3) wave_analyse(h);
+  if (h.tri_mode != 0 && h.tri_mode != 3 && h.tri_mode != 4) h.tri_mode = -2;     // anything else: the default
+  if (h.tri_mode == 3) wave_analyse(h);
   else if (h.tri_mode == 4) lane_analyse(h);
   else if (h.tri_mode == -2) { wave_analyse(h); lane_analyse(h); }
-  else if (h.tri_mode != 0) tritask_analyse(h);
   cudaStream_t st = h.stream;
   h.d_ilu.ensure(h.lnnz());
   B200_CUDA(cudaEventRecord(h.evf0, st));
@@ -398,8 +396,6 @@ void ilu0_factor(Handle &h) {
     sell_refresh_values(h, h.L, h.d_ilu.p);
     sell_refresh_values(h, h.U, h.d_ilu.p);
     if (h.U.nslots) k_gather_diag_slots<<<(h.U.nslots + 255) / 256, 256, 0, st>>>(h.U.nslots, h.U.perm.p, h.d_ldiag(), h.d_ilu.p, h.d_dinv_slot.p);
-    if (h.tt_ready) tritask_refresh_values(h);
-    if (h.sk.ready) skew_refresh_values(h);
     if (h.wv.ready) wave_refresh_values(h);
     if (h.lt.ready) lane_refresh_values(h);
     B200_CUDA(cudaGetLastError());
@@ -411,9 +407,8 @@ void ilu0_factor(Handle &h) {
   h.st_factor_ms = ms;
   B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "ILU0 factorisation: dependency wait timed out");
   h.ilu_valid = true; h.ilu_exists = true;
-  h.st_factor_launch = h.n > 0 ? (h.tt_ready ? 7 : 5) : 0;   // factor, invert diag, 2 x SELL refresh, diag gather, 2 x stream refresh
-  if (h.tri_mode == -1) tri_autotune(h);
-  else if (h.tri_mode == -2) tri_autotune_wave(h);
+  h.st_factor_launch = h.n > 0 ? 5 : 0;   // factor, invert diag, 2 x SELL refresh, diag gather
+  if (h.tri_mode == -2) tri_autotune_wave(h);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1061,10 +1056,8 @@ void lu_apply(Handle &h, double *u, const double *v) {
   B200_REQUIRE(h.ilu_valid, "LU preconditioner applied without a valid ILU0 factor");
   if (h.n == 0) return;
   if (h.cholesky) { lu_apply_ichol(h, u, v); return; }
-  if (h.tri_mode == 2 && h.sk.ready) { lu_apply_skew(h, u, v); return; }   // experimental, opt-in; not ready -> level kernel
   if (h.tri_mode == 3 && h.wv.ready) { lu_apply_wave(h, u, v); return; }   // grid stencils; not detected -> level kernel
   if (h.tri_mode == 4 && h.lt.ready) { lu_apply_lane(h, u, v); return; }   // grid stencils; not detected -> level kernel
-  if (h.tri_mode == 1) { lu_apply_task(h, u, v); return; }
   k_tri_prepare<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.L.nslots, h.d_yl.p, h.U.nslots, h.d_xu.p, h.tri_counters.p, h.nlev_f + h.nlev_b + 2);
   if (h.tri_node >= 2) {                                           // node-lane plans: only the node-aware sweeps may run on them
     const int nch = (h.tri_maxw + 15) / 16;
@@ -1102,33 +1095,6 @@ void lu_apply(Handle &h, double *u, const double *v) {
   h.st_launch += 3; h.st_pcond++;
 }
 
-// Both kernels produce bit-identical results; which one is faster depends on the dependency structure
-// (long natural-order chains favour the task kernel).  Timed once per handle on the real factor.
-static void tri_autotune(Handle &h) {
-  if (h.n == 0 || !tritask_usable(h)) { h.tri_mode = 0; return; }
-  cudaStream_t st = h.stream;
-  DBuf<double> a, b; a.ensure(h.n); b.ensure(h.n);
-  B200_CUDA(cudaMemsetAsync(h.ctrl.p, 0, sizeof(Ctrl), st));
-  B200_CUDA(cudaMemsetAsync(a.p, 0, (size_t)h.n * sizeof(double), st));
-  float ms[2] = {0, 0};
-  for (int mode = 0; mode < 2; ++mode) {
-    h.tri_mode = mode;
-    lu_apply(h, b.p, a.p);
-    B200_CUDA(cudaEventRecord(h.evf0, st));
-    for (int r = 0; r < 2; ++r) lu_apply(h, b.p, a.p);
-    B200_CUDA(cudaEventRecord(h.evf1, st));
-    B200_CUDA(cudaStreamSynchronize(st));
-    B200_CUDA(cudaEventElapsedTime(&ms[mode], h.evf0, h.evf1));
-  }
-  B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-  B200_CUDA(cudaStreamSynchronize(st));
-  B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "triangular solve: dependency wait timed out while tuning");
-  h.tt_ms_level = ms[0] / 2; h.tt_ms_task = ms[1] / 2;
-  h.tri_mode = ms[1] < ms[0] ? 1 : 0;
-  h.st_launch -= 18; h.st_pcond -= 6;
-  a.release(); b.release();
-}
-
 // Default (B200_TRI_MODE unset): when the factor is that of a structured-grid stencil, the level kernel, the wave-tile kernel and the
 // lane-tile kernel (bit-identical results) are timed once on the real factor and the fastest is kept; the losers' plans are released.
 static void tri_autotune_wave(Handle &h) {
@@ -1157,7 +1123,6 @@ static void tri_autotune_wave(Handle &h) {
   B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
   B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "triangular solve: dependency wait timed out while tuning");
-  h.tt_ms_level = ms[0] / 3; h.tt_ms_task = ms[best ? best : (have[2] ? 2 : 1)] / 3;
   h.tri_mode = modes[best];
   if (h.tri_mode != 3) wave_release(h);
   if (h.tri_mode != 4) lane_release(h);

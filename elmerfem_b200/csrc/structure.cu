@@ -236,8 +236,6 @@ void ilu_pattern_build(Handle &h) {
 void ilu_invalidate(Handle &h) {
   h.ilu_valid = h.ilu_exists = false; h.tri_ready = false; h.ilu_pat_ready = false;
   h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0; h.grid_ilu_kern = nullptr; h.ilu_map_maxu = 0; h.ilu_map_tried = false; h.d_ilu_pos.release(); h.d_ilu_posptr.release();
-  tritask_release(h);
-  skew_release(h);
   wave_release(h);
   lane_release(h);
   ichol_release(h);

@@ -1,7 +1,7 @@
 """Triangular-solve kernels side by side: bitwise comparison against the first variant + timing.
-    python profiles/tools/sptrsv_modes.py 200 heat 0 1                       level kernel vs task kernel
-    python profiles/tools/sptrsv_modes.py 200 heat 0 2 2,B200_SKEW_BLOCKS_PER_SM=2   level kernel vs the experimental skewed-lane kernel
-A variant is `<B200_TRI_MODE>[,ENV=value,...]`.  Run mode 2 under `timeout`: it has not been on hardware yet (round 1)."""
+    python profiles/tools/sptrsv_modes.py 200 heat 0 3 4 -2            level kernel, wave tiles, lane tiles, the default (autotune)
+    python profiles/tools/sptrsv_modes.py 200 heat 0 4,B200_LANE_E=3   level kernel vs lane tiles with request lead 3
+A variant is `<B200_TRI_MODE>[,ENV=value,...]` (environment of earlier variants persists)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
@@ -18,8 +18,6 @@ ref = None
 for var in variants:
     env = dict(kv.split("=") for kv in var.split(",") if "=" in kv)
     mode = var.split(",")[0]
-    for k in ("B200_TT_ROWS", "B200_TT_WPB"):
-        os.environ.pop(k, None)
     os.environ["B200_TRI_MODE"] = mode
     os.environ.update(env)
     M = B.Matrix()

@@ -77,3 +77,27 @@ def test_solve_needs_a_gpu(dump, capsys):
     else:
         with pytest.raises(B.B200Error):
             replay.main(["--dir", d, "--sif", sif])
+
+
+@pytest.mark.gpu
+def test_replay_on_the_gpu_matches_the_oracle(dump, capsys, oracle):
+    """The whole tool on hardware: dump -> reader -> keyword front-end -> device scaling -> BiCGStab(4)+ILU(1) -> back-scaling.  Iteration
+    count as the oracle under the device summation order; solution norm and residual as the oracle's (SolveLinearSystem's order of
+    operations: ScaleLinearSystem, IterSolver, BackScaleLinearSystem)."""
+    import re
+    d, sif, n = dump
+    assert replay.main(["--dir", d, "--sif", sif]) == 0
+    out = capsys.readouterr().out
+    m = re.search(r"HUTI_INFO = (\d+), iterations = (\d+), \|\|Ax-b\|\|/\|\|b\|\| = ([0-9.eE+-]+), norm = ([0-9.eE+-]+)", out)
+    assert m and int(m.group(1)) == 1
+    S, b = meshio.read_linsys("linsys", d)
+    A = synth.CRS.from_scipy(S, 1)
+    oracle.set_dot_order(3)
+    try:
+        ref = oracle.solve_linear_system(A, b, method="bicgstabl", precond="ilu1", tol=1e-9, maxit=500, bicgstabl_l=4)
+    finally:
+        oracle.set_dot_order(0)
+    assert ref["info"] == 1 and int(m.group(2)) == ref["iters"]
+    assert float(m.group(3)) < 1e-8
+    x = ref["x"]
+    assert abs(float(m.group(4)) - float(np.sqrt(np.sum(x * x) / x.size))) <= 1e-7 * float(m.group(4))
