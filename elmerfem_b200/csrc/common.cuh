@@ -152,6 +152,7 @@ struct Handle {
   DBuf<int> d_urhs; DBuf<double> d_yl, d_xu;     // backward rhs map (U slot -> L slot); slot-ordered solve vectors
   // incomplete Cholesky ('Linear System Symmetric ILU', A % Cholesky): the factor's lower part by columns (rows descending: the order
   // in which CRS_LUSolve's column-oriented backward loop updates an unknown) and the level plan of that sweep
+  int ilu_reg_ok = -1;                           // rows narrow enough for k_ilu0_factor_reg: -1 unknown, 0 no, 1 yes
   bool cholesky = false, ch_ready = false; int ch_nlev = 0, ch_nslices = 0;
   DBuf<int> ch_ptr, ch_row, ch_pos, ch_perm, ch_gate, ch_lvlcnt, ch_counters; DBuf<double> ch_y, ch_x;
   // tri_mode: 0 level kernel, 3 wave tiles, 4 lane tiles, -2 time them at the first factorisation and keep the fastest

@@ -312,6 +312,82 @@ static void launch_coresident(const void *kernel, int blocks, int threads, cudaS
 
 static void tri_autotune_wave(Handle &h);
 
+// The factorisation for narrow rows (<= 32 entries, <= 16 of them left of the diagonal, pivot rows of <= 32 upper entries: scalar 27-point
+// stencils) with the row in REGISTERS, one entry per lane.  What limits k_ilu0_factor_map is not arithmetic but the chain of dependent
+// memory round trips a row makes AFTER its pivot rows are finished (1401 levels x 23 us on the 200^3 problem).  Here everything that does
+// not depend on the pivot rows' values -- the row itself, the pivot rows' extents, the position map, turned from scatter form (entry u of
+// pivot row m -> position in this row) into gather form (position -> entry u) through shared memory -- is fetched BEFORE the wait on the
+// rowdone flags; after it a single round trip brings the pivots and, per lane, the one operand of each pivot row that lands on the lane's
+// position; the elimination then runs from registers with one shuffle + one division per pivot (no shared memory, no warp barrier), and the
+// row is published.  Same operations on the same operands in the same order as k_ilu0_factor: bit-identical ILUValues.
+__global__ void __launch_bounds__(256, 4) k_ilu0_factor_reg(int nslots, const int *__restrict__ perm, const int *__restrict__ rows, const int *__restrict__ cols,
+                                                          const int *__restrict__ diag, const double *__restrict__ Avals, const int *__restrict__ src, double *LU,
+                                                          int *rowdone, Ctrl *ctrl, const long long *__restrict__ posptr, int maxu,
+                                                          const unsigned char *__restrict__ pos) {
+  constexpr int NM = 16;
+  __shared__ unsigned char s_inv[8][NM][32];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int slot = gwarp; slot < nslots; slot += nwarps) {
+    const int r = perm[slot];
+    if (r < 0) continue;
+    const int rs = rows[r], len = rows[r + 1] - rs, nlow = diag[r] - rs;
+    const unsigned char *pm = pos + posptr[r];
+    // ---- before the wait: the row, the pivot rows' diagonals' positions, the gather form of the position map
+    double v = 0.0;
+    if (lane < len) { if (src) { const int q = src[rs + lane]; v = q >= 0 ? Avals[q] : 0.0; } else v = Avals[rs + lane]; }
+    const int kcol = lane < nlow ? cols[rs + lane] : -1;
+    const int kd = kcol >= 0 ? diag[kcol] : 0;
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < NM; ++m) s_inv[wib][m][lane] = 255;
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+      if (m < nlow && lane < maxu) { const unsigned char pp = pm[(size_t)m * maxu + lane]; if (pp != 255) s_inv[wib][m][pp] = (unsigned char)lane; }
+    __syncwarp();
+    unsigned char gi[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) gi[m] = s_inv[wib][m][lane];
+    // ---- wait until every row of the strict lower pattern is finished
+    long long spins = 0;
+    if (kcol >= 0) {
+      while (ld_acquire(rowdone + kcol) == 0) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        __nanosleep(20);
+      }
+    }
+    __syncwarp();
+    // ---- one round trip: pivots, and per lane the operand of each pivot row that meets the lane's position
+    const double ukk_l = kcol >= 0 ? __ldcg(LU + kd) : 0.0;
+    double pv[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      const int kdm = __shfl_sync(FULL, kd, m);
+      pv[m] = (m < nlow && gi[m] != 255) ? __ldcg(LU + kdm + 1 + gi[m]) : 0.0;
+    }
+    // ---- 3624-3637 from registers
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      if (m < nlow) {
+        double skm = __shfl_sync(FULL, v, m);
+        const double ukk = __shfl_sync(FULL, ukk_l, m);
+        if (skm != 0.0) {                                           // 3626
+          if (fabs(ukk) > AEPS) skm = __ddiv_rn(skm, ukk);         // 3628-3629
+          if (lane == m) v = skm;
+          if (gi[m] != 255) v = nfms(v, skm, pv[m]);               // 3631-3636
+        }
+      }
+    }
+    if (lane < len) __stcg(LU + rs + lane, v);                      // 3643-3649
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(rowdone + r, 1);
+  }
+}
+
 // CRS_IncompleteLU with A % Cholesky set: the factor lives in the lower part + diagonal of d_ilu (same pattern as the LU factor)
 static void ichol_factor(Handle &h) {
   ichol_analyse(h);
@@ -380,7 +456,19 @@ void ilu0_factor(Handle &h) {
       }
     }
     const bool use_map = map_ok && h.ilu_map_maxu > 0;
-    const void *kern = use_map ? (const void *)k_ilu0_factor_map : (const void *)k_ilu0_factor;
+    // narrow rows (scalar 27-point stencils): the register kernel
+    static const bool reg_ok = !(getenv("B200_ILU_REG") && atoi(getenv("B200_ILU_REG")) == 0);
+    bool use_reg = use_map && reg_ok && h.ilu_map_maxu <= 32;
+    if (use_reg) {
+      if (h.ilu_reg_ok < 0) {
+        const std::vector<int> &R = h.lrows(), &Dg = h.ldiag();
+        bool ok = true;
+        for (int i = 0; i < h.n && ok; ++i) ok = (R[i + 1] - R[i] <= 32) && (Dg[i] - R[i] <= 16);
+        h.ilu_reg_ok = ok ? 1 : 0;
+      }
+      use_reg = h.ilu_reg_ok == 1;
+    }
+    const void *kern = use_reg ? (const void *)k_ilu0_factor_reg : use_map ? (const void *)k_ilu0_factor_map : (const void *)k_ilu0_factor;
     if (h.grid_ilu_kern != kern) { h.grid_ilu = persistent_blocks(kern, 256, 0); h.grid_ilu_kern = kern; }
     int blocks = std::max(1, std::min(h.grid_ilu, (h.L.nslots + 7) / 8));
     B200_CUDA(cudaEventRecord(h.evf0, st));                          // (the one-time symbolic map is not part of the factorisation time)

@@ -235,7 +235,7 @@ void ilu_pattern_build(Handle &h) {
 
 void ilu_invalidate(Handle &h) {
   h.ilu_valid = h.ilu_exists = false; h.tri_ready = false; h.ilu_pat_ready = false;
-  h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0; h.grid_ilu_kern = nullptr; h.ilu_map_maxu = 0; h.ilu_map_tried = false; h.d_ilu_pos.release(); h.d_ilu_posptr.release();
+  h.grid_ilu = h.grid_tri_l = h.grid_tri_u = 0; h.grid_ilu_kern = nullptr; h.ilu_map_maxu = 0; h.ilu_map_tried = false; h.ilu_reg_ok = -1; h.d_ilu_pos.release(); h.d_ilu_posptr.release();
   wave_release(h);
   lane_release(h);
   ichol_release(h);

@@ -54,10 +54,10 @@ __global__ void k_wave_sentinel(long long nv, double *__restrict__ x) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) x[i] = sent;
 }
 
-// The same two conversions with BOTH sides coalesced: a block takes a chunk of 32 consecutive steps of one tile, i.e. for every line of
+// The way in with BOTH sides coalesced: a block takes a chunk of 32 consecutive steps of one tile, i.e. for every line of
 // the tile 32 consecutive rows a.  Natural side: one warp per line, lanes = the 32 rows (256 contiguous bytes); tile side: rows of NTHR
-// values per step; the skewed transposition goes through shared memory (row length NTHR + 1: conflict-free).  k_wave_in/k_wave_out
-// touched one 32-byte sector per 8-byte element on the tile side (115 + 210 us per application on the 200^3 problem).
+// values per step; the skewed transposition goes through shared memory (row length NTHR + 1: conflict-free).  k_wave_in
+// touches one 32-byte sector per 8-byte element on the tile side (115 us per application on the 200^3 problem).
 constexpr int WV_CH = 32;
 __global__ void __launch_bounds__(256) k_wave_in2(WaveGeom g, const int *__restrict__ tile_sig, const int *__restrict__ tile_grp, const double *__restrict__ v,
                                                   double *__restrict__ yin, double *__restrict__ y) {
@@ -86,32 +86,6 @@ __global__ void __launch_bounds__(256) k_wave_in2(WaveGeom g, const int *__restr
     }
   }
 }
-__global__ void __launch_bounds__(256) k_wave_out2(WaveGeom g, const int *__restrict__ tile_sig, const int *__restrict__ tile_grp, double *__restrict__ x,
-                                                   double *__restrict__ u) {
-  extern __shared__ double wv_tr[];
-  const double sent = __longlong_as_double((long long)SENTINEL);
-  const int NTHR = g.nthr(), LD = NTHR + 1, nch = (g.NT + WV_CH - 1) / WV_CH;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (long long q = blockIdx.x; q < (long long)g.ntiles * nch; q += gridDim.x) {
-    const int k = (int)(q / nch), t0 = (int)(q - (long long)k * nch) * WV_CH;
-    const int sig = tile_sig[k], C = tile_grp[k];
-    __syncthreads();
-    for (int e = threadIdx.x; e < WV_CH * NTHR; e += blockDim.x) {  // tile layout -> shared; the slots are handed back as sentinels
-      const int s = e / NTHR, t = e - s * NTHR;
-      if (t0 + s < g.NT) {
-        const long long p = ((long long)k * g.NT + t0 + s) * NTHR + t;
-        wv_tr[s * LD + t] = x[p]; x[p] = sent;
-      }
-    }
-    __syncthreads();
-    for (int t = wib; t < NTHR; t += nw) {                          // shared -> natural: warp per line
-      const WaveLine ln = wv_line(g, sig, C, t % g.TB, t / g.TB);
-      const int a = t0 + lane - ln.tau0;
-      if (ln.valid && (unsigned)a < (unsigned)g.NR && t0 + lane < g.NT) u[a + (long long)g.NR * (ln.b + (long long)g.NL * ln.c)] = wv_tr[lane * LD + t];
-    }
-  }
-}
-
 __device__ __forceinline__ unsigned wv_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void wv_prefetch_l2(const void *p, unsigned bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
 #ifdef WV_NO_BAR
@@ -420,11 +394,10 @@ static void wave_launch(Handle &h, const double *S, const double *rhs, double *o
 void lu_apply_wave(Handle &h, double *u, const double *v) {
   B200_REQUIRE(h.wv.ready, "wave-tile triangular solve without a plan");
   WavePlan &w = h.wv;
-  // B200_WAVE_CONV: 1 = element-wise conversions both ways, 2 = transposing conversions both ways; default: transposing on the way in
-  // (64 us instead of 115 on the 200^3 problem), element-wise on the way out (210 us; the transposing kernel's misaligned line-chunk
-  // stores to the natural-order vector take 440 us)
-  static const int conv = getenv("B200_WAVE_CONV") ? atoi(getenv("B200_WAVE_CONV")) : 0;
-  const bool conv2 = conv != 1, conv2_out = conv == 2;
+  // Transposing conversion on the way in (64 us instead of 115 on the 200^3 problem; B200_WAVE_CONV=1: element-wise), element-wise on the
+  // way out (210 us).  [Measured and dropped for the way out: the same chunk transposition (440 us) and whole lines staged in shared
+  // memory and written as one contiguous run (730 us).]
+  static const bool conv2 = !(getenv("B200_WAVE_CONV") && atoi(getenv("B200_WAVE_CONV")) == 1);
   const int blocks = std::min((h.n + 255) / 256, NUM_SMS * 8);
   const size_t trsm = (size_t)WV_CH * (w.g.nthr() + 1) * sizeof(double);
   const int cblocks = (int)std::min<long long>((long long)w.g.ntiles * ((w.g.NT + WV_CH - 1) / WV_CH), NUM_SMS * 6);
@@ -432,8 +405,7 @@ void lu_apply_wave(Handle &h, double *u, const double *v) {
   else k_wave_in<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, v, w.yin.p, w.g.vlen(), w.y.p);
   wave_launch<false>(h, w.SL.p, w.yin.p, w.y.p);
   wave_launch<true>(h, w.SU.p, w.y.p, w.x.p);
-  if (conv2_out) k_wave_out2<<<cblocks, 256, trsm, h.stream>>>(w.g, w.tile_sig.p, w.tile_grp.p, w.x.p, u);
-  else k_wave_out<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, w.x.p, u);
+  k_wave_out<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, w.x.p, u);
   B200_CUDA(cudaGetLastError());
   h.st_launch += 4; h.st_pcond++;
 }
