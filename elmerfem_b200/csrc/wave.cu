@@ -127,7 +127,7 @@ constexpr int WV_PFG = 4;      // steps per prefetch instruction
 template <bool UPPER, int TB, int TC, int E, int PF>
 __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) + 32) k_wave(WaveGeom g, const int *__restrict__ tile_of, const int *__restrict__ tile_sig,
                                                                                             const int *__restrict__ tile_grp, const double *__restrict__ S,
-                                                                                            const double *__restrict__ RHS, double *Q, Ctrl *ctrl, long long *trace) {
+                                                                                            const double *__restrict__ RHS, double *Q, Ctrl *ctrl, long long *trace, double *nat) {
   if (ctrl->done) return;
   constexpr int NTHR = TB * TC, NH = TB + 2 + 2 * TC, NE = UPPER ? 14 : 13;
   constexpr int YW = TB + 2, YH = TC + 1, YSLOT = YW * YH;
@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) +
       const int jb = tid % TB, w = tid / TB;
       const WaveLine ln = wv_line(g, sig, C, jb, w);
       double *qp = Q + (ln.valid ? wv_pos_mirror(g, tile_of, 0, ln.b, ln.c) : 0);     // row a at qp - a * NTHR
+      // the backward sweep also stores its result in natural order (row a of the mirrored line at np - a): no conversion pass afterwards
+      double *np = (nat && ln.valid) ? nat + (g.NR - 1) + (long long)g.NR * ((g.NL - 1 - ln.b) + (long long)g.NL * (g.NP - 1 - ln.c)) : nullptr;
       const double *yA = Yr + (w + 1) * YW + (jb + 1), *yB = Yr + w * YW + (jb + 2), *yC = Yr + w * YW + (jb + 1), *yD = Yr + w * YW + jb;
       double *yO = Yr + (w + 1) * YW + (jb + 2);
       const double *gS = S + step0 * (NE * NTHR) + tid, *gR = RHS + step0 * NTHR + tid;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) +
             if (acc != acc) acc = __longlong_as_double((long long)CANON_NAN);
             if (!active) acc = 0.0;
             yO[(tau & (WV_RING - 1)) * YSLOT] = acc;
-            if (active) wv_st_relaxed(qp - (long long)a * NTHR, acc);
+            if (active) { wv_st_relaxed(qp - (long long)a * NTHR, acc); if (UPPER && np) np[-a] = acc; }
             h = acc;
             Am = A0; A0 = An; B0 = Bn; Cm = C0; C0 = Cn; Dm = D0; D0 = Dn;
             wv_bar(NALL);
@@ -361,7 +363,7 @@ void wave_refresh_values(Handle &h) {
 }
 
 template <bool UPPER, int TB, int TC, int E, int PF>
-static void wave_launch_cfg(Handle &h, const double *S, const double *rhs, double *out) {
+static void wave_launch_cfg(Handle &h, const double *S, const double *rhs, double *out, double *nat) {
   const void *kern = (const void *)k_wave<UPPER, TB, TC, E, PF>;
   constexpr int NTHR = TB * TC, NH = TB + 2 + 2 * TC, NBLK = NTHR + 32 * ((NH + 31) / 32) + 32;
   const size_t smem = (size_t)WV_RING * (TB + 2) * (TC + 1) * 8 + 16;
@@ -374,38 +376,42 @@ static void wave_launch_cfg(Handle &h, const double *S, const double *rhs, doubl
   const int blocks = std::max(1, std::min(sms * want, h.wv.g.ntiles));
   WaveGeom g = h.wv.g; Ctrl *ctrl = h.ctrl.p; long long *trace = h.wv.trace_on ? h.wv.trace.p : nullptr;
   const int *tile_of = h.wv.tile_of.p, *tsig = h.wv.tile_sig.p, *tgrp = h.wv.tile_grp.p;
-  void *argv[] = {(void *)&g, (void *)&tile_of, (void *)&tsig, (void *)&tgrp, (void *)&S, (void *)&rhs, (void *)&out, (void *)&ctrl, (void *)&trace};
+  void *argv[] = {(void *)&g, (void *)&tile_of, (void *)&tsig, (void *)&tgrp, (void *)&S, (void *)&rhs, (void *)&out, (void *)&ctrl, (void *)&trace, (void *)&nat};
   B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(NBLK), argv, smem, h.stream));
 }
 
 template <bool UPPER>
-static void wave_launch(Handle &h, const double *S, const double *rhs, double *out) {
+static void wave_launch(Handle &h, const double *S, const double *rhs, double *out, double *nat) {
   switch (h.wv_cfg) {                                                // <tile TB x TC, request lead, prefetch lead>
-    case 1: wave_launch_cfg<UPPER, 16, 4, 7, 16>(h, S, rhs, out); break;
-    case 2: wave_launch_cfg<UPPER, 16, 8, 7, 0>(h, S, rhs, out); break;
-    case 3: wave_launch_cfg<UPPER, 8, 8, 7, 16>(h, S, rhs, out); break;
-    case 4: wave_launch_cfg<UPPER, 16, 8, 7, 32>(h, S, rhs, out); break;
-    case 5: wave_launch_cfg<UPPER, 32, 4, 7, 16>(h, S, rhs, out); break;
-    case 6: wave_launch_cfg<UPPER, 16, 8, 7, 16>(h, S, rhs, out); break;
-    default: wave_launch_cfg<UPPER, 16, 8, 3, 16>(h, S, rhs, out); break;     // measured best on 201^3 (request lead 3: 2.12 ms, 7: 2.35 ms)
+    case 1: wave_launch_cfg<UPPER, 16, 4, 7, 16>(h, S, rhs, out, nat); break;
+    case 2: wave_launch_cfg<UPPER, 16, 8, 7, 0>(h, S, rhs, out, nat); break;
+    case 3: wave_launch_cfg<UPPER, 8, 8, 7, 16>(h, S, rhs, out, nat); break;
+    case 4: wave_launch_cfg<UPPER, 16, 8, 7, 32>(h, S, rhs, out, nat); break;
+    case 5: wave_launch_cfg<UPPER, 32, 4, 7, 16>(h, S, rhs, out, nat); break;
+    case 6: wave_launch_cfg<UPPER, 16, 8, 7, 16>(h, S, rhs, out, nat); break;
+    default: wave_launch_cfg<UPPER, 16, 8, 3, 16>(h, S, rhs, out, nat); break;     // measured best on 201^3 (request lead 3: 2.12 ms, 7: 2.35 ms)
   }
 }
 
 void lu_apply_wave(Handle &h, double *u, const double *v) {
   B200_REQUIRE(h.wv.ready, "wave-tile triangular solve without a plan");
   WavePlan &w = h.wv;
-  // Transposing conversion on the way in (64 us instead of 115 on the 200^3 problem; B200_WAVE_CONV=1: element-wise), element-wise on the
-  // way out (210 us).  [Measured and dropped for the way out: the same chunk transposition (440 us) and whole lines staged in shared
-  // memory and written as one contiguous run (730 us).]
+  // Way in: transposing conversion (k_wave_in2, 64 us on the 200^3 problem; B200_WAVE_CONV=1: element-wise k_wave_in, 115 us).  [Reading the
+  // right-hand side straight from the natural-order vector inside the forward sweep was measured too: +90 us, its per-thread loads are
+  // not covered by the stream prefetch.]  Way out: the backward sweep stores its result in natural order as well and a fill kernel hands
+  // the slots back as sentinels (18 us; B200_WAVE_OUT=1: the conversion pass k_wave_out, 210 us).  [Measured and dropped for the way out:
+  // a chunk transposition like k_wave_in2 (440 us) and whole lines staged in shared memory and written as one contiguous run (730 us).]
+  static const bool direct = !(getenv("B200_WAVE_OUT") && atoi(getenv("B200_WAVE_OUT")) == 1);
   static const bool conv2 = !(getenv("B200_WAVE_CONV") && atoi(getenv("B200_WAVE_CONV")) == 1);
   const int blocks = std::min((h.n + 255) / 256, NUM_SMS * 8);
   const size_t trsm = (size_t)WV_CH * (w.g.nthr() + 1) * sizeof(double);
   const int cblocks = (int)std::min<long long>((long long)w.g.ntiles * ((w.g.NT + WV_CH - 1) / WV_CH), NUM_SMS * 6);
   if (conv2) k_wave_in2<<<cblocks, 256, trsm, h.stream>>>(w.g, w.tile_sig.p, w.tile_grp.p, v, w.yin.p, w.y.p);
   else k_wave_in<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, v, w.yin.p, w.g.vlen(), w.y.p);
-  wave_launch<false>(h, w.SL.p, w.yin.p, w.y.p);
-  wave_launch<true>(h, w.SU.p, w.y.p, w.x.p);
-  k_wave_out<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, w.x.p, u);
+  wave_launch<false>(h, w.SL.p, w.yin.p, w.y.p, nullptr);
+  wave_launch<true>(h, w.SU.p, w.y.p, w.x.p, direct ? u : nullptr);
+  if (direct) k_wave_sentinel<<<NUM_SMS * 8, 256, 0, h.stream>>>(w.g.vlen(), w.x.p);
+  else k_wave_out<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, w.x.p, u);
   B200_CUDA(cudaGetLastError());
   h.st_launch += 4; h.st_pcond++;
 }
