@@ -57,7 +57,7 @@ def lib():
         "b200_itersolver": [vpp, dp, dp, C.c_char_p, ip, ip],
         "b200_matvec": [vpp, dp, dp], "b200_diag_precondition": [vpp, dp, dp], "b200_lu_precondition": [vpp, dp, dp],
         "b200_dot": [vpp, ip, dp, dp, dp], "b200_nrm2": [vpp, ip, dp, dp],
-        "b200_get_ilu_values": [vpp, dp], "b200_set_ilu_order": [vpp, ip], "b200_set_symmetric_ilu": [vpp, ip], "b200_set_bilu_blocks": [vpp, ip], "b200_get_ilu_structure": [vpp, ip, ip, ip, ip], "b200_get_structure": [vpp, ip, ip, ip], "b200_get_levels": [vpp, ip, ip],
+        "b200_get_ilu_values": [vpp, dp], "b200_set_ilu_order": [vpp, ip], "b200_set_symmetric_ilu": [vpp, ip], "b200_set_ilut": [vpp, ip, dp], "b200_set_bilu_blocks": [vpp, ip], "b200_get_ilu_structure": [vpp, ip, ip, ip, ip], "b200_get_structure": [vpp, ip, ip, ip], "b200_get_levels": [vpp, ip, ip],
         "b200_comm_unique_id": [C.c_char_p], "b200_comm_init": [vpp, ip, ip, C.c_char_p],
         "b200_set_partition": [vpp, ip, ip, ip, ip, ip, ip, ip, ip],
         "b200_get_halo_plan": [vpp, ip, ip, ip, ip, ip, ip],
@@ -277,6 +277,10 @@ class Matrix:
     def set_symmetric_ilu(self, flag):
         """A % Cholesky ("Linear System Symmetric ILU"): incomplete Cholesky instead of incomplete LU."""
         _check(lib().b200_set_symmetric_ilu(self.handle, _i(1 if flag else 0)), "b200_set_symmetric_ilu")
+
+    def set_ilut(self, tol, on=True):
+        """ILUT with drop tolerance `tol` ("Linear System Preconditioning = ILUT"); on=False returns to ILU(order)."""
+        _check(lib().b200_set_ilut(self.handle, _i(1 if on else 0), C.byref(C.c_double(float(tol)))), "b200_set_ilut")
 
     def set_bilu_blocks(self, blocks):
         """BILU: factorise the block-diagonal part, MOD(i,blocks) == MOD(j,blocks) (CRS_BlockDiagonal); <= 1 switches it off."""

@@ -495,6 +495,18 @@ int b200_set_ilu_order(void **handle, const int *order) {
     ilu_invalidate(h);
   });
 }
+int b200_set_ilut(void **handle, const int *flag, const double *tol) {
+  return guarded([&] {
+    Handle &h = H(handle);
+    B200_REQUIRE(flag && tol, "b200_set_ilut: null argument");
+    B200_REQUIRE(h.nranks == 1 || true, "");
+    const bool f = *flag != 0;
+    if (f == h.ilut && (!f || *tol == h.ilut_tol)) return;
+    h.ilut = f; h.ilut_tol = *tol;
+    if (f) { h.ilu_order = 0; h.bilu_blocks = 0; }
+    ilu_invalidate(h);
+  });
+}
 int b200_set_symmetric_ilu(void **handle, const int *flag) {
   return guarded([&] {
     Handle &h = H(handle);

@@ -127,7 +127,8 @@ struct Handle {
   // ILU(n > 0): the factor lives on its own pattern (CRSMatrix.F90:3488-3510); ILU0 aliases the matrix pattern
   int ilu_order = 0; bool ilu_pat_ready = false; long long ilu_nnz = 0;
   int bilu_blocks = 0;                             // > 1: BILU, the factor of the block-diagonal part (CRS_BlockDiagonal, CRSMatrix.F90:2382-2420)
-  bool ilu_sep() const { return ilu_order > 0 || bilu_blocks > 1; }   // factor on its own pattern
+  bool ilut = false; double ilut_tol = 0.0;      // ILUT: the pattern comes out of the factorisation (ilut_factor installs it)
+  bool ilu_sep() const { return ilu_order > 0 || bilu_blocks > 1 || ilut; }   // factor on its own pattern
   std::vector<int> hl_rows, hl_cols, hl_diag;    // 0-based host copies of ILURows/ILUCols/ILUDiag
   DBuf<int> dl_rows, dl_cols, dl_diag, dl_src;   // device copies; dl_src: position of the entry in the matrix values, -1 for fill
   const std::vector<int> &lrows() const { return ilu_sep() ? hl_rows : h_rows; }

@@ -86,6 +86,7 @@ struct SolvePlan {
   int ilu_order = -1;       // >= 0 when an ILU(n) / BILU preconditioner is selected
   int bilu_blocks = 0;      // > 1: ILU(0) of the block-diagonal part with that many blocks
   bool cholesky = false;    // Linear System Symmetric ILU
+  bool ilut = false; double ilut_tol = 0.0;   // Linear System Preconditioning = ILUT, Linear System ILUT Tolerance
 };
 
 static void plan_from_sif(const Sif &P, int n, int ndeg, SolvePlan &pl) {
@@ -174,7 +175,11 @@ static void plan_from_sif(const Sif &P, int n, int ndeg, SolvePlan &pl) {
   pl.cholesky = P.logical("Linear System Symmetric ILU");             // 526: A % Cholesky
   if (pcs == "none") pc = B200_PRECOND_NONE;
   else if (pcs == "diagonal") pc = B200_PRECOND_DIAGONAL;
-  else if (pcs == "ilut") throw Declined{"ILUT"};
+  else if (pcs == "ilut") {                                           // 535-538: PRECOND_ILUT, tolerance 0 when the keyword is absent
+    pl.ilut = true; pl.ilut_tol = P.real("Linear System ILUT Tolerance", 0.0);
+    pl.ilu_order = 0; pl.bilu_blocks = 0;
+    pc = B200_PRECOND_ILU0;
+  }
   else if (pcs.rfind("ilu", 0) == 0) {
     int ilun; bool got; double o = P.real("Linear System ILU Order", 0.0, &got);
     if (got) ilun = (int)lround(o);
@@ -235,8 +240,11 @@ extern "C" int b200_itersolver(void **handle, const double *b, double *x, const 
     plan_from_sif(P, h.n, h.ndeg, pl);
     int *ipar = pl.ipar; double *dpar = pl.dpar;
     int method = pl.method, pc = pl.pc;
-    if (pl.ilu_order >= 0 && (pl.ilu_order != h.ilu_order || pl.bilu_blocks != h.bilu_blocks || pl.cholesky != h.cholesky)) {
-      B200_CUDA(cudaSetDevice(h.device)); h.ilu_order = pl.ilu_order; h.bilu_blocks = pl.bilu_blocks; h.cholesky = pl.cholesky; ilu_invalidate(h);
+    if (pl.ilu_order >= 0 && (pl.ilu_order != h.ilu_order || pl.bilu_blocks != h.bilu_blocks || pl.cholesky != h.cholesky || pl.ilut != h.ilut ||
+                              (pl.ilut && pl.ilut_tol != h.ilut_tol))) {
+      B200_CUDA(cudaSetDevice(h.device));
+      h.ilu_order = pl.ilu_order; h.bilu_blocks = pl.bilu_blocks; h.cholesky = pl.cholesky; h.ilut = pl.ilut; h.ilut_tol = pl.ilut_tol;
+      ilu_invalidate(h);
     }
     // ---- recompute policy (579-587): factorise when no factor exists or Refactorize and SolveCount mod n == 0
     int sc = solve_count ? *solve_count : 0;

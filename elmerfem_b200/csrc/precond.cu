@@ -16,6 +16,9 @@
 namespace b200 {
 
 constexpr int ILU_MAXROW = 128;            // rows up to this length are staged in shared memory
+__device__ __forceinline__ int ld_relaxed_i(const int *p) {
+  int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
 constexpr long long SPIN_LIMIT = 1LL << 27;
 
 // ---------------------------------------------------------------------------------------------
@@ -420,8 +423,225 @@ static void ichol_factor(Handle &h) {
   h.tri_mode = 0;                                                   // the Cholesky sweeps are the only solve path of this factor
 }
 
+// ---------------------------------------------------------------------------------------------
+// ILUT, CRS_ILUT / ComputeILUT (CRSMatrix.F90:4144-4340; 'Linear System Preconditioning = ILUT', 'Linear System ILUT Tolerance').  The
+// pattern of the factor is decided by the values, row by row, so there is no symbolic phase and no level schedule: one warp per row in
+// NATURAL order (warp w takes rows w, w + W, ...), a row waits for each of its pivot rows on its rowdone flag as it reaches it -- every
+// dependency points to a smaller row and every warp walks upwards, so the smallest unfinished row never waits and the wavefront forms by
+// itself.  The working row lives in shared memory as a column-sorted list (the reference's flagged full-length vector, 4231-4258): pivots
+// are taken in ascending column order; the upper part of a finished pivot row is merged in 32 entries at a time -- present columns are
+// updated in place (S(j) = S(j) - S(k) U(k,j)), absent ones are inserted at their sorted position with S(j) = 0 - S(k) U(k,j), which is what
+// the reference's zero-initialised vector gives.  Then the drop rule (keep |S| >= TOL * ||A(i,:)||_2, always the diagonal; the norm summed
+// in storage order) and the row goes to a pool at an atomically reserved offset.  Same operations, same order: bit-identical factors.
+constexpr int ILUT_CAP = 1024;        // entries of a working row
+constexpr int ILUT_WARPS = 4;
+__global__ void __launch_bounds__(ILUT_WARPS * 32) k_ilut_factor(int n, const int *__restrict__ rows, const int *__restrict__ cols, const double *__restrict__ Avals,
+                                                                  double tol, int *pcols, double *pvals, unsigned long long cap, unsigned long long *top,
+                                                                  long long *rstart, int *rlen, int *rdiag, int *rowdone, Ctrl *ctrl, int *overflow) {
+  extern __shared__ __align__(16) unsigned char ilut_sm[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int *scol = reinterpret_cast<int *>(ilut_sm) + wib * ILUT_CAP;
+  double *sval = reinterpret_cast<double *>(ilut_sm + (size_t)ILUT_WARPS * ILUT_CAP * sizeof(int)) + wib * ILUT_CAP;
+  int *nip = reinterpret_cast<int *>(ilut_sm + (size_t)ILUT_WARPS * ILUT_CAP * (sizeof(int) + sizeof(double))) + wib * 32;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  long long spins = 0;
+  for (int i = gwarp; i < n; i += nwarps) {
+    const int rs = rows[i], len = rows[i + 1] - rs;
+    bool dead = ld_relaxed_i(overflow) != 0;                        // a row or the pool overflowed somewhere: publish and leave
+    if (!dead && len > ILUT_CAP) { if (lane == 0) atomicExch(overflow, 2); dead = true; }
+    int L = dead ? 0 : len;
+    for (int t = lane; t < L; t += 32) { scol[t] = cols[rs + t]; sval[t] = Avals[rs + t]; }
+    __syncwarp();
+    double s2 = 0.0;                                                // 4262, before the row is touched
+    for (int t = 0; t < L; ++t) { const double a = fabs(sval[t]); s2 = __dadd_rn(s2, __dmul_rn(a, a)); }
+    const double thr = __dmul_rn(tol, __dsqrt_rn(s2));
+    int pos = 0;
+    while (!dead && pos < L) {
+      const int k = scol[pos];
+      if (k >= i) break;
+      while (ld_acquire(rowdone + k) == 0) {
+        if (++spins > SPIN_LIMIT) { ctrl->spin_timeout = 1; break; }
+        __nanosleep(40);
+      }
+      if (ld_relaxed_i(overflow) != 0) { dead = true; break; }
+      const long long ks = rstart[k];
+      const int kl = rlen[k], kdg = rdiag[k];
+      const double piv = __ldcg(pvals + ks + kdg);
+      double Sk = sval[pos];
+      if (fabs(piv) > AEPS) Sk = __ddiv_rn(Sk, piv);               // 4244-4245
+      __syncwarp();
+      if (lane == 0) sval[pos] = Sk;
+      __syncwarp();
+      const int U = kl - kdg - 1;
+      const long long base = ks + kdg + 1;
+      for (int c0 = 0; c0 < U && !dead; c0 += 32) {                 // 4247-4254
+        const int e = c0 + lane;
+        const bool have = e < U;
+        const int j = have ? __ldcg(pcols + base + e) : 0x7fffffff;
+        const double v = have ? __ldcg(pvals + base + e) : 0.0;
+        int lo = pos + 1, hi = L;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (scol[mid] < j) lo = mid + 1; else hi = mid; }
+        const bool found = have && lo < L && scol[lo] == j;
+        if (found) sval[lo] = nfms(sval[lo], Sk, v);
+        const unsigned nf = __ballot_sync(FULL, have && !found);
+        if (nf) {
+          const int cnt = __popc(nf), r = __popc(nf & ((1u << lane) - 1u));
+          if (L + cnt > ILUT_CAP) { if (lane == 0) atomicExch(overflow, 2); dead = true; break; }
+          if (have && !found) nip[r] = lo;
+          __syncwarp();
+          for (int hiq = L; hiq > pos + 1; hiq -= 32) {             // make room: tail elements move up by the number of new columns below them
+            const int q = hiq - 1 - lane;
+            const bool in = q >= pos + 1;
+            int cq = 0, sh = 0; double vq = 0.0;
+            if (in) {
+              cq = scol[q]; vq = sval[q];
+              int a = 0, b = cnt;
+              while (a < b) { const int m = (a + b) >> 1; if (nip[m] <= q) a = m + 1; else b = m; }
+              sh = a;
+            }
+            __syncwarp();
+            if (in && sh) { scol[q + sh] = cq; sval[q + sh] = vq; }
+            __syncwarp();
+          }
+          if (have && !found) { scol[lo + r] = j; sval[lo + r] = nfms(0.0, Sk, v); }
+          L += cnt;
+        }
+        __syncwarp();
+      }
+      ++pos;
+    }
+    // ---- 4264-4277: drop rule, the row goes to the pool in column order
+    int K = 0;
+    if (!dead)
+      for (int c0 = 0; c0 < L; c0 += 32) {
+        const int t = c0 + lane;
+        const bool keep = t < L && (fabs(sval[t]) >= thr || scol[t] == i);
+        K += __popc(__ballot_sync(FULL, keep));
+      }
+    unsigned long long off = 0;
+    if (lane == 0 && K) off = atomicAdd(top, (unsigned long long)K);
+    off = __shfl_sync(FULL, off, 0);
+    if (!dead && off + (unsigned long long)K > cap) { if (lane == 0) atomicCAS(overflow, 0, 1); dead = true; }
+    int dg = -1;
+    if (!dead) {
+      int run = 0;
+      for (int c0 = 0; c0 < L; c0 += 32) {
+        const int t = c0 + lane;
+        const bool keep = t < L && (fabs(sval[t]) >= thr || scol[t] == i);
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) {
+          const int w = run + __popc(m & ((1u << lane) - 1u));
+          __stcg(pcols + off + w, scol[t]); __stcg(pvals + off + w, sval[t]);
+          if (scol[t] == i) dg = w;
+        }
+        run += __popc(m);
+      }
+      dg = __reduce_max_sync(FULL, dg);
+    }
+    if (lane == 0) { rstart[i] = (long long)off; rlen[i] = dead ? 0 : K; rdiag[i] = dg; }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(rowdone + i, 1);
+  }
+}
+// pool -> CRS order on the factor's own pattern
+__global__ void k_ilut_gather(int n, const int *__restrict__ orows, const long long *__restrict__ rstart, const int *__restrict__ rdiag, const int *__restrict__ pcols,
+                              const double *__restrict__ pvals, int *__restrict__ ocols, double *__restrict__ ovals, int *__restrict__ odiag) {
+  const int lane = threadIdx.x & 31;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+    const int o = orows[i], len = orows[i + 1] - o;
+    const long long s = rstart[i];
+    for (int t = lane; t < len; t += 32) { ocols[o + t] = pcols[s + t]; ovals[o + t] = pvals[s + t]; }
+    if (lane == 0) odiag[i] = o + rdiag[i];
+  }
+}
+
+static void ilut_factor(Handle &h) {
+  cudaStream_t st = h.stream;
+  const int n = h.n;
+  B200_REQUIRE(h.nranks >= 1, "ILUT: bad handle");
+  B200_CUDA(cudaEventRecord(h.evf0, st));
+  h.ilu_pat_ready = false; h.tri_ready = false;
+  wave_release(h); lane_release(h); ichol_release(h);
+  if (n > 0) {
+    const double *src = h.have_prec ? h.d_prec.p : h.d_vals.p;        // CRSMatrix.F90:4203-4207
+    DBuf<int> pcols, rlen, rdiag, ovf; DBuf<double> pvals; DBuf<long long> rstart; DBuf<unsigned long long> top;
+    rlen.ensure(n); rdiag.ensure(n); rstart.ensure(n); ovf.ensure(1); top.ensure(1);
+    h.d_rowdone.ensure(n);
+    const size_t smem = (size_t)ILUT_WARPS * (ILUT_CAP * (sizeof(int) + sizeof(double)) + 32 * sizeof(int));
+    B200_CUDA(cudaFuncSetAttribute((const void *)k_ilut_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, dev = 0, sms = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k_ilut_factor, ILUT_WARPS * 32, smem));
+    B200_REQUIRE(per_sm > 0, "ILUT: kernel does not fit on an SM");
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = std::max(1, std::min(per_sm * sms, (n + ILUT_WARPS - 1) / ILUT_WARPS));
+    unsigned long long cap = (unsigned long long)std::max<long long>(4 * h.nnz, 4096);
+    int ov = 0;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+      pcols.ensure(cap); pvals.ensure(cap);
+      B200_CUDA(cudaMemsetAsync(h.d_rowdone.p, 0, (size_t)n * sizeof(int), st));
+      B200_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), st));
+      B200_CUDA(cudaMemsetAsync(top.p, 0, sizeof(unsigned long long), st));
+      B200_CUDA(cudaMemsetAsync(&h.ctrl.p->spin_timeout, 0, sizeof(int), st));
+      int N = n; double tol = h.ilut_tol; const int *rows = h.d_rows.p, *cols = h.d_cols.p;
+      int *pc = pcols.p, *rl = rlen.p, *rd = rdiag.p, *done = h.d_rowdone.p, *of = ovf.p; double *pv = pvals.p; long long *rsx = rstart.p;
+      unsigned long long *tp = top.p; Ctrl *ctrl = h.ctrl.p;
+      void *argv[] = {(void *)&N, (void *)&rows, (void *)&cols, (void *)&src, (void *)&tol, (void *)&pc, (void *)&pv, (void *)&cap, (void *)&tp,
+                      (void *)&rsx, (void *)&rl, (void *)&rd, (void *)&done, (void *)&ctrl, (void *)&of};
+      B200_CUDA(cudaLaunchCooperativeKernel((const void *)k_ilut_factor, dim3(blocks), dim3(ILUT_WARPS * 32), argv, smem, st));
+      B200_CUDA(cudaMemcpyAsync(&ov, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaMemcpyAsync(h.h_ctrl, h.ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      B200_REQUIRE(h.h_ctrl->spin_timeout == 0, "ILUT factorisation: dependency wait timed out");
+      B200_REQUIRE(ov != 2, "ILUT: a row of the factor exceeds 1024 entries (tolerance too small for the accelerated path)");
+      if (ov == 0) break;
+      cap *= 4;                                                     // the pool was too small: again with four times the room
+    }
+    B200_REQUIRE(ov == 0, "ILUT: the factor does not fit in the entry pool");
+    // the factor's own pattern: row pointers on the host (the plans are built there), columns / values / diagonal positions gathered on the device
+    std::vector<int> hlen(n), hdg(n);
+    B200_CUDA(cudaMemcpy(hlen.data(), rlen.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(hdg.data(), rdiag.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    h.hl_rows.assign((size_t)n + 1, 0); h.hl_diag.assign(n, 0);
+    long long tot = 0;
+    for (int i = 0; i < n; ++i) {
+      B200_REQUIRE(hdg[i] >= 0, "ILUT: a row of the matrix has no diagonal entry");
+      h.hl_rows[i] = (int)tot; h.hl_diag[i] = (int)tot + hdg[i]; tot += hlen[i];
+      B200_REQUIRE(tot < 2147483647LL, "ILUT: the factor exceeds int32 entries");
+    }
+    h.hl_rows[n] = (int)tot;
+    h.ilu_nnz = tot;
+    h.dl_rows.ensure((size_t)n + 1); h.dl_cols.ensure((size_t)tot); h.dl_diag.ensure(n); h.d_ilu.ensure((size_t)tot);
+    B200_CUDA(cudaMemcpyAsync(h.dl_rows.p, h.hl_rows.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    k_ilut_gather<<<NUM_SMS * 8, 256, 0, st>>>(n, h.dl_rows.p, rstart.p, rdiag.p, pcols.p, pvals.p, h.dl_cols.p, h.d_ilu.p, h.dl_diag.p);
+    B200_CUDA(cudaGetLastError());
+    h.hl_cols.resize((size_t)tot);
+    B200_CUDA(cudaMemcpyAsync(h.hl_cols.data(), h.dl_cols.p, (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    pcols.release(); pvals.release(); rlen.release(); rdiag.release(); rstart.release(); ovf.release(); top.release();
+    h.ilu_pat_ready = true;
+    tri_analyse(h);                                                 // levels and sweep plans of THIS factor's pattern
+    int eb = std::min((n + 255) / 256, NUM_SMS * 8);
+    k_ilu0_invert_diag<<<eb, 256, 0, st>>>(n, h.d_ldiag(), h.d_ilu.p);            // 4323-4329
+    sell_refresh_values(h, h.L, h.d_ilu.p);
+    sell_refresh_values(h, h.U, h.d_ilu.p);
+    if (h.U.nslots) k_gather_diag_slots<<<(h.U.nslots + 255) / 256, 256, 0, st>>>(h.U.nslots, h.U.perm.p, h.d_ldiag(), h.d_ilu.p, h.d_dinv_slot.p);
+    B200_CUDA(cudaGetLastError());
+  }
+  B200_CUDA(cudaEventRecord(h.evf1, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  float ms = 0; B200_CUDA(cudaEventElapsedTime(&ms, h.evf0, h.evf1));
+  h.st_factor_ms = ms;
+  h.ilu_valid = true; h.ilu_exists = true;
+  h.st_factor_launch = n > 0 ? 6 : 0;
+  h.tri_mode = 0;
+}
+
 void ilu0_factor(Handle &h) {
   B200_REQUIRE(h.have_vals, "ILU0 requested before b200_set_values");
+  if (h.ilut) { ilut_factor(h); return; }
   if (h.cholesky) { ichol_factor(h); return; }
   tri_analyse(h);
 
@@ -510,9 +730,6 @@ void ilu0_factor(Handle &h) {
 // flooding L2 with polls.  The counter is only a throttle; correctness rests on the sentinels.
 //   forward  (UPPER = false): out_i = rhs_i - sum_{j<i} L_ij out_j                   (4642-4649)
 //   backward (UPPER = true) : out_i = Dinv_i * (rhs_i - sum_{j>i} U_ij out_j)       (4653-4660)
-__device__ __forceinline__ int ld_relaxed_i(const int *p) {
-  int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
 // Vectors of the solves live in slot (level) order: `out` has one entry per slot, the column ids of
 // T are slot ids.  rhs_idx == nullptr: rhs is in natural order (forward sweep input); otherwise
 // rhs[rhs_idx[slot]] (backward sweep reading the forward result).  nat_out != nullptr: the result is

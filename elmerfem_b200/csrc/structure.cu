@@ -199,6 +199,7 @@ static void ilu1_round(int n, const std::vector<int> &rows, const std::vector<in
 
 void ilu_pattern_build(Handle &h) {
   if (!h.ilu_sep() || h.ilu_pat_ready) return;
+  B200_REQUIRE(!h.ilut, "ILUT: the pattern is installed by the factorisation");
   const int n = h.n;
   std::vector<int> r = h.h_rows, c = h.h_cols, d = h.h_diag, r2, c2, d2;
   if (h.bilu_blocks > 1) {                                 // CRS_BlockDiagonal: keep the entries with MOD(i,Blocks) == MOD(j,Blocks)

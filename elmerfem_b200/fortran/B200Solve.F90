@@ -215,6 +215,7 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   CALL AddReal( 'Linear System Convergence Tolerance' )
   CALL AddReal( 'Linear System Divergence Limit' )
   CALL AddReal( 'Linear System ILU Order' )
+  CALL AddReal( 'Linear System ILUT Tolerance' )
   CALL AddReal( 'SGS Overrelaxation Factor' )
   CALL AddReal( 'Linear System ILU Factor' )
   CALL AddLog( 'Linear System Refactorize' )

@@ -111,6 +111,11 @@ int b200_set_ilu_order(void **handle, const int *order);
  * CRS_LUSolve (4618-4638: row-oriented forward sweep, column-oriented backward sweep).  b200_get_ilu_values then returns the lower part
  * and the diagonal (the reference leaves the upper part of ILUValues unwritten; here it is 0).  Changing the flag drops the factor. */
 int b200_set_symmetric_ilu(void **handle, const int *flag);
+/* ILUT ("Linear System Preconditioning = ILUT", "Linear System ILUT Tolerance"; CRS_ILUT, fem/src/CRSMatrix.F90:4144-4340): incomplete LU
+ * whose pattern is decided by the values -- entry (i,j) of the eliminated row is kept if |value| >= tol * ||A(i,:)||_2, the diagonal always.
+ * flag != 0 selects it (and resets ILU order / BILU), flag == 0 returns to ILU(order).  The factor lives on its own pattern
+ * (b200_get_ilu_structure / b200_get_ilu_values after b200_factorize); rows of more than 1024 entries are refused. */
+int b200_set_ilut(void **handle, const int *flag, const double *tol);
 /* BILU ("Linear System Preconditioning = BILU"): the incomplete factorisation acts on the block-diagonal part of the matrix,
  * entries with MOD(i,blocks) == MOD(j,blocks) (CRS_BlockDiagonal, fem/src/CRSMatrix.F90:2382-2420; IterSolve.F90:745-765), blocks =
  * Solver % Variable % Dofs.  blocks <= 1 switches it off.  Order 0 only through the keyword front-end (see b200_itersolver). */

@@ -405,6 +405,55 @@ int crs_ichol_factor(int N, const int *Rows, const int *Cols, const int *Diag, c
   return 1;
 }
 
+// CRSMatrix.F90:4144-4340 CRS_ILUT / ComputeILUT: incomplete LU with threshold dropping.  Row by row: the row is scattered into full form,
+// eliminated against every flagged column k < i in ascending order (fill-ins of the upper parts of the pivot rows join the flagged set as
+// they appear), then every flagged entry with |S(k)| >= TOL * ||A(i,:)||_2 -- and always the diagonal -- is stored in column order; the
+// diagonal is inverted at the end (4323-4329).  The pattern is an OUTPUT.  Returns the number of stored entries, or -(needed so far) when
+// `cap` entries do not suffice.  1-based contents.
+long crs_ilut(int N, const int *Rows, const int *Cols, const double *Values, double TOL, long cap, int *ILURows, int *ILUCols, int *ILUDiag,
+              double *ILUValues) {
+  std::vector<char> C(N + 2, 0);
+  std::vector<double> S(N + 2, 0.0);
+  ILURows[0] = 1;
+  for (int i = 1; i <= N; ++i) {
+    for (int k = Rows[i - 1]; k <= Rows[i] - 1; ++k) { C[Cols[k - 1]] = 1; S[Cols[k - 1]] = Values[k - 1]; }
+    int RowMin = Cols[Rows[i - 1] - 1], RowMax = Cols[Rows[i] - 2];
+    for (int k = RowMin; k <= i - 1; ++k) {
+      if (C[k]) {
+        const double piv = ILUValues[ILUDiag[k - 1] - 1];
+        if (std::fabs(piv) > AEPS) S[k] = S[k] / piv;
+        for (int l = ILUDiag[k - 1] + 1; l <= ILURows[k] - 1; ++l) {
+          const int j = ILUCols[l - 1];
+          if (!C[j]) { C[j] = 1; RowMax = std::max(RowMax, j); }
+          S[j] = S[j] - S[k] * ILUValues[l - 1];
+        }
+      }
+    }
+    double s2 = 0.0;                                                    // 4262: SQRT( SUM( ABS(Values(row))**2 ) ), summed in order
+    for (int k = Rows[i - 1]; k <= Rows[i] - 1; ++k) { const double a = std::fabs(Values[k - 1]); s2 = s2 + a * a; }
+    const double NORMA = std::sqrt(s2);
+    long j = (long)ILURows[i - 1] - 1;
+    for (int k = RowMin; k <= RowMax; ++k) {
+      if (C[k]) {
+        if (std::fabs(S[k]) >= TOL * NORMA || k == i) {
+          ++j;
+          if (j > cap) return -j;
+          ILUCols[j - 1] = k; ILUValues[j - 1] = S[k];
+          if (k == i) ILUDiag[i - 1] = (int)j;
+        }
+        S[k] = 0.0; C[k] = 0;
+      }
+    }
+    ILURows[i] = (int)(j + 1);
+  }
+  for (int i = 1; i <= N; ++i) {
+    double &d = ILUValues[ILUDiag[i - 1] - 1];
+    if (std::fabs(d) < AEPS) d = 1.0;
+    else d = 1.0 / d;
+  }
+  return (long)ILURows[N] - 1;
+}
+
 // A % Cholesky of the matrix the callbacks below work on ('Linear System Symmetric ILU')
 static int g_cholesky = 0;
 
@@ -1543,6 +1592,10 @@ int orc_crs_ilu0(int n, const int *rows, const int *cols, const int *diag, const
   return crs_ilu0(n, rows, cols, diag, vals, iluvals);
 }
 void orc_set_cholesky(int flag) { g_cholesky = flag; }
+long orc_crs_ilut(int n, const int *rows, const int *cols, const double *vals, double tol, long cap, int *ilurows, int *ilucols, int *iludiag,
+                  double *iluvals) {
+  return crs_ilut(n, rows, cols, vals, tol, cap, ilurows, ilucols, iludiag, iluvals);
+}
 int orc_crs_ichol_factor(int n, const int *rows, const int *cols, const int *diag, const double *vals, const int *ilurows, const int *ilucols,
                          const int *iludiag, double *iluvals) {
   return crs_ichol_factor(n, rows, cols, diag, vals, ilurows, ilucols, iludiag, iluvals);

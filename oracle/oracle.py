@@ -59,6 +59,8 @@ def lib():
     L.orc_optimize_bandwidth.argtypes = [C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, C.c_int]
     L.orc_initialize_matrix.argtypes = [C.c_int, _ip, _ip, C.c_int, C.c_void_p, C.c_void_p, _ip, _ip, _ip]
     L.orc_set_cholesky.argtypes = [C.c_int]
+    L.orc_crs_ilut.restype = C.c_long
+    L.orc_crs_ilut.argtypes = [C.c_int, _ip, _ip, _dp, C.c_double, C.c_long, _ip, _ip, _ip, _dp]
     L.orc_crs_ichol_factor.argtypes = [C.c_int, _ip, _ip, _ip, _dp, _ip, _ip, _ip, _dp]
     L.orc_set_threads.argtypes = [C.c_int]
     L.orc_max_threads.restype = C.c_int
@@ -139,6 +141,17 @@ def ilun(A, order):
     else:
         lib().orc_crs_ilun_factor(A.n, A.rows, A.cols, A.vals, rows, cols, diag, vals)
     return CRS(rows, cols, diag, vals, A.ndeg)
+
+
+def ilut(A, tol):
+    """CRS_ILUT(A, TOL) (CRSMatrix.F90:4144-4340): returns a CRS holding ILURows/ILUCols/ILUDiag/ILUValues (pattern decided by the values)."""
+    cap = max(4 * A.nnz, 1024)
+    while True:
+        r = np.zeros(A.n + 1, dtype=np.int32); c = np.zeros(cap, dtype=np.int32); d = np.zeros(A.n, dtype=np.int32); v = np.zeros(cap)
+        nz = lib().orc_crs_ilut(A.n, A.rows, A.cols, A.vals, float(tol), cap, r, c, d, v)
+        if nz >= 0:
+            return CRS(r, c[:nz].copy(), d, v[:nz].copy(), A.ndeg)
+        cap *= 4
 
 
 def lu_precond(A, ilu, v):

@@ -215,7 +215,7 @@ def test_itersolver_keywords(oracle, heat, heat_gpu):
     assert got is not None and got["info"] == 1 and got["solve_count"] == 1
     assert iters_close(got["iters"], ref["iters"])
     assert rel_l2(got["x"], ref["x"]) <= 1e-7
-    declined = heat_gpu.itersolver(b, None, sif.replace("ILU0", "ILUT"), 0)
+    declined = heat_gpu.itersolver(b, None, sif.replace("ILU0", "Multigrid"), 0)
     assert declined is None
     assert heat_gpu.itersolver(b, None, sif + "\n      Linear System Complex = True\n", 0) is None
 

@@ -107,7 +107,6 @@ def test_the_reference_sif_sections():
 
 @pytest.mark.parametrize("line,why", [
     ("Linear System Complex = True", "complex"),
-    ("Linear System Preconditioning = ILUT", "ILUT"),
     ("Linear System Preconditioning = BILU2", "BILU order"),
     ("Linear System Preconditioning = Multigrid", "multigrid"),
     ("Linear System Preconditioning = vanka", "vanka"),

@@ -35,7 +35,7 @@ Solver 3
   Linear System Solver = Iterative
   Linear System Iterative Method = GCR
   Linear System Max Iterations = 10
-  Linear System Preconditioning = ILUT
+  Linear System Preconditioning = Multigrid
 End
 """
 
