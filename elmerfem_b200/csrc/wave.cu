@@ -326,7 +326,6 @@ void wave_analyse(Handle &h) {
   const char *why = nullptr;
   SkewGeom sg;
   if (h.ilu_sep()) why = "ILU(n > 0) / BILU pattern";
-  else if (h.nranks > 1) why = "partitioned handle";
   else why = sk_detect(h.n, h.h_rows.data(), h.h_cols.data(), h.h_diag.data(), sg);
   if (why) {
     if (getenv("B200_WAVE_DEBUG")) fprintf(stderr, "[wave] not usable (%s): level kernel stays\n", why);
