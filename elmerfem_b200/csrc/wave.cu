@@ -165,9 +165,13 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) +
       double *np = (nat && ln.valid) ? nat + (g.NR - 1) + (long long)g.NR * ((g.NL - 1 - ln.b) + (long long)g.NL * (g.NP - 1 - ln.c)) : nullptr;
       const double *yA = Yr + (w + 1) * YW + (jb + 1), *yB = Yr + w * YW + (jb + 2), *yC = Yr + w * YW + (jb + 1), *yD = Yr + w * YW + jb;
       double *yO = Yr + (w + 1) * YW + (jb + 2);
+      // this thread's column of the stream / right-hand side at the first step of the unrolled group of four: the loads of a step use
+      // compile-time offsets from it (one pointer update per four steps instead of a 64-bit multiply per load)
       const double *gS = S + step0 * (NE * NTHR) + tid, *gR = RHS + step0 * NTHR + tid;
       const int tau0 = ln.tau0;
       const bool valid = ln.valid;
+      double *qrow = qp + (long long)tau0 * NTHR;                    // row of step t0 (first of the group of four) at qrow; a = tau - tau0
+      double *nrow = np ? np + tau0 : nullptr;
       double Am = 0.0, A0 = 0.0, B0 = 0.0, Cm = 0.0, C0 = 0.0, Dm = 0.0, D0 = 0.0, h = 0.0;
       double hi = 0.0, mid = 0.0;                                   // forward: partial rows of steps tau and tau + 1
       double P1[8], P2[6];                                          // backward: products of steps tau (terms 0..7) and tau + 1 (terms 0..5)
@@ -195,26 +199,26 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) +
             {                                                       // chain A of step tau + 3: terms 8..12 (+ inverse diagonal, right-hand side)
               const int st = tau + 3;
               if (valid && (unsigned)(st - tau0) < (unsigned)NR) {
-                const double *src = gS + (long long)st * (NE * NTHR);
+                const double *src = gS + (u + 3) * (NE * NTHR);
 #pragma unroll
                 for (int e = 0; e < 5; ++e) VA[un][e] = ld_stream(src + (8 + e) * NTHR);
-                if (UPPER) { VA[un][5] = ld_stream(src + 13 * NTHR); VA[un][6] = ld_stream(gR + (long long)st * NTHR); }
+                if (UPPER) { VA[un][5] = ld_stream(src + 13 * NTHR); VA[un][6] = ld_stream(gR + (u + 3) * NTHR); }
               }
             }
             {                                                       // chain B of step tau + 4: terms 6, 7
               const int st = tau + 4;
               if (valid && (unsigned)(st - tau0) < (unsigned)NR) {
-                const double *src = gS + (long long)st * (NE * NTHR);
+                const double *src = gS + (u + 4) * (NE * NTHR);
                 VB[un][0] = ld_stream(src + 6 * NTHR); VB[un][1] = ld_stream(src + 7 * NTHR);
               }
             }
             {                                                       // chain C of step tau + 5: terms 0..5 (+ right-hand side)
               const int st = tau + 5;
               if (valid && (unsigned)(st - tau0) < (unsigned)NR) {
-                const double *src = gS + (long long)st * (NE * NTHR);
+                const double *src = gS + (u + 5) * (NE * NTHR);
 #pragma unroll
                 for (int e = 0; e < 6; ++e) VC[un][e] = ld_stream(src + e * NTHR);
-                if (!UPPER) VC[un][6] = ld_stream(gR + (long long)st * NTHR);
+                if (!UPPER) VC[un][6] = ld_stream(gR + (u + 5) * NTHR);
               }
             }
             const int r1 = ((tau - 1) & (WV_RING - 1)) * YSLOT, r3 = ((tau - 3) & (WV_RING - 1)) * YSLOT;
@@ -243,12 +247,13 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) +
             if (acc != acc) acc = __longlong_as_double((long long)CANON_NAN);
             if (!active) acc = 0.0;
             yO[(tau & (WV_RING - 1)) * YSLOT] = acc;
-            if (active) { wv_st_relaxed(qp - (long long)a * NTHR, acc); if (UPPER && np) np[-a] = acc; }
+            if (active) { wv_st_relaxed(qrow - u * NTHR, acc); if (UPPER && np) nrow[-u] = acc; }
             h = acc;
             Am = A0; A0 = An; B0 = Bn; Cm = C0; C0 = Cn; Dm = D0; D0 = Dn;
             wv_bar(NALL);
           }
         }
+        gS += 4 * (NE * NTHR); gR += 4 * NTHR; qrow -= 4 * NTHR; nrow -= 4;
       }
     } else if (tid < NALL) {
       // ---------------- loader thread: halo line hh ----------------
