@@ -41,7 +41,9 @@ def _worker(rank, world, port, out_q, method, precond, kind="heat"):
         if method == "idrs":
             from oracle import oracle as O
             P = np.asfortranarray(O.shadow_space(p["gn"], 4)[p["goffset"][rank]:p["goffset"][rank + 1]])
-        got = M.solve(p["b"], method=method, precond=precond, tol=TOL, maxit=500, bicgstabl_l=4, P=P)
+        if precond == "ilut":                                   # block-Jacobi ILUT of the owned x owned block
+            M.set_ilut(1e-3)
+        got = M.solve(p["b"], method=method, precond="ilu0" if precond == "ilut" else precond, tol=TOL, maxit=500, bicgstabl_l=4, P=P)
         # y = A x through the halo exchange, for a vector every rank can evaluate
         lo, hi = p["goffset"][rank], p["goffset"][rank + 1]
         xg = np.sin(0.37 * np.arange(lo, hi) + 1.0)
@@ -55,7 +57,7 @@ def _worker(rank, world, port, out_q, method, precond, kind="heat"):
 
 @pytest.mark.parametrize("WORLD,method,precond,kind", [(2, "bicgstab", "ilu0", "heat"), (2, "cg", "diagonal", "heat"), (2, "bicgstabl", "ilu0", "heat"),
                                                        (2, "gcr", "none", "heat"), (2, "bicgstabl", "ilu0", "elasticity"), (3, "cg", "diagonal", "heat"),
-                                                       (4, "bicgstab", "ilu0", "heat"), (4, "idrs", "diagonal", "heat")])
+                                                       (2, "gcr", "ilut", "heat"), (4, "bicgstab", "ilu0", "heat"), (4, "idrs", "diagonal", "heat")])
 def test_multi_gpu_parity(oracle, b200, WORLD, method, precond, kind):
     """2 ranks: one neighbour each; 3 and 4 ranks: interior ranks push to / wait on two neighbours (uneven slabs for 3)."""
     import ctypes as C
@@ -101,9 +103,9 @@ def test_multi_gpu_parity(oracle, b200, WORLD, method, precond, kind):
     rowid = np.repeat(np.arange(A.n), np.diff(A.rows))
     Abd = A.copy()
     Abd.vals[block[rowid] != block[A.cols - 1]] = 0.0
-    ilu = oracle.ilu0(Abd) if precond == "ilu0" else None
+    ilu = oracle.ilu0(Abd) if precond == "ilu0" else (oracle.ilut(Abd, 1e-3) if precond == "ilut" else None)
     P = oracle.shadow_space(A.n, 4) if method == "idrs" else None
-    ref = oracle.itersolve(A, rhs, method=method, precond=precond, ilu=ilu, tol=TOL, maxit=500, bicgstabl_l=4, P=P)
+    ref = oracle.itersolve(A, rhs, method=method, precond="ilu0" if precond == "ilut" else precond, ilu=ilu, tol=TOL, maxit=500, bicgstabl_l=4, P=P)
     x = np.concatenate([np.array(r_[2]) for r_ in res])
     infos = {r_[3] for r_ in res}; iters = {r_[4] for r_ in res}
     assert infos == {1} and ref["info"] == 1
