@@ -300,18 +300,25 @@ FUNCTION B200BeforeLinsolve( Model, Solver, A, b, x, n, DOFs, Norm ) RESULT(stat
   END IF
   IF ( rc /= 0 ) CALL Fatal( Caller, 'b200_itersolver failed' )
 
-  ! ---- error mapping of IterSolve.F90:1016-1038
+  ! ---- error mapping of IterSolve.F90:1016-1038, code by code: convergence sets LinConverged = 1; divergence raises NumericalError
+  ! (fatal unless 'Global Abort Not Converged' says otherwise); too many iterations raises it only when 'Linear System Abort Not
+  ! Converged' (default True) asks for it; a halted iteration warns and continues; every other code (breakdowns) just continues.
+  ! Anything but convergence leaves LinConverged = 0.
   Solver % Variable % LinConverged = 0
-  IF ( info(1) == 1 ) Solver % Variable % LinConverged = 1        ! HUTI_CONVERGENCE
-  IF ( info(1) == 3 ) Solver % Variable % LinConverged = 2        ! HUTI_DIVERGENCE
-  IF ( info(1) /= 1 ) THEN
+  IF ( info(1) == 1 ) THEN                                          ! HUTI_CONVERGENCE
+    Solver % Variable % LinConverged = 1
+  ELSE IF ( info(1) == 3 ) THEN                                     ! HUTI_DIVERGENCE
+    CALL NumericalError( Caller, 'System diverged over maximum tolerance.' )
+  ELSE IF ( info(1) == 2 ) THEN                                     ! HUTI_MAXITER
     L = ListGetLogical( Params, 'Linear System Abort Not Converged', Found )
     IF ( .NOT. Found ) L = .TRUE.
     IF ( L ) THEN
-      CALL Fatal( Caller, 'Failed convergence tolerances.' )
+      CALL NumericalError( Caller, 'Too many iterations were needed.' )
     ELSE
-      CALL Warn( Caller, 'Failed convergence tolerances.' )
+      CALL Info( Caller, 'Linear iteration did not converge to tolerance', Level=6 )
     END IF
+  ELSE IF ( info(1) == 4 ) THEN                                     ! HUTI_HALTED
+    CALL Warn( Caller, 'Iteration halted due to problem in algorithm, trying to continue' )
   END IF
   WRITE( Message, '(A,I0,A,I0)' ) 'B200 linear solve: HUTI_INFO=', info(1), ' iterations=', info(2)
   CALL Info( Caller, Message, Level=5 )
