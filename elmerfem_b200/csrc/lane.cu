@@ -118,7 +118,7 @@ __device__ __forceinline__ long long lt_gtime() { long long t; asm volatile("mov
 // per four steps.  [Measured first: a shared-memory ring fed by bulk copies, with a producer warp and a full / empty mbarrier pair per
 // slot -- the consumer's mbarrier test + LDS + arrive cost 265 of 690 cycles per step.]
 constexpr int LT_LEAD = 2;
-template <bool UPPER, int TC, int E, int ABL = 0>   // ABL: timing ablations of profiles/tools/lane_lab.py (wrong results): 1 no entry loads, 2 no row arithmetic, 3 no replay, 4 no stores
+template <bool UPPER, int TC, int E>
 __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restrict__ tile_of, const int *__restrict__ tile_sig, const int *__restrict__ tile_grp,
                                                  const double *__restrict__ S, double *Q, double *R2, Ctrl *ctrl, long long *trace) {
   if (ctrl->done) return;
@@ -172,12 +172,12 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
       // replayed values of step tau + LT_E.  FIRST: a strong (L1-bypassing) load does not issue before the warp's earlier loads have
       // returned (measured: 500-900 cycles behind the 15 streaming loads of a step, 70 when it comes before them)
 #pragma unroll
-      for (int p = 0; p <= TC; ++p) Hh[p][(U + E) % (E + 1)] = (ABL == 3) ? 0.0 : lt_ld_relaxed_if(qp[p] - (U + E) * STRIDE, (unsigned)(ab + U + E - 2 * p) < nrq[p]);
+      for (int p = 0; p <= TC; ++p) Hh[p][(U + E) % (E + 1)] = lt_ld_relaxed_if(qp[p] - (U + E) * STRIDE, (unsigned)(ab + U + E - 2 * p) < nrq[p]);
       // entries of step tau + LT_LEAD (the stream is padded by LT_LEAD steps: no guard at the end of the last tile)
 #pragma unroll
       for (int p = 0; p < TC; ++p)
 #pragma unroll
-        for (int e = 0; e < NROW; ++e) if (ABL != 1) V[(U + LT_LEAD) & 3][p][e] = ld_stream(sp + (U + LT_LEAD) * BLKD + (p * NROW + e) * 32);
+        for (int e = 0; e < NROW; ++e) V[(U + LT_LEAD) & 3][p][e] = ld_stream(sp + (U + LT_LEAD) * BLKD + (p * NROW + e) * 32);
       if ((U & 3) == 0) lt_prefetch_l2_if(sp + (long long)(U + LT_PF) * BLKD, 4u * SLOT, lane == 0 && tau + LT_PF + 4 <= NT);
       if (trace) { const long long c = clock64(); ph[3] += c - pc; pc = c; }
       // the two shuffles
@@ -195,13 +195,13 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
       out[0] = 0.0;
 #pragma unroll
       for (int p = 1; p <= TC; ++p) {
-        double acc = (ABL == 2) ? V[U & 3][p - 1][NE] + V[U & 3][p - 1][0] * h.X[p][(U + 7) & 7] + h.R[p][(U + 7) & 7] + h.T[p - 1][(U + 3) & 7] : lt_row<UPPER, TC, U>(h, p, V[U & 3][p - 1], V[U & 3][p - 1][NE]);
+        double acc = lt_row<UPPER, TC, U>(h, p, V[U & 3][p - 1], V[U & 3][p - 1][NE]);
         if (acc != acc) acc = __longlong_as_double((long long)CANON_NAN);
         const bool active = (unsigned)(ab + U - 2 * p) < nrs[p];
         if (!active) acc = 0.0;
         out[p] = acc;
-        if (ABL != 4) lt_st_relaxed_if(qp[p] - U * STRIDE, acc, active);
-        if (!UPPER && ABL != 4) lt_st_if(rp[p] - U * RSTR, acc, active);
+        lt_st_relaxed_if(qp[p] - U * STRIDE, acc, active);
+        if (!UPPER) lt_st_if(rp[p] - U * RSTR, acc, active);
       }
       if (trace) { const long long c = clock64(); ph[2] += c - pc; pc = c; }
       // replayed values of this step (requested LT_E steps ago; a producer that is not that far ahead yet is polled)
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
       bool need = false;
 #pragma unroll
       for (int p = 0; p <= TC; ++p) { hv[p] = Hh[p][U % (E + 1)]; need = need || lt_is_sentinel(hv[p]); }
-      if (ABL != 3 && __any_sync(FULL, need)) {
+      if (__any_sync(FULL, need)) {
         const long long c0 = trace ? clock64() : 0;
         unsigned tries = 0;
         do {
@@ -302,13 +302,6 @@ void lane_refresh_values(Handle &h) {
 template <bool UPPER, int TC>
 static void lane_launch_tc(Handle &h, const double *S, double *out, double *r2) {
   const void *kern = h.lt_e == 1 ? (const void *)k_lane<UPPER, TC, 1> : (h.lt_e == 7 ? (const void *)k_lane<UPPER, TC, 7> : (const void *)k_lane<UPPER, TC, 3>);
-  if (TC == 1) {                                                     // timing ablations (lane_lab.py); results are wrong by construction
-    static const int abl = getenv("B200_LANE_ABL") ? atoi(getenv("B200_LANE_ABL")) : 0;
-    if (abl == 1) kern = (const void *)k_lane<UPPER, 1, 1, 1>;
-    if (abl == 2) kern = (const void *)k_lane<UPPER, 1, 1, 2>;
-    if (abl == 3) kern = (const void *)k_lane<UPPER, 1, 1, 3>;
-    if (abl == 4) kern = (const void *)k_lane<UPPER, 1, 1, 4>;
-  }
   int dev = 0, sms = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
