@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int NT = g.NT, NR = g.NR, ntiles = g.ntiles, kstep = gridDim.x * W;
   constexpr long long STRIDE = TC * 32, RSTR = TC * LT_ROWS_U * 32;   // distance of consecutive rows of a line: result vector, backward stream
+  constexpr long long RS2 = UPPER ? 1 : RSTR;                        // ... and in the second destination (natural order for the backward sweep)
   long long spins = 0;
   for (int k = blockIdx.x + gridDim.x * wib; k < ntiles; k += kstep) {
     const int sig = tile_sig[k], C = tile_grp[k];
@@ -143,7 +144,10 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
       nrs[p] = (ln.valid && !rep) ? (unsigned)NR : 0u;
       const long long q0 = ln.valid ? lt_pos_mirror(g, tile_of, 0, ln.b, ln.c) : 0;
       qp[p] = Q + q0 + (long long)(2 * lane + 2 * p) * STRIDE;
-      rp[p] = UPPER ? nullptr : R2 + lt_rhs_index(q0, LT_ROWS_U) + (long long)(2 * lane + 2 * p) * RSTR;
+      // second destination of a result: forward sweep -> the right-hand-side row of the backward stream; backward sweep -> the
+      // natural-order vector (row a of the mirrored line at base - a): no conversion pass afterwards
+      if (!UPPER) rp[p] = R2 + lt_rhs_index(q0, LT_ROWS_U) + (long long)(2 * lane + 2 * p) * RSTR;
+      else rp[p] = (R2 && ln.valid) ? R2 + (NR - 1) + (long long)NR * ((g.NL - 1 - ln.b) + (long long)g.NL * (g.NP - 1 - ln.c)) + (2 * lane + 2 * p) : nullptr;
     }
     int ab = -2 * lane;                                             // t0 - 2 lane (t0: first step of the unrolled group of 8)
     const double *sp = S + (long long)k * NT * BLKD + lane;          // the lane's column of the current step's block
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
         if (!active) acc = 0.0;
         out[p] = acc;
         lt_st_relaxed_if(qp[p] - U * STRIDE, acc, active);
-        if (!UPPER) lt_st_if(rp[p] - U * RSTR, acc, active);
+        lt_st_if(rp[p] - U * RS2, acc, active && rp[p] != nullptr);
       }
       if (trace) { const long long c = clock64(); ph[2] += c - pc; pc = c; }
       // replayed values of this step (requested LT_E steps ago; a producer that is not that far ahead yet is polled)
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
 #pragma unroll
       for (int p = 0; p <= TC; ++p) {
         h.X[p][U & 7] = (p == 0 || lane < LT_GH) ? hv[p] : out[p];
-        if (U == 7) { qp[p] -= 8 * STRIDE; if (!UPPER) rp[p] -= 8 * RSTR; }
+        if (U == 7) { qp[p] -= 8 * STRIDE; if (rp[p]) rp[p] -= 8 * RS2; }
       }
       if (U == 7) { ab += 8; sp += 8 * BLKD; }
       if (trace) { const long long c = clock64(); ph[4] += c - pc; pc = c; }
@@ -333,8 +337,10 @@ void lu_apply_lane(Handle &h, double *u, const double *v) {
   if (getenv("B200_LANE_TRACE") && !w.traced && h.st_pcond >= 2) { w.traced = true; lane_trace_enable(h, true); }   // the third application
   k_lane_in<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, v, w.SL.p, w.g.vlen(), w.y.p);
   lane_launch<false>(h, w.SL.p, w.y.p, w.SU.p);
-  lane_launch<true>(h, w.SU.p, w.x.p, nullptr);
-  k_lane_out<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, w.x.p, u);
+  static const bool direct = !(getenv("B200_LANE_OUT") && atoi(getenv("B200_LANE_OUT")) == 1);      // 1: conversion pass k_lane_out
+  lane_launch<true>(h, w.SU.p, w.x.p, direct ? u : nullptr);
+  if (direct) k_lane_sentinel<<<NUM_SMS * 8, 256, 0, h.stream>>>(w.g.vlen(), w.x.p);   // the slots are handed back as sentinels
+  else k_lane_out<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, w.x.p, u);
   B200_CUDA(cudaGetLastError());
   h.st_launch += 4; h.st_pcond++;
   if (w.trace_on) {                                                // diagnostic: one traced application, written as text
