@@ -38,6 +38,37 @@ __global__ void k_lane_in(LaneGeom g, const int *__restrict__ tile_of, int n, co
     SL[lt_rhs_index(lt_pos(g, tile_of, a, b, c), LT_ROWS_L)] = v[i];
   }
 }
+// The same with both sides coalesced: a warp takes 32 consecutive steps of one plane slot of one tile, i.e. for each of the tile's 32 lanes
+// 32 consecutive rows of its line (256 contiguous bytes of the natural-order vector), transposes them through shared memory and writes
+// whole 32-wide rows of the layout (k_lane_in touches one 32-byte sector per 8-byte element on the layout side).
+__global__ void __launch_bounds__(128) k_lane_in2(LaneGeom g, const int *__restrict__ tile_sig, const int *__restrict__ tile_grp, const double *__restrict__ v,
+                                                  double *__restrict__ SL, double *__restrict__ y) {
+  __shared__ double tr[4][32][33];
+  const double sent = __longlong_as_double((long long)SENTINEL);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nch = g.NT / 32 + (g.NT % 32 ? 1 : 0);
+  const long long nwork = (long long)g.ntiles * g.TC * nch, gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long q = gw; q < nwork; q += nwarps) {
+    const int k = (int)(q / ((long long)g.TC * nch)), rem = (int)(q - (long long)k * g.TC * nch), p = rem / nch + 1, t0 = (rem % nch) * 32;
+    const int sig = tile_sig[k], C = tile_grp[k];
+    __syncwarp();
+    for (int j = 0; j < 32; ++j) {                                  // natural -> shared: the warp's lanes are 32 consecutive rows of line j
+      double val = 0.0;
+      if (j >= LT_GH) {
+        const LaneLine ln = lt_line(g, sig, C, j, p);
+        const int a = t0 + lane - 2 * j - 2 * p;
+        if (ln.valid && (unsigned)a < (unsigned)g.NR) val = v[a + (long long)g.NR * (ln.b + (long long)g.NL * ln.c)];
+      }
+      tr[wib][lane][j] = val;
+    }
+    __syncwarp();
+    for (int r = 0; r < 32 && t0 + r < g.NT; ++r) {                 // shared -> layout rows
+      const long long pos = (((long long)k * g.NT + t0 + r) * g.TC + (p - 1)) * 32 + lane;
+      SL[lt_rhs_index(pos, LT_ROWS_L)] = tr[wib][r][lane];
+      y[pos] = sent;
+    }
+  }
+}
 // tile layout -> natural order; the slots are handed back as sentinels for the next application
 __global__ void k_lane_out(LaneGeom g, const int *__restrict__ tile_of, int n, double *__restrict__ x, double *__restrict__ u) {
   const double sent = __longlong_as_double((long long)SENTINEL);
@@ -335,7 +366,9 @@ void lu_apply_lane(Handle &h, double *u, const double *v) {
   LanePlan &w = h.lt;
   const int blocks = std::min((h.n + 255) / 256, NUM_SMS * 8);
   if (getenv("B200_LANE_TRACE") && !w.traced && h.st_pcond >= 2) { w.traced = true; lane_trace_enable(h, true); }   // the third application
-  k_lane_in<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, v, w.SL.p, w.g.vlen(), w.y.p);
+  static const bool conv2 = !(getenv("B200_LANE_CONV") && atoi(getenv("B200_LANE_CONV")) == 1);      // 1: element-wise k_lane_in
+  if (conv2) k_lane_in2<<<NUM_SMS * 12, 128, 0, h.stream>>>(w.g, w.tile_sig.p, w.tile_grp.p, v, w.SL.p, w.y.p);
+  else k_lane_in<<<blocks, 256, 0, h.stream>>>(w.g, w.tile_of.p, h.n, v, w.SL.p, w.g.vlen(), w.y.p);
   lane_launch<false>(h, w.SL.p, w.y.p, w.SU.p);
   static const bool direct = !(getenv("B200_LANE_OUT") && atoi(getenv("B200_LANE_OUT")) == 1);      // 1: conversion pass k_lane_out
   lane_launch<true>(h, w.SU.p, w.x.p, direct ? u : nullptr);
