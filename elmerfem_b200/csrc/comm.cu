@@ -505,6 +505,9 @@ int b200_set_partition(void **handle, const int *gn, const int *n_own, const int
     B200_REQUIRE(goffset[0] == 0 && goffset[np] == *gn, "goffset must run from 0 to gn");
     const int lo = goffset[me], hi = goffset[me + 1];
     B200_REQUIRE(hi - lo == N, "n_own inconsistent with goffset");
+    // per-rank sizes are int32 by the ABI (as Elmer's Matrix_t): the owned rows and THEIR entries must fit, the global system need not
+    // (C3: 2.0e9 global entries, 5.0e8 per rank on 4 ranks); a wrapped-around row pointer is caught here
+    B200_REQUIRE(NNZ >= 0 && (long long)rows[N] - rows[0] == NNZ && NNZ < 2147483647LL, "b200_set_partition: this rank's entries do not fit int32 row pointers (nnz inconsistent with rows)");
     h.gn = *gn; h.index_base = base;
     if (h.halo) { Halo *old = h.halo; h.halo = nullptr; p2p_release(h, *old); old->G.release(); delete old; }
     Halo *Hp = new Halo(); h.halo = Hp; Halo &H = *Hp;
