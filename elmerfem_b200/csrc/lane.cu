@@ -6,12 +6,16 @@
 // critical path of the sweep.  Here a tile is ONE WARP: lane = sheared grid line, TC planes per lane, lanes skewed by two steps, so that
 // every operand of a row is a register of the lane or arrives by one warp shuffle from lane j-1 (lanegeom.h).  A step (= one dependency
 // level of the tile) is a few shuffles, TC x 13 multiply-subtract pairs in the reference's order and TC coalesced stores: no barrier, no
-// shared-memory hand-off.  Only the lines just outside a tile (two ghost lanes, one plane below) come from L2, requested LT_E steps ahead
+// shared-memory hand-off.  Only the lines just outside a tile (two ghost lanes, one plane below) come from L2, requested E steps ahead (template parameter, default 1)
 // with the sentinel protocol; neighbouring tiles run concurrently, a few steps apart.
-// Matrix entries + right-hand sides of a tile step are one contiguous block each; lane 0 of the warp moves them with two bulk copies
-// (cp.async.bulk, mbarrier completion) into a private D-slot shared-memory ring D steps ahead, lane 1 prefetches the stream into L2
-// further ahead.  Arithmetic: the reference's operations in the reference's order, separate roundings; pad entries are (+0) x (+0).
-// Bit-identical to the level kernel and to the CPU loop.
+// Matrix entries + right-hand sides of a tile step are one contiguous block of the sweep's stream; every lane reads ITS column of it
+// straight into registers two steps ahead (coalesced 256-byte warp loads, L1 bypassed) from L2, where lane 0 has put the block with
+// cp.async.bulk.prefetch.L2 LT_PF steps earlier.  [Measured first: a shared-memory ring fed by bulk copies -- by the warp's own lane 0, then
+// by a producer warp with full / empty mbarriers: 3.66 and 2.27 ms per application on the 200^3 problem against 2.02 ms now.]  The strong
+// (L1-bypassing) loads of the replayed values come FIRST in a step: such a load does not issue before the warp's earlier loads have
+// returned.  Arithmetic: the reference's operations in the reference's order, separate roundings; pad entries are (+0) x (+0).
+// Bit-identical to the level kernel and to the CPU loop.  Which of the three kernels runs is decided per structure by timing them
+// (precond.cu, tri_autotune_wave): flat grids go here, cubes to the wave tiles (profiles/r02_sptrsv_modes.txt).
 #include "common.cuh"
 #include "kernels.cuh"
 #include "lanegeom.h"
@@ -83,36 +87,6 @@ __global__ void k_lane_sentinel(long long nv, double *__restrict__ x) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) x[i] = sent;
 }
 
-__device__ __forceinline__ unsigned lt_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void lt_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void lt_mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void lt_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void lt_mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LT_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra LT_DONE;\n"
-      "bra LT_WAIT;\n"
-      "LT_DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ bool lt_mbar_try(unsigned bar, unsigned parity) {     // may suspend for a bounded time
-  unsigned ok;
-  asm volatile("{\n .reg .pred P1;\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n selp.u32 %0, 1, 0, P1;\n }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ bool lt_mbar_test(unsigned bar, unsigned parity) {    // never suspends
-  unsigned ok;
-  asm volatile("{\n .reg .pred P1;\n mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n selp.u32 %0, 1, 0, P1;\n }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void lt_mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void lt_prefetch_l2(const void *p, unsigned bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void lt_prefetch_l2_if(const void *p, unsigned bytes, bool ok) {
   asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q cp.async.bulk.prefetch.L2.global [%0], %1;\n }" ::"l"(p), "r"(bytes), "r"((int)ok) : "memory");
@@ -204,7 +178,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
     auto step = [&](auto Uc, int tau) {
       constexpr int U = decltype(Uc)::value;
       if (trace) pc = clock64();
-      // replayed values of step tau + LT_E.  FIRST: a strong (L1-bypassing) load does not issue before the warp's earlier loads have
+      // replayed values of step tau + E.  FIRST: a strong (L1-bypassing) load does not issue before the warp's earlier loads have
       // returned (measured: 500-900 cycles behind the 15 streaming loads of a step, 70 when it comes before them)
 #pragma unroll
       for (int p = 0; p <= TC; ++p) Hh[p][(U + E) % (E + 1)] = lt_ld_relaxed_if(qp[p] - (U + E) * STRIDE, (unsigned)(ab + U + E - 2 * p) < nrq[p]);
@@ -239,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
         lt_st_if(rp[p] - U * RS2, acc, active && rp[p] != nullptr);
       }
       if (trace) { const long long c = clock64(); ph[2] += c - pc; pc = c; }
-      // replayed values of this step (requested LT_E steps ago; a producer that is not that far ahead yet is polled)
+      // replayed values of this step (requested E steps ago; a producer that is not that far ahead yet is polled)
       double hv[TC + 1];
       bool need = false;
 #pragma unroll

@@ -8,10 +8,11 @@
 // no arithmetic produces, a loader that still finds it polls).  Shearing the line coordinate (beta = b + c) makes the tile DAG acyclic
 // with dependencies only towards smaller (sigma, C), so neighbouring tiles run concurrently, one L2 hop apart, and the critical path
 // holds (number of tile rows + columns) hops instead of one per level.  Matrix entries and right-hand sides of a tile step are
-// contiguous rows of NTHR values; every compute thread streams ITS column of them into an NSLOT-deep shared-memory ring with cp.async
-// (coalesced 256-byte warp requests, thread-private slots: no synchronisation beyond cp.async.wait_group, and steps in which the
-// thread has no row are not fetched at all).  [A TMA bulk-copy ring was measured first: one thread pays ~300 cycles per step for the
-// expect_tx + copy issue and ~260 for the mbarrier wait, more than the whole step otherwise costs.]
+// contiguous rows of NTHR values; every compute thread reads ITS column of them straight into registers three to five steps ahead
+// (coalesced 256-byte warp loads, L1 bypassed) from L2, where a prefetch warp has put the block with cp.async.bulk.prefetch.L2; steps in
+// which the thread has no row are not loaded.  [Measured first and dropped: a TMA bulk-copy ring (one thread pays ~300 cycles per step for
+// the expect_tx + copy issue and ~260 for the mbarrier wait) and a cp.async ring (+240 cycles of LSU issue per step).]  The backward sweep
+// stores its result in natural order as well, so only the way in needs a layout pass (k_wave_in2).
 // Arithmetic: the reference's operations in the reference's order (entries in ascending column order, separate multiply / subtract
 // roundings, inverse diagonal last); pad entries (neighbours outside the grid) are (+0) x (+0).  Bit-identical to the level kernel and
 // to the CPU loop.
