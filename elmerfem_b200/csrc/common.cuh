@@ -104,12 +104,14 @@ struct Halo;   // multi-GPU plan (comm.cu)
 // wave-tile triangular solve (wave.cu, B200_TRI_MODE=3): geometry, tile tables, the two per-step entry streams, work vectors
 struct WavePlan {
   WaveGeom g; DBuf<int> tile_of, tile_sig, tile_grp; DBuf<double> SL, SU, yin, y, x; DBuf<long long> trace;
+  DBuf<int> mapL, mapU;            // per stream entry: position of its value in the ILU array, -1 = pad (built once per structure)
   bool ready = false, tried = false, trace_on = false;
 };
 
 // lane-tile triangular solve (lane.cu, B200_TRI_MODE=4): geometry, tile tables, the two per-step entry streams, work vectors
 struct LanePlan {
   LaneGeom g; DBuf<int> tile_of, tile_sig, tile_grp; DBuf<double> SL, SU, y, x; DBuf<long long> trace;
+  DBuf<int> mapL, mapU;            // as in WavePlan
   bool ready = false, tried = false, trace_on = false, traced = false;
 };
 
@@ -276,6 +278,10 @@ void ilu0_factor(Handle &h);                           // d_ilu from d_prec/d_va
 void lu_apply(Handle &h, double *u, const double *v);  // u = (LU)^-1 v   (device pointers)
 void diag_apply(Handle &h, double *u, const double *v);
 void sgs_sweeps(Handle &h, const double *b, double *x, double *t1, double *t2, double omega);   // one forward + one backward Gauss-Seidel sweep
+// stream refill by gather (structure.cu): S[e] = map[e] >= 0 ? ilu[map[e]] : 0, and the one-time construction of the map from a scatter of indices
+void stream_map_build(Handle &h, long long n, const double *S_with_indices, int *map);
+void stream_gather(Handle &h, long long n, const int *map, const double *ilu, double *S);
+void stream_iota1(Handle &h, long long n, double *a);
 void wave_analyse(Handle &h);                          // wave-tile plan (host detection of the grid stencil; no-op when it does not apply)
 void wave_refresh_values(Handle &h);
 void wave_release(Handle &h);

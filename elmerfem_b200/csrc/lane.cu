@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) k_lane(LaneGeom g, const int *__restri
 // ---- host ------------------------------------------------------------------------------------------------------------------------------
 void lane_release(Handle &h) {
   LanePlan &w = h.lt;
-  w.SL.release(); w.SU.release(); w.y.release(); w.x.release(); w.tile_of.release(); w.tile_sig.release(); w.tile_grp.release(); w.trace.release();
+  w.SL.release(); w.SU.release(); w.y.release(); w.x.release(); w.tile_of.release(); w.tile_sig.release(); w.tile_grp.release(); w.trace.release(); w.mapL.release(); w.mapU.release();
   w.ready = false; w.tried = false;
 }
 
@@ -293,6 +293,16 @@ void lane_analyse(Handle &h) {
   w.SL.ensure((nv + pad) * LT_ROWS_L); w.SU.ensure((nv + pad) * LT_ROWS_U);
   B200_CUDA(cudaMemsetAsync(w.SL.p, 0, (nv + pad) * LT_ROWS_L * sizeof(double), h.stream));
   B200_CUDA(cudaMemsetAsync(w.SU.p, 0, (nv + pad) * LT_ROWS_U * sizeof(double), h.stream));
+  {                                                                 // refill map (structure.cu): the scatter once, on indices
+    DBuf<double> idx; idx.ensure((size_t)h.nnz);
+    stream_iota1(h, h.nnz, idx.p);
+    k_lane_fill<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(g, w.tile_of.p, h.n, h.d_rows.p, h.d_cols.p, idx.p, w.SL.p, w.SU.p);
+    w.mapL.ensure((nv + pad) * LT_ROWS_L); w.mapU.ensure((nv + pad) * LT_ROWS_U);
+    stream_map_build(h, (long long)((nv + pad) * LT_ROWS_L), w.SL.p, w.mapL.p);
+    stream_map_build(h, (long long)((nv + pad) * LT_ROWS_U), w.SU.p, w.mapU.p);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+    idx.release();
+  }
   w.y.ensure(nv); w.x.ensure(nv);
   k_lane_sentinel<<<NUM_SMS * 8, 256, 0, h.stream>>>((long long)nv, w.x.p);
   B200_CUDA(cudaGetLastError());
@@ -304,8 +314,9 @@ void lane_analyse(Handle &h) {
 
 void lane_refresh_values(Handle &h) {
   if (!h.lt.ready || h.n == 0) return;
-  k_lane_fill<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.lt.g, h.lt.tile_of.p, h.n, h.d_rows.p, h.d_cols.p, h.d_ilu.p, h.lt.SL.p, h.lt.SU.p);
-  B200_CUDA(cudaGetLastError());
+  const size_t nv = (size_t)h.lt.g.vlen(), pad = (size_t)4 * h.lt.g.TC * 32;
+  stream_gather(h, (long long)((nv + pad) * LT_ROWS_L), h.lt.mapL.p, h.d_ilu.p, h.lt.SL.p);     // (right-hand-side rows: map -1 -> 0; every application rewrites them)
+  stream_gather(h, (long long)((nv + pad) * LT_ROWS_U), h.lt.mapU.p, h.d_ilu.p, h.lt.SU.p);
 }
 
 template <bool UPPER, int TC>

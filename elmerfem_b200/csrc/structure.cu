@@ -247,6 +247,25 @@ void ilu_invalidate(Handle &h) {
 // b(i) and subtracts L(i, c) b(i) from every b(c) of its lower part.  Unknown c therefore receives its updates from the rows i > c that
 // hold column c, in DESCENDING i, before it is scaled.  ch_ptr / ch_row / ch_pos list exactly that per column (the gather form of the
 // same sums, same order); the dependency levels of the sweep follow from the lists.  Needs the row-level forward plan.
+// The tile kernels' entry streams are refilled after every factorisation.  The row-wise scatter (k_wave_fill / k_lane_fill: 27 scattered
+// 8-byte stores per row) took 11 ms on the 200^3 problem; here the same scatter runs ONCE per structure on an array of indices (entry q
+// holds q + 1), which turns into a map stream entry -> ILU position, and every refill is a coalesced gather through that map.
+__global__ void k_stream_iota1(long long n, double *__restrict__ a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] = (double)(i + 1);
+}
+__global__ void k_stream_map(long long n, const double *__restrict__ S, int *__restrict__ map) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) map[i] = (int)S[i] - 1;
+}
+__global__ void k_stream_gather(long long n, const int *__restrict__ map, const double *__restrict__ ilu, double *__restrict__ S) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int m = map[i];
+    S[i] = m >= 0 ? ilu[m] : 0.0;
+  }
+}
+void stream_iota1(Handle &h, long long n, double *a) { if (n) k_stream_iota1<<<NUM_SMS * 8, 256, 0, h.stream>>>(n, a); B200_CUDA(cudaGetLastError()); }
+void stream_map_build(Handle &h, long long n, const double *S, int *map) { if (n) k_stream_map<<<NUM_SMS * 8, 256, 0, h.stream>>>(n, S, map); B200_CUDA(cudaGetLastError()); }
+void stream_gather(Handle &h, long long n, const int *map, const double *ilu, double *S) { if (n) k_stream_gather<<<NUM_SMS * 8, 256, 0, h.stream>>>(n, map, ilu, S); B200_CUDA(cudaGetLastError()); }
+
 void ichol_release(Handle &h) {
   h.ch_ptr.release(); h.ch_row.release(); h.ch_pos.release(); h.ch_perm.release(); h.ch_gate.release(); h.ch_lvlcnt.release(); h.ch_counters.release();
   h.ch_y.release(); h.ch_x.release(); h.ch_ready = false;

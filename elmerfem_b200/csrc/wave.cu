@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(TB * TC + 32 * ((TB + 2 + 2 * TC + 31) / 32) +
 // ---- host ------------------------------------------------------------------------------------------------------------------------------
 void wave_release(Handle &h) {
   WavePlan &w = h.wv;
-  w.SL.release(); w.SU.release(); w.yin.release(); w.y.release(); w.x.release(); w.tile_of.release(); w.tile_sig.release(); w.tile_grp.release(); w.trace.release();
+  w.SL.release(); w.SU.release(); w.yin.release(); w.y.release(); w.x.release(); w.tile_of.release(); w.tile_sig.release(); w.tile_grp.release(); w.trace.release(); w.mapL.release(); w.mapU.release();
   w.ready = false; w.tried = false;
 }
 
@@ -351,6 +351,16 @@ void wave_analyse(Handle &h) {
   w.SL.ensure(steps * 13 * nthr); w.SU.ensure(steps * 14 * nthr);
   B200_CUDA(cudaMemsetAsync(w.SL.p, 0, steps * 13 * nthr * sizeof(double), h.stream));
   B200_CUDA(cudaMemsetAsync(w.SU.p, 0, steps * 14 * nthr * sizeof(double), h.stream));
+  {                                                                 // refill map (structure.cu): the scatter once, on indices
+    DBuf<double> idx; idx.ensure((size_t)h.nnz);
+    stream_iota1(h, h.nnz, idx.p);
+    k_wave_fill<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(g, w.tile_of.p, h.n, h.d_rows.p, h.d_cols.p, idx.p, w.SL.p, w.SU.p);
+    w.mapL.ensure(steps * 13 * nthr); w.mapU.ensure(steps * 14 * nthr);
+    stream_map_build(h, (long long)(steps * 13 * nthr), w.SL.p, w.mapL.p);
+    stream_map_build(h, (long long)(steps * 14 * nthr), w.SU.p, w.mapU.p);
+    B200_CUDA(cudaStreamSynchronize(h.stream));
+    idx.release();
+  }
   w.yin.ensure(steps * nthr); w.y.ensure(steps * nthr); w.x.ensure(steps * nthr);
   B200_CUDA(cudaMemsetAsync(w.yin.p, 0, steps * nthr * sizeof(double), h.stream));
   k_wave_sentinel<<<NUM_SMS * 8, 256, 0, h.stream>>>((long long)(steps * nthr), w.x.p);
@@ -363,8 +373,9 @@ void wave_analyse(Handle &h) {
 
 void wave_refresh_values(Handle &h) {
   if (!h.wv.ready || h.n == 0) return;
-  k_wave_fill<<<std::min((h.n + 255) / 256, NUM_SMS * 8), 256, 0, h.stream>>>(h.wv.g, h.wv.tile_of.p, h.n, h.d_rows.p, h.d_cols.p, h.d_ilu.p, h.wv.SL.p, h.wv.SU.p);
-  B200_CUDA(cudaGetLastError());
+  const size_t steps = (size_t)h.wv.g.nsteps(), nthr = (size_t)h.wv.g.nthr();
+  stream_gather(h, (long long)(steps * 13 * nthr), h.wv.mapL.p, h.d_ilu.p, h.wv.SL.p);
+  stream_gather(h, (long long)(steps * 14 * nthr), h.wv.mapU.p, h.d_ilu.p, h.wv.SU.p);
 }
 
 template <bool UPPER, int TB, int TC, int E, int PF>
